@@ -1,0 +1,121 @@
+"""TEST INFRASTRUCTURE ONLY -- ctypes wrapper around oracle/billiards_oracle.c.
+
+Importable from ``tests/``, ``__graft_entry__.smoke()`` and ``bench.py``'s
+``cpu_baseline`` / ``--impl reference`` legs; never from the product package.
+"""
+from __future__ import annotations
+
+import ctypes
+import os
+import subprocess
+
+import numpy as np
+
+HERE = os.path.dirname(os.path.abspath(__file__))
+SO_PATH = os.path.join(HERE, "_oracle.so")
+SOURCES = [os.path.join(HERE, "billiards_oracle.c"), os.path.join(HERE, "render_oracle.c")]
+
+_c_dp = ctypes.POINTER(ctypes.c_double)
+_c_ip = ctypes.POINTER(ctypes.c_int32)
+
+
+def build(force: bool = False) -> str:
+    """Compile the C restatement with gcc (no FMA contraction, IEEE fp64)."""
+    srcs = [s for s in SOURCES if os.path.exists(s)]
+    hdr = os.path.join(os.path.dirname(HERE), "pyphy_engine_b200", "csrc", "portable_trig.h")
+    newest = max(os.path.getmtime(p) for p in srcs + [hdr])
+    if force or not os.path.exists(SO_PATH) or os.path.getmtime(SO_PATH) < newest:
+        cmd = ["gcc", "-O2", "-ffp-contract=off", "-fno-fast-math", "-fopenmp", "-fPIC", "-shared",
+               "-Wall", "-o", SO_PATH] + srcs + ["-lm"]
+        subprocess.check_call(cmd)
+    return SO_PATH
+
+
+_lib = None
+
+
+def lib():
+    global _lib
+    if _lib is None:
+        build()
+        _lib = ctypes.CDLL(SO_PATH)
+        _lib.oracle_step_batch.restype = ctypes.c_int64
+        _lib.oracle_trig.restype = ctypes.c_double
+        _lib.oracle_trig.argtypes = [ctypes.c_int, ctypes.c_double, ctypes.c_int]
+    return _lib
+
+
+def _dp(a):
+    return a.ctypes.data_as(_c_dp)
+
+
+def _ip(a):
+    return a.ctypes.data_as(_c_ip)
+
+
+class OracleBatch:
+    """State of ``n_worlds`` independent worlds with a common object layout,
+    stepped by the C restatement of ``Dynamics.step`` (primitives.py:628-656).
+
+    wall: (n_worlds, n_walls, 4, 2) vertices; pos/vel: (n_worlds, n_balls, 2);
+    rad/mass: (n_worlds, n_balls) (rad < 0 marks an empty slot); order: object
+    insertion order, walls numbered 0..n_walls-1 and balls n_walls..; g = (gx, gy).
+    """
+
+    def __init__(self, wall, pos, vel, rad, mass, order=None, dt=0.01, g=(0.0, 0.0), trig_mode=0):
+        f8 = np.float64
+        self.wall = np.ascontiguousarray(wall, f8)
+        self.pos = np.ascontiguousarray(pos, f8).copy()
+        self.vel = np.ascontiguousarray(vel, f8).copy()
+        self.n_worlds, self.n_balls = self.pos.shape[:2]
+        self.n_walls = self.wall.shape[1]
+        assert self.wall.shape == (self.n_worlds, self.n_walls, 4, 2)
+        self.rad = np.ascontiguousarray(np.broadcast_to(rad, (self.n_worlds, self.n_balls)), f8).copy()
+        self.mass = np.ascontiguousarray(np.broadcast_to(mass, (self.n_worlds, self.n_balls)), f8).copy()
+        if order is None:
+            order = np.arange(self.n_walls + self.n_balls)
+        self.order = np.ascontiguousarray(order, np.int32)
+        assert self.order.shape == (self.n_walls + self.n_balls,)
+        self.dt, self.g, self.trig_mode = float(dt), (float(g[0]), float(g[1])), int(trig_mode)
+        nw, nb = self.n_worlds, self.n_balls
+        # Dynamics._include_object, primitives.py:556-563
+        self.tcol = np.zeros((nw, nb), f8)
+        self.fvel = np.zeros((nw, nb, 2), f8)
+        self.nrml = np.zeros((nw, nb, 2), f8)
+        self.partner = np.full((nw, nb), -1, np.int32)
+        self.pending = np.ones((nw,), np.int32)
+        self.status = np.zeros((nw,), np.int32)
+        self.status_step = np.full((nw,), -1, np.int32)
+        self.steps_done = 0
+        self.n_events_total = 0
+
+    def step(self, n_steps=1, record_traj=False, max_events=0, n_threads=1):
+        """Advance every world by ``n_steps`` calls of ``Dynamics.step``.
+
+        Returns (traj or None, events or None); traj is (n_steps, n_worlds,
+        n_balls, 2); events is (k, 4) int32 rows (world, step, ball, partner).
+        """
+        L = lib()
+        traj = np.empty((n_steps, self.n_worlds, self.n_balls, 2), np.float64) if record_traj else None
+        ev = np.zeros((max_events, 4), np.int32) if max_events > 0 else None
+        n = L.oracle_step_batch(
+            ctypes.c_int(self.n_worlds), ctypes.c_int(self.n_balls), ctypes.c_int(self.n_walls),
+            _ip(self.order), _dp(self.pos), _dp(self.vel), _dp(self.rad), _dp(self.mass), _dp(self.wall),
+            _dp(self.tcol), _dp(self.fvel), _dp(self.nrml), _ip(self.partner), _ip(self.pending),
+            _ip(self.status), _ip(self.status_step),
+            ctypes.c_double(self.dt), ctypes.c_double(self.g[0]), ctypes.c_double(self.g[1]),
+            ctypes.c_int(self.steps_done), ctypes.c_int(n_steps),
+            _dp(traj) if traj is not None else None,
+            _ip(ev) if ev is not None else None, ctypes.c_int64(max_events),
+            ctypes.c_int(self.trig_mode), ctypes.c_int(n_threads))
+        self.steps_done += n_steps
+        self.n_events_total += int(n)
+        if ev is not None:
+            if n > max_events:
+                raise RuntimeError("event buffer too small: %d > %d" % (n, max_events))
+            ev = ev[:n]
+        return traj, ev
+
+
+def trig(which: str, x: float, mode: int) -> float:
+    return lib().oracle_trig({"sin": 0, "asin": 1, "acos": 2}[which], float(x), int(mode))
