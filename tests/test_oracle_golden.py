@@ -62,7 +62,7 @@ def test_crowded_prefix_portable_trig():
         ob, traj, ev = run_oracle(case, trig_mode=1, n_steps=12)
         ref = case["events"]
         assert np.array_equal(ev, ref[ref[:, 0] < 12])
-        assert np.max(np.abs(traj - case["traj"][:12])) < 1e-6
+        assert np.max(np.abs(traj - case["traj"][:12])) < 1e-3
 
 
 def test_portable_trig_accuracy():
