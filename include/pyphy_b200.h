@@ -40,6 +40,12 @@ extern "C" {
 
 #define PPB_VERSION 1
 
+#if defined(__GNUC__)
+#define PPB_API __attribute__((visibility("default")))
+#else
+#define PPB_API
+#endif
+
 /* return codes */
 #define PPB_OK 0
 #define PPB_E_INVALID (-1) /* bad argument */
@@ -63,6 +69,7 @@ extern "C" {
 #define PPB_ST_TRAP_AMISS 6      /* dynamics.py:43-45 */
 #define PPB_ST_MATH_DOMAIN 7     /* math.acos / math.asin ValueError, geometry.py:174,444 */
 #define PPB_ST_ASSERT_TCOL_EQ 8  /* primitives.py:664 */
+#define PPB_ST_ITER_LIMIT 9      /* engine guard, see ppb_config.max_substeps */
 
 #define PPB_MAX_BALLS 32 /* ball slots per world */
 #define PPB_MAX_WALLS 16 /* wall slots per world (64 collision edges) */
@@ -77,7 +84,9 @@ typedef struct ppb_config {
   int32_t canvas_w;       /* World(xSz, ySz), primitives.py:857 */
   int32_t canvas_h;
   int32_t device;         /* CUDA device ordinal */
-  int32_t reserved0;
+  int32_t max_substeps;  /* guard on the sub-step loop of one step() (the reference would spin for
+                             minutes or never return); 0 = default 1048576.  A world that exceeds it is
+                             halted with PPB_ST_ITER_LIMIT */
   double dt;              /* Dynamics(deltaT=0.01), primitives.py:536 */
   double gx, gy;          /* Dynamics.g_ (a Point), primitives.py:541, 566 */
   double friction;        /* extension, 0 = reference behaviour */
@@ -108,51 +117,51 @@ typedef struct ppb_wall_style {
   float fill[4];      /* fColor r,g,b,a */
 } ppb_wall_style;
 
-const char *ppb_last_error(void);
-int ppb_version(void);
+PPB_API const char *ppb_last_error(void);
+PPB_API int ppb_version(void);
 
 /* pm.World(...) + pm.Dynamics(world, g, deltaT) for n_worlds worlds
  * (primitives.py:536-563, 857-877).  Allocates the device state. */
-int ppb_create(const ppb_config *cfg, ppb_batch **out);
-int ppb_destroy(ppb_batch *b);
+PPB_API int ppb_create(const ppb_config *cfg, ppb_batch **out);
+PPB_API int ppb_destroy(ppb_batch *b);
 
 /* world.add_object(wall) for every wall slot of worlds [world0, world0+count):
  * `wall` is [count][n_walls][4][2] vertices in Bbox order (primitives.py:224-228,
  * 291-300; geometry.py:471-505). */
-int ppb_set_walls(ppb_batch *b, int32_t world0, int32_t count, const double *wall, void *stream);
+PPB_API int ppb_set_walls(ppb_batch *b, int32_t world0, int32_t count, const double *wall, void *stream);
 
 /* world.add_object(ball) + Dynamics._include_object for every ball slot
  * (primitives.py:556-563, 916-929): pos, vel are [count][n_balls][2]; rad, mass
  * [count][n_balls] (rad < 0 = empty slot).  Resets the collision caches of these
  * worlds (tCol_ = 0, objCol_ = None, all balls queued) and their status. */
-int ppb_set_balls(ppb_batch *b, int32_t world0, int32_t count, const double *pos, const double *vel,
+PPB_API int ppb_set_balls(ppb_batch *b, int32_t world0, int32_t count, const double *pos, const double *vel,
                   const double *rad, const double *mass, void *stream);
 
 /* ball.set_position / ball.set_velocity without touching the caches
  * (primitives.py:462-466); NULL leaves that quantity unchanged. */
-int ppb_update_balls(ppb_batch *b, int32_t world0, int32_t count, const double *pos, const double *vel,
+PPB_API int ppb_update_balls(ppb_batch *b, int32_t world0, int32_t count, const double *pos, const double *vel,
                      void *stream);
 
 /* Dynamics.add_all_dynamic_collision_queue (primitives.py:697-700): every ball of
  * these worlds is rescanned at the start of the next step. */
-int ppb_requeue(ppb_batch *b, int32_t world0, int32_t count, void *stream);
+PPB_API int ppb_requeue(ppb_batch *b, int32_t world0, int32_t count, void *stream);
 
 /* ball.get_position / get_velocity (primitives.py:450-457): [count][n_balls][2] each, may be NULL */
-int ppb_get_balls(ppb_batch *b, int32_t world0, int32_t count, double *pos, double *vel, void *stream);
+PPB_API int ppb_get_balls(ppb_batch *b, int32_t world0, int32_t count, double *pos, double *vel, void *stream);
 
 /* Dynamics.tCol_ / objCol_ (primitives.py:548-549): [count][n_balls]; partner -1 = (None, None) */
-int ppb_get_collision_cache(ppb_batch *b, int32_t world0, int32_t count, double *tcol, int32_t *partner,
+PPB_API int ppb_get_collision_cache(ppb_batch *b, int32_t world0, int32_t count, double *tcol, int32_t *partner,
                             void *stream);
 
 /* per-world outcome and the number of completed steps ([count] each, may be NULL);
  * for a halted world steps_done is the step it raised in */
-int ppb_get_status(ppb_batch *b, int32_t world0, int32_t count, int32_t *status, int32_t *steps_done,
+PPB_API int ppb_get_status(ppb_batch *b, int32_t world0, int32_t count, int32_t *status, int32_t *steps_done,
                    void *stream);
 
 /* Drawing attributes (BallDef / WallDef / GenericWall colours).  Builds the
  * pre-rendered ball sprites (get_ball_im, primitives.py:33-61) on the device for
  * every integer radius in [r_min, r_max]. */
-int ppb_set_styles(ppb_batch *b, const ppb_ball_style *balls /*[n_balls]*/,
+PPB_API int ppb_set_styles(ppb_batch *b, const ppb_ball_style *balls /*[n_balls]*/,
                    const ppb_wall_style *walls /*[n_walls]*/, int32_t r_min, int32_t r_max, void *stream);
 
 /* n_steps x Dynamics.step() (primitives.py:628-656) for every world, asynchronous.
@@ -161,42 +170,44 @@ int ppb_set_styles(ppb_batch *b, const ppb_ball_style *balls /*[n_balls]*/,
  *   frames_dev : NULL or [n_steps / render_every][n_worlds][H][W][4] uint8 --
  *                World.generate_image() after every render_every-th step
  *                (primitives.py:991-1008, dataio.py:119-120)                       */
-int ppb_step_async(ppb_batch *b, int32_t n_steps, void *traj_dev, uint8_t *frames_dev,
+PPB_API int ppb_step_async(ppb_batch *b, int32_t n_steps, void *traj_dev, uint8_t *frames_dev,
                    int32_t render_every, void *stream);
 
 /* World.generate_image() of the current state: [n_worlds][H][W][4] uint8, asynchronous */
-int ppb_render_async(ppb_batch *b, uint8_t *frames_dev, void *stream);
+PPB_API int ppb_render_async(ppb_batch *b, uint8_t *frames_dev, void *stream);
 
 /* Host-buffer convenience used by the reference-facing API (DataSaver.fetch,
  * dataio.py:131-196): runs n_steps with the copies inside the call.
  *   traj_host   : NULL or [n_steps][n_worlds][n_balls][2] float32 (dataio.py:103-104 casts to fp32)
  *   frames_host : NULL or [n_steps / render_every][n_worlds][H][W][4] uint8
  * Host buffers should be page-locked for full copy bandwidth. */
-int ppb_simulate_host(ppb_batch *b, int32_t n_steps, float *traj_host, uint8_t *frames_host,
+PPB_API int ppb_simulate_host(ppb_batch *b, int32_t n_steps, float *traj_host, uint8_t *frames_host,
                       int32_t render_every, void *stream);
 
 /* events recorded since the last ppb_set_balls on world 0 / ppb_clear_events:
  * copies up to `cap` records (unordered across worlds; sort by (world, seq)) and
  * returns the total number produced in *n_total (may exceed event_capacity). */
-int ppb_read_events(ppb_batch *b, ppb_event *out, int64_t cap, int64_t *n_total, void *stream);
-int ppb_clear_events(ppb_batch *b, void *stream);
+PPB_API int ppb_read_events(ppb_batch *b, ppb_event *out, int64_t cap, int64_t *n_total, void *stream);
+PPB_API int ppb_clear_events(ppb_batch *b, void *stream);
 
-/* counters since creation: [0] kernels launched, [1] world-steps advanced by the
- * integrate kernel, [2] world-steps advanced by the collide kernel, [3] events */
-int ppb_get_counters(ppb_batch *b, int64_t out[4], void *stream);
+/* counters since creation: [0] kernels launched by this batch, [1] world-steps taken by the
+ * collide kernel (all other world-steps went through the integrate kernel), [2] sub-step loop
+ * iterations inside the collide kernel, [3] collision events */
+PPB_API int ppb_get_counters(ppb_batch *b, int64_t out[4], void *stream);
 
 /* raw device pointers for zero-copy consumers (e.g. torch via __cuda_array_interface__):
- * which = 0: ball state [n_worlds][n_balls] x {x, y, vx, vy} (batch dtype)
+ * which = 0: positions   [n_worlds][n_balls] x {x, y} (batch dtype)
  *         1: tCol        [n_worlds][n_balls]
  *         2: walls       [n_worlds][n_walls][4][2]
- *         3: radius/mass [n_worlds][n_balls] x {r, m}                              */
-int ppb_device_ptr(ppb_batch *b, int32_t which, void **ptr, int64_t *nbytes);
+ *         3: radius/mass [n_worlds][n_balls] x {r, m}
+ *         4: velocities  [n_worlds][n_balls] x {vx, vy}                             */
+PPB_API int ppb_device_ptr(ppb_batch *b, int32_t which, void **ptr, int64_t *nbytes);
 
 /* time (ms) of the integrate / collide / render kernels summed over the last
  * ppb_step_async call, measured with CUDA events on its stream; valid after the
  * stream has been synchronised.  Enabled by ppb_set_profiling(b, 1). */
-int ppb_set_profiling(ppb_batch *b, int32_t on);
-int ppb_get_kernel_times(ppb_batch *b, float ms[3], int32_t launches[3]);
+PPB_API int ppb_set_profiling(ppb_batch *b, int32_t on);
+PPB_API int ppb_get_kernel_times(ppb_batch *b, float ms[3], int32_t launches[3]);
 
 #ifdef __cplusplus
 }

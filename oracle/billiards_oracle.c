@@ -47,7 +47,8 @@ enum {
   ST_ASSERT_INTPOINT = 5,   /* dynamics.py:34 */
   ST_TRAP_AMISS = 6,        /* dynamics.py:44-45 */
   ST_MATH_DOMAIN = 7,       /* math.acos / math.asin ValueError, geometry.py:174,444 */
-  ST_ASSERT_TCOL_EQ = 8     /* primitives.py:664 */
+  ST_ASSERT_TCOL_EQ = 8,    /* primitives.py:664 */
+  ST_ITER_LIMIT = 9         /* guard shared with the engine (ppb_config.max_substeps) */
 };
 
 typedef struct { double x, y; } pt_t;
@@ -214,6 +215,7 @@ typedef struct {
   int32_t *pending;   /* colQueue_ non-empty: every ball is rescanned at the next loop head */
   int32_t *status, *status_step;
   double dt, gx, gy;
+  int max_substeps;
 } world_t;
 
 /* dynamics.get_toc_ball_wall, dynamics.py:8-63 */
@@ -313,6 +315,7 @@ static void world_step(world_t *w, int world_id, int step_idx, evlog_t *ev) {
   if (*w->status != ST_OK) return;
   int err = 0;
   double tStep = 0;
+  int iters = 0;
   for (;;) {
     if (*w->pending) {                                                            /* :634-638 */
       *w->pending = 0;
@@ -326,6 +329,7 @@ static void world_step(world_t *w, int world_id, int step_idx, evlog_t *ev) {
     double rem = w->dt - tStep;
     double t = (rem < mnt) ? rem : mnt;                                           /* :647 */
     if (t <= 0) break;
+    if (++iters > w->max_substeps) { err = ST_ITER_LIMIT; break; }
     for (int b = 0; b < w->n_balls && !err; ++b) {                                /* :653 */
       if (w->rad[b] < 0) continue;
       if (w->tcol[b] <= t) {                                                      /* :617 */
@@ -370,7 +374,8 @@ int64_t oracle_step_batch(int n_worlds, int n_balls, int n_walls, const int32_t 
                           const double *wall, double *tcol, double *fvel, double *nrml,
                           int32_t *partner, int32_t *pending, int32_t *status, int32_t *status_step,
                           double dt, double gx, double gy, int step0, int n_steps,
-                          double *traj, int32_t *ev_buf, int64_t ev_cap, int trig_mode, int n_threads) {
+                          double *traj, int32_t *ev_buf, int64_t ev_cap, int trig_mode, int n_threads,
+                          int max_substeps) {
   g_trig_mode = trig_mode;
   int64_t n_events = 0;
   /* the event list is ordered (world-major, call order inside a world), so it is
@@ -390,6 +395,7 @@ int64_t oracle_step_batch(int n_worlds, int n_balls, int n_walls, const int32_t 
     w.nrml = nrml + (size_t)wi * n_balls * 2; w.partner = partner + (size_t)wi * n_balls;
     w.pending = pending + wi; w.status = status + wi; w.status_step = status_step + wi;
     w.dt = dt; w.gx = gx; w.gy = gy;
+    w.max_substeps = max_substeps > 0 ? max_substeps : (1 << 20);
     for (int s = 0; s < n_steps; ++s) {
       world_step(&w, wi, step0 + s, &ev);
       if (traj) memcpy(traj + ((size_t)s * n_worlds + wi) * n_balls * 2, w.pos,

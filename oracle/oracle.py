@@ -62,7 +62,8 @@ class OracleBatch:
     insertion order, walls numbered 0..n_walls-1 and balls n_walls..; g = (gx, gy).
     """
 
-    def __init__(self, wall, pos, vel, rad, mass, order=None, dt=0.01, g=(0.0, 0.0), trig_mode=0):
+    def __init__(self, wall, pos, vel, rad, mass, order=None, dt=0.01, g=(0.0, 0.0), trig_mode=0,
+                 max_substeps=0):
         f8 = np.float64
         self.wall = np.ascontiguousarray(wall, f8)
         self.pos = np.ascontiguousarray(pos, f8).copy()
@@ -77,6 +78,7 @@ class OracleBatch:
         self.order = np.ascontiguousarray(order, np.int32)
         assert self.order.shape == (self.n_walls + self.n_balls,)
         self.dt, self.g, self.trig_mode = float(dt), (float(g[0]), float(g[1])), int(trig_mode)
+        self.max_substeps = int(max_substeps)
         nw, nb = self.n_worlds, self.n_balls
         # Dynamics._include_object, primitives.py:556-563
         self.tcol = np.zeros((nw, nb), f8)
@@ -107,7 +109,7 @@ class OracleBatch:
             ctypes.c_int(self.steps_done), ctypes.c_int(n_steps),
             _dp(traj) if traj is not None else None,
             _ip(ev) if ev is not None else None, ctypes.c_int64(max_events),
-            ctypes.c_int(self.trig_mode), ctypes.c_int(n_threads))
+            ctypes.c_int(self.trig_mode), ctypes.c_int(n_threads), ctypes.c_int(self.max_substeps))
         self.steps_done += n_steps
         self.n_events_total += int(n)
         if ev is not None:

@@ -1,0 +1,684 @@
+// ppb_api.cu -- C ABI of the batched billiards engine (include/pyphy_b200.h).
+// Host side only: owns the device state, converts host fp64 arrays to the batch dtype,
+// sequences the K1/K2/K3 launches of a step and the copy pipeline of ppb_simulate_host.
+#include <cuda_runtime.h>
+
+#include <cmath>
+#include <cstdarg>
+#include <cstdio>
+#include <cstring>
+#include <new>
+#include <string>
+#include <vector>
+
+#include "ppb_launch.h"
+
+using namespace ppb;
+
+namespace {
+
+thread_local std::string g_err;
+
+int fail(int code, const char *fmt, ...) {
+  char buf[512];
+  va_list ap;
+  va_start(ap, fmt);
+  vsnprintf(buf, sizeof buf, fmt, ap);
+  va_end(ap);
+  g_err = buf;
+  return code;
+}
+
+#define CU(call)                                                                                  \
+  do {                                                                                            \
+    cudaError_t e_ = (call);                                                                      \
+    if (e_ != cudaSuccess) return fail(PPB_E_CUDA, "%s: %s (%s:%d)", #call, cudaGetErrorString(e_), \
+                                       __FILE__, __LINE__);                                       \
+  } while (0)
+
+inline uint32_t h_color_to_u8(double v) {
+  if (v < 0) v = 0;
+  if (v > 1) v = 1;
+  return ((uint32_t)(v * 65535.0 + 0.5)) >> 8;
+}
+inline uint32_t h_premul_rgba8(const float c[4]) {
+  const double a = c[3];
+  return h_color_to_u8(c[0] * a) | (h_color_to_u8(c[1] * a) << 8) | (h_color_to_u8(c[2] * a) << 16) |
+         (h_color_to_u8(a) << 24);
+}
+
+}  // namespace
+
+struct ppb_batch {
+  ppb_config cfg;
+  Layout L;
+  StatePtrs S;
+  StepParams P;
+  RenderLayout RL;
+  int sm_count = 0;
+  int collide_grid = 1;
+  size_t esz = 4;
+  bool styles_set = false;
+  uint32_t *atlas = nullptr;
+  size_t atlas_bytes = 0;
+  uint32_t *d_fill8 = nullptr, *d_stroke8 = nullptr;
+  int64_t launches = 0;
+  int32_t host_step = 0;  // mirrors *S.step_base
+  // profiling (CUDA events around every kernel of the last ppb_step_async)
+  bool profiling = false;
+  std::vector<cudaEvent_t> ev_pool;
+  std::vector<int> ev_kind;  // kernel kind per (start, stop) pair
+  size_t ev_used = 0;
+  // scratch of ppb_simulate_host
+  void *scr_traj[2] = {nullptr, nullptr};
+  float *scr_traj32[2] = {nullptr, nullptr};
+  uint8_t *scr_frames[2] = {nullptr, nullptr};
+  size_t scr_traj_bytes = 0, scr_frames_bytes = 0;
+  int scr_chunk = 0;
+  cudaStream_t copy_stream = nullptr;
+  cudaEvent_t ev_done[2] = {nullptr, nullptr}, ev_copied[2] = {nullptr, nullptr};
+};
+
+namespace {
+
+bool is64(const ppb_batch *b) { return b->cfg.dtype == PPB_F64; }
+
+int check_range(const ppb_batch *b, int32_t world0, int32_t count) {
+  if (!b) return fail(PPB_E_INVALID, "null batch");
+  if (world0 < 0 || count < 0 || (int64_t)world0 + count > b->cfg.n_worlds)
+    return fail(PPB_E_INVALID, "world range [%d, %d) outside [0, %d)", world0, world0 + count, b->cfg.n_worlds);
+  return PPB_OK;
+}
+
+// host fp64 -> device array of the batch dtype
+int upload(ppb_batch *b, void *dst_base, size_t elem_off, const double *src, size_t n, cudaStream_t st) {
+  if (n == 0) return PPB_OK;
+  if (is64(b)) {
+    CU(cudaMemcpyAsync((char *)dst_base + elem_off * 8, src, n * 8, cudaMemcpyHostToDevice, st));
+    CU(cudaStreamSynchronize(st));
+  } else {
+    std::vector<float> tmp(n);
+    for (size_t i = 0; i < n; ++i) tmp[i] = (float)src[i];
+    CU(cudaMemcpyAsync((char *)dst_base + elem_off * 4, tmp.data(), n * 4, cudaMemcpyHostToDevice, st));
+    CU(cudaStreamSynchronize(st));
+  }
+  return PPB_OK;
+}
+int download(ppb_batch *b, const void *src_base, size_t elem_off, double *dst, size_t n, cudaStream_t st) {
+  if (n == 0) return PPB_OK;
+  if (is64(b)) {
+    CU(cudaMemcpyAsync(dst, (const char *)src_base + elem_off * 8, n * 8, cudaMemcpyDeviceToHost, st));
+    CU(cudaStreamSynchronize(st));
+  } else {
+    std::vector<float> tmp(n);
+    CU(cudaMemcpyAsync(tmp.data(), (const char *)src_base + elem_off * 4, n * 4, cudaMemcpyDeviceToHost, st));
+    CU(cudaStreamSynchronize(st));
+    for (size_t i = 0; i < n; ++i) dst[i] = (double)tmp[i];
+  }
+  return PPB_OK;
+}
+
+cudaError_t do_reset(ppb_batch *b, int world0, int count, int keep, cudaStream_t st) {
+  ++b->launches;
+  return is64(b) ? Launch<double>::reset_cache(b->S, b->cfg.n_balls, world0, count, keep, b->host_step, st)
+                 : Launch<float>::reset_cache(b->S, b->cfg.n_balls, world0, count, keep, b->host_step, st);
+}
+
+struct Prof {
+  ppb_batch *b;
+  cudaStream_t st;
+  int kind;
+  bool on;
+  size_t idx = 0;
+  Prof(ppb_batch *b_, cudaStream_t st_, int kind_) : b(b_), st(st_), kind(kind_), on(b_->profiling) {
+    if (!on) return;
+    if (b->ev_used + 2 > b->ev_pool.size()) {
+      for (int i = 0; i < 2; ++i) {
+        cudaEvent_t e;
+        if (cudaEventCreate(&e) != cudaSuccess) {
+          on = false;
+          return;
+        }
+        b->ev_pool.push_back(e);
+      }
+    }
+    idx = b->ev_used;
+    b->ev_used += 2;
+    b->ev_kind.resize(b->ev_used / 2);
+    b->ev_kind[idx / 2] = kind;
+    cudaEventRecord(b->ev_pool[idx], st);
+  }
+  ~Prof() {
+    if (on) cudaEventRecord(b->ev_pool[idx + 1], st);
+  }
+};
+
+int step_once(ppb_batch *b, int step_off, void *traj, uint8_t *frame, cudaStream_t st) {
+  StepParams P = b->P;
+  P.step_off = step_off;
+  {
+    Prof p(b, st, 0);
+    CU(is64(b) ? Launch<double>::integrate(b->S, b->cfg.n_balls, P, traj, st)
+               : Launch<float>::integrate(b->S, b->cfg.n_balls, P, traj, st));
+    ++b->launches;
+  }
+  {
+    Prof p(b, st, 1);
+    CU(is64(b) ? Launch<double>::collide(b->S, b->L, P, traj, b->collide_grid, st)
+               : Launch<float>::collide(b->S, b->L, P, traj, b->collide_grid, st));
+    ++b->launches;
+  }
+  if (frame) {
+    Prof p(b, st, 2);
+    CU(is64(b) ? Launch<double>::render(b->S, b->L, b->RL, b->atlas, frame, st)
+               : Launch<float>::render(b->S, b->L, b->RL, b->atlas, frame, st));
+    ++b->launches;
+  }
+  return PPB_OK;
+}
+
+void free_scratch(ppb_batch *b) {
+  for (int i = 0; i < 2; ++i) {
+    if (b->scr_traj[i]) cudaFree(b->scr_traj[i]);
+    if (b->scr_traj32[i]) cudaFree(b->scr_traj32[i]);
+    if (b->scr_frames[i]) cudaFree(b->scr_frames[i]);
+    b->scr_traj[i] = nullptr;
+    b->scr_traj32[i] = nullptr;
+    b->scr_frames[i] = nullptr;
+    if (b->ev_done[i]) cudaEventDestroy(b->ev_done[i]);
+    if (b->ev_copied[i]) cudaEventDestroy(b->ev_copied[i]);
+    b->ev_done[i] = b->ev_copied[i] = nullptr;
+  }
+  if (b->copy_stream) cudaStreamDestroy(b->copy_stream);
+  b->copy_stream = nullptr;
+  b->scr_traj_bytes = b->scr_frames_bytes = 0;
+  b->scr_chunk = 0;
+}
+
+}  // namespace
+
+extern "C" {
+
+const char *ppb_last_error(void) { return g_err.c_str(); }
+int ppb_version(void) { return PPB_VERSION; }
+
+int ppb_create(const ppb_config *cfg, ppb_batch **out) {
+  if (!cfg || !out) return fail(PPB_E_INVALID, "null argument");
+  *out = nullptr;
+  if (cfg->n_worlds < 1) return fail(PPB_E_INVALID, "n_worlds must be >= 1");
+  if (cfg->n_balls < 1 || cfg->n_balls > PPB_MAX_BALLS)
+    return fail(PPB_E_INVALID, "n_balls must be in [1, %d]", PPB_MAX_BALLS);
+  if (cfg->n_walls < 0 || cfg->n_walls > PPB_MAX_WALLS)
+    return fail(PPB_E_INVALID, "n_walls must be in [0, %d]", PPB_MAX_WALLS);
+  if (cfg->dtype != PPB_F32 && cfg->dtype != PPB_F64) return fail(PPB_E_INVALID, "dtype must be PPB_F32 or PPB_F64");
+  if (!(cfg->dt > 0)) return fail(PPB_E_INVALID, "dt must be positive");
+  if (cfg->canvas_w < 0 || cfg->canvas_h < 0) return fail(PPB_E_INVALID, "canvas size must be >= 0");
+  if (cfg->event_capacity < 0) return fail(PPB_E_INVALID, "event_capacity must be >= 0");
+  int ndev = 0;
+  if (cudaGetDeviceCount(&ndev) != cudaSuccess || ndev < 1)
+    return fail(PPB_E_CUDA, "no CUDA device available (this library has no CPU fallback)");
+  if (cfg->device < 0 || cfg->device >= ndev) return fail(PPB_E_INVALID, "device %d out of range", cfg->device);
+  CU(cudaSetDevice(cfg->device));
+
+  ppb_batch *b = new (std::nothrow) ppb_batch();
+  if (!b) return fail(PPB_E_NOMEM, "out of host memory");
+  b->cfg = *cfg;
+  b->cfg.order = nullptr;
+  const int nB = cfg->n_balls, nW = cfg->n_walls, nO = nB + nW;
+  memset(&b->L, 0, sizeof b->L);
+  b->L.n_balls = nB;
+  b->L.n_walls = nW;
+  b->L.n_obj = nO;
+  std::vector<int> seen(nO, 0);
+  for (int k = 0; k < nO; ++k) {
+    const int q = cfg->order ? cfg->order[k] : k;
+    if (q < 0 || q >= nO || seen[q]) {
+      delete b;
+      return fail(PPB_E_INVALID, "order must be a permutation of 0..%d", nO - 1);
+    }
+    seen[q] = 1;
+    b->L.order[k] = (int16_t)q;
+    if (q < nW) b->L.rank_wall[q] = (int16_t)k;
+    else b->L.rank_ball[q - nW] = (int16_t)k;
+  }
+  // Dynamics.step walks the dynamic objects in ball insertion order (primitives.py:642, 653);
+  // slot numbers are that order, so ball ranks must be increasing
+  for (int i = 1; i < nB; ++i)
+    if (b->L.rank_ball[i] < b->L.rank_ball[i - 1]) {
+      delete b;
+      return fail(PPB_E_INVALID, "ball slots must appear in increasing order in `order`");
+    }
+  b->P.dt = cfg->dt;
+  b->P.gx = cfg->gx;
+  b->P.gy = cfg->gy;
+  b->P.friction = cfg->friction;
+  b->P.step_off = 0;
+  b->P.max_substeps = cfg->max_substeps > 0 ? cfg->max_substeps : (1 << 20);
+  b->esz = is64(b) ? 8 : 4;
+  CU(cudaDeviceGetAttribute(&b->sm_count, cudaDevAttrMultiProcessorCount, cfg->device));
+
+  const size_t nw = (size_t)cfg->n_worlds, nb = nw * nB;
+  memset(&b->S, 0, sizeof b->S);
+  b->S.n_worlds = cfg->n_worlds;
+  b->S.event_capacity = cfg->event_capacity;
+  struct {
+    void **p;
+    size_t bytes;
+  } allocs[] = {
+      {&b->S.pos, nb * 2 * b->esz},   {&b->S.vel, nb * 2 * b->esz},
+      {&b->S.aux, nb * 4 * b->esz},   {&b->S.tcol, nb * b->esz},
+      {&b->S.rm, nb * 2 * b->esz},    {&b->S.wall, nw * (size_t)(nW > 0 ? nW : 1) * 8 * b->esz},
+      {&b->S.hdr, nw * 16},           {(void **)&b->S.partner, nb * 4},
+      {(void **)&b->S.nev, nw * 4},   {(void **)&b->S.events, (size_t)(cfg->event_capacity > 0 ? cfg->event_capacity : 1) * sizeof(ppb_event)},
+      {(void **)&b->S.counters, 8 * sizeof(unsigned long long)},
+      {(void **)&b->S.step_base, 16},
+  };
+  for (auto &a : allocs) {
+    cudaError_t e = cudaMalloc(a.p, a.bytes ? a.bytes : 16);
+    if (e != cudaSuccess) {
+      ppb_destroy(b);
+      return fail(e == cudaErrorMemoryAllocation ? PPB_E_NOMEM : PPB_E_CUDA, "cudaMalloc(%zu bytes): %s", a.bytes,
+                  cudaGetErrorString(e));
+    }
+    cudaMemset(*a.p, 0, a.bytes ? a.bytes : 16);
+  }
+  // empty worlds: every slot empty (radius -1), caches reset, all balls queued
+  {
+    std::vector<double> rm(nb * 2);
+    for (size_t i = 0; i < nb; ++i) {
+      rm[2 * i] = -1.0;
+      rm[2 * i + 1] = 1.0;
+    }
+    int rc = upload(b, b->S.rm, 0, rm.data(), rm.size(), 0);
+    if (rc != PPB_OK) {
+      ppb_destroy(b);
+      return rc;
+    }
+    cudaError_t e = do_reset(b, 0, cfg->n_worlds, 0, 0);
+    if (e == cudaSuccess) e = cudaDeviceSynchronize();
+    if (e != cudaSuccess) {
+      ppb_destroy(b);
+      return fail(PPB_E_CUDA, "initial reset failed: %s", cudaGetErrorString(e));
+    }
+  }
+  b->collide_grid = is64(b) ? Launch<double>::collide_grid(cfg->n_worlds, b->sm_count)
+                            : Launch<float>::collide_grid(cfg->n_worlds, b->sm_count);
+  memset(&b->RL, 0, sizeof b->RL);
+  b->RL.W = cfg->canvas_w;
+  b->RL.H = cfg->canvas_h;
+  *out = b;
+  return PPB_OK;
+}
+
+int ppb_destroy(ppb_batch *b) {
+  if (!b) return PPB_OK;
+  cudaSetDevice(b->cfg.device);
+  cudaDeviceSynchronize();
+  free_scratch(b);
+  void *ptrs[] = {b->S.pos, b->S.vel, b->S.aux, b->S.tcol, b->S.rm, b->S.wall, b->S.hdr, b->S.partner,
+                  b->S.nev, b->S.events, b->S.counters, b->S.step_base, b->atlas, b->d_fill8, b->d_stroke8};
+  for (void *p : ptrs)
+    if (p) cudaFree(p);
+  for (cudaEvent_t e : b->ev_pool) cudaEventDestroy(e);
+  delete b;
+  return PPB_OK;
+}
+
+int ppb_set_walls(ppb_batch *b, int32_t world0, int32_t count, const double *wall, void *stream) {
+  int rc = check_range(b, world0, count);
+  if (rc) return rc;
+  if (!wall && b->cfg.n_walls > 0) return fail(PPB_E_INVALID, "wall is null");
+  CU(cudaSetDevice(b->cfg.device));
+  const size_t per = (size_t)b->cfg.n_walls * 8;
+  return upload(b, b->S.wall, (size_t)world0 * per, wall, (size_t)count * per, (cudaStream_t)stream);
+}
+
+int ppb_set_balls(ppb_batch *b, int32_t world0, int32_t count, const double *pos, const double *vel,
+                  const double *rad, const double *mass, void *stream) {
+  int rc = check_range(b, world0, count);
+  if (rc) return rc;
+  if (!pos || !vel || !rad || !mass) return fail(PPB_E_INVALID, "null array");
+  CU(cudaSetDevice(b->cfg.device));
+  cudaStream_t st = (cudaStream_t)stream;
+  const size_t nB = (size_t)b->cfg.n_balls, n = (size_t)count * nB, off = (size_t)world0 * nB;
+  // empty slots carry zero velocity and position so that the integrate kernel may stream over them
+  std::vector<double> p(pos, pos + n * 2), v(vel, vel + n * 2), rm(n * 2);
+  for (size_t i = 0; i < n; ++i) {
+    rm[2 * i] = rad[i];
+    rm[2 * i + 1] = mass[i];
+    if (rad[i] < 0) p[2 * i] = p[2 * i + 1] = v[2 * i] = v[2 * i + 1] = 0.0;
+    else if (!(mass[i] > 0)) return fail(PPB_E_INVALID, "mass has to be a positive number");  // primitives.py:588
+  }
+  if ((rc = upload(b, b->S.pos, off * 2, p.data(), n * 2, st))) return rc;
+  if ((rc = upload(b, b->S.vel, off * 2, v.data(), n * 2, st))) return rc;
+  if ((rc = upload(b, b->S.rm, off * 2, rm.data(), n * 2, st))) return rc;
+  CU(do_reset(b, world0, count, 0, st));
+  CU(cudaStreamSynchronize(st));
+  return PPB_OK;
+}
+
+int ppb_update_balls(ppb_batch *b, int32_t world0, int32_t count, const double *pos, const double *vel,
+                     void *stream) {
+  int rc = check_range(b, world0, count);
+  if (rc) return rc;
+  CU(cudaSetDevice(b->cfg.device));
+  cudaStream_t st = (cudaStream_t)stream;
+  const size_t nB = (size_t)b->cfg.n_balls, n = (size_t)count * nB, off = (size_t)world0 * nB;
+  if (pos && (rc = upload(b, b->S.pos, off * 2, pos, n * 2, st))) return rc;
+  if (vel && (rc = upload(b, b->S.vel, off * 2, vel, n * 2, st))) return rc;
+  return PPB_OK;
+}
+
+int ppb_requeue(ppb_batch *b, int32_t world0, int32_t count, void *stream) {
+  int rc = check_range(b, world0, count);
+  if (rc) return rc;
+  CU(cudaSetDevice(b->cfg.device));
+  CU(do_reset(b, world0, count, 1, (cudaStream_t)stream));
+  CU(cudaStreamSynchronize((cudaStream_t)stream));
+  return PPB_OK;
+}
+
+int ppb_get_balls(ppb_batch *b, int32_t world0, int32_t count, double *pos, double *vel, void *stream) {
+  int rc = check_range(b, world0, count);
+  if (rc) return rc;
+  CU(cudaSetDevice(b->cfg.device));
+  cudaStream_t st = (cudaStream_t)stream;
+  const size_t nB = (size_t)b->cfg.n_balls, n = (size_t)count * nB, off = (size_t)world0 * nB;
+  if (pos && (rc = download(b, b->S.pos, off * 2, pos, n * 2, st))) return rc;
+  if (vel && (rc = download(b, b->S.vel, off * 2, vel, n * 2, st))) return rc;
+  return PPB_OK;
+}
+
+int ppb_get_collision_cache(ppb_batch *b, int32_t world0, int32_t count, double *tcol, int32_t *partner,
+                            void *stream) {
+  int rc = check_range(b, world0, count);
+  if (rc) return rc;
+  CU(cudaSetDevice(b->cfg.device));
+  cudaStream_t st = (cudaStream_t)stream;
+  const size_t nB = (size_t)b->cfg.n_balls, n = (size_t)count * nB, off = (size_t)world0 * nB;
+  if (tcol && (rc = download(b, b->S.tcol, off, tcol, n, st))) return rc;
+  if (partner) {
+    CU(cudaMemcpyAsync(partner, b->S.partner + off, n * 4, cudaMemcpyDeviceToHost, st));
+    CU(cudaStreamSynchronize(st));
+  }
+  return PPB_OK;
+}
+
+int ppb_get_status(ppb_batch *b, int32_t world0, int32_t count, int32_t *status, int32_t *steps_done, void *stream) {
+  int rc = check_range(b, world0, count);
+  if (rc) return rc;
+  CU(cudaSetDevice(b->cfg.device));
+  cudaStream_t st = (cudaStream_t)stream;
+  std::vector<uint32_t> raw((size_t)count * 4);
+  CU(cudaMemcpyAsync(raw.data(), (char *)b->S.hdr + (size_t)world0 * 16, (size_t)count * 16, cudaMemcpyDeviceToHost, st));
+  CU(cudaStreamSynchronize(st));
+  for (int i = 0; i < count; ++i) {
+    // Hdr<float>: tmin, step, flags, pad      Hdr<double>: tmin(2 words), step, flags
+    const uint32_t step = is64(b) ? raw[4 * i + 2] : raw[4 * i + 1];
+    const uint32_t flags = is64(b) ? raw[4 * i + 3] : raw[4 * i + 2];
+    if (status) status[i] = (int32_t)((flags >> 8) & 0xffu);
+    if (steps_done) steps_done[i] = (int32_t)step;
+  }
+  return PPB_OK;
+}
+
+int ppb_set_styles(ppb_batch *b, const ppb_ball_style *balls, const ppb_wall_style *walls, int32_t r_min,
+                   int32_t r_max, void *stream) {
+  if (!b || !balls || (!walls && b->cfg.n_walls > 0)) return fail(PPB_E_INVALID, "null argument");
+  if (r_min < 0 || r_max < r_min || r_max > 4096) return fail(PPB_E_INVALID, "bad radius range [%d, %d]", r_min, r_max);
+  CU(cudaSetDevice(b->cfg.device));
+  cudaStream_t st = (cudaStream_t)stream;
+  const int nB = b->cfg.n_balls, nW = b->cfg.n_walls;
+  b->RL.r_min = r_min;
+  b->RL.r_max = r_max;
+  int max_st = 0;
+  std::vector<uint32_t> fill8(nB), stroke8(nB);
+  for (int i = 0; i < nB; ++i) {
+    if (balls[i].s_thick < 0 || balls[i].s_thick > 1024) return fail(PPB_E_INVALID, "bad s_thick");
+    b->RL.s_thick[i] = balls[i].s_thick;
+    if (balls[i].s_thick > max_st) max_st = balls[i].s_thick;
+    fill8[i] = h_premul_rgba8(balls[i].fill);
+    stroke8[i] = h_premul_rgba8(balls[i].stroke);
+  }
+  for (int q = 0; q < nW; ++q) {
+    b->RL.wall[q].kind = walls[q].kind;
+    b->RL.wall[q].rgba8 = h_premul_rgba8(walls[q].fill);
+  }
+  const size_t max_sz = (size_t)2 * (r_max + max_st);
+  const size_t sprite_bytes = ((max_sz * max_sz * 4 + 15) / 16) * 16;
+  const size_t nr = (size_t)(r_max - r_min + 1);
+  b->RL.sprite_stride = (int32_t)sprite_bytes;
+  b->RL.sprite_slot_stride = (int32_t)(sprite_bytes * nr);
+  const size_t need = sprite_bytes * nr * nB;
+  if (need > ((size_t)1 << 31)) return fail(PPB_E_INVALID, "sprite atlas too large");
+  if (need > b->atlas_bytes) {
+    if (b->atlas) cudaFree(b->atlas);
+    b->atlas = nullptr;
+    CU(cudaMalloc((void **)&b->atlas, need));
+    b->atlas_bytes = need;
+  }
+  if (!b->d_fill8) CU(cudaMalloc((void **)&b->d_fill8, PPB_MAX_BALLS * 4));
+  if (!b->d_stroke8) CU(cudaMalloc((void **)&b->d_stroke8, PPB_MAX_BALLS * 4));
+  CU(cudaMemsetAsync(b->atlas, 0, need, st));
+  CU(cudaMemcpyAsync(b->d_fill8, fill8.data(), nB * 4, cudaMemcpyHostToDevice, st));
+  CU(cudaMemcpyAsync(b->d_stroke8, stroke8.data(), nB * 4, cudaMemcpyHostToDevice, st));
+  CU(launch_build_sprites(b->atlas, b->RL, nB, b->d_fill8, b->d_stroke8, st));
+  ++b->launches;
+  CU(cudaStreamSynchronize(st));
+  b->styles_set = true;
+  return PPB_OK;
+}
+
+int ppb_step_async(ppb_batch *b, int32_t n_steps, void *traj_dev, uint8_t *frames_dev, int32_t render_every,
+                   void *stream) {
+  if (!b) return fail(PPB_E_INVALID, "null batch");
+  if (n_steps < 0) return fail(PPB_E_INVALID, "n_steps must be >= 0");
+  if (frames_dev) {
+    if (!b->styles_set) return fail(PPB_E_STATE, "ppb_set_styles must be called before rendering");
+    if (render_every < 1) return fail(PPB_E_INVALID, "render_every must be >= 1");
+    if (b->RL.W < 1 || b->RL.H < 1) return fail(PPB_E_STATE, "batch was created without a canvas");
+  }
+  CU(cudaSetDevice(b->cfg.device));
+  cudaStream_t st = (cudaStream_t)stream;
+  b->ev_used = 0;
+  const size_t frame_bytes = (size_t)b->cfg.n_worlds * b->RL.W * b->RL.H * 4;
+  for (int s = 0; s < n_steps; ++s) {
+    uint8_t *frame = nullptr;
+    if (frames_dev && ((s + 1) % render_every) == 0) frame = frames_dev + (size_t)((s + 1) / render_every - 1) * frame_bytes;
+    int rc = step_once(b, s, traj_dev, frame, st);
+    if (rc) return rc;
+  }
+  if (n_steps > 0) {
+    CU(launch_advance_step_base(b->S.step_base, n_steps, st));
+    ++b->launches;
+    b->host_step += n_steps;
+  }
+  return PPB_OK;
+}
+
+int ppb_render_async(ppb_batch *b, uint8_t *frames_dev, void *stream) {
+  if (!b || !frames_dev) return fail(PPB_E_INVALID, "null argument");
+  if (!b->styles_set) return fail(PPB_E_STATE, "ppb_set_styles must be called before rendering");
+  if (b->RL.W < 1 || b->RL.H < 1) return fail(PPB_E_STATE, "batch was created without a canvas");
+  CU(cudaSetDevice(b->cfg.device));
+  cudaStream_t st = (cudaStream_t)stream;
+  b->ev_used = 0;
+  {
+    Prof p(b, st, 2);
+    CU(is64(b) ? Launch<double>::render(b->S, b->L, b->RL, b->atlas, frames_dev, st)
+               : Launch<float>::render(b->S, b->L, b->RL, b->atlas, frames_dev, st));
+    ++b->launches;
+  }
+  return PPB_OK;
+}
+
+int ppb_simulate_host(ppb_batch *b, int32_t n_steps, float *traj_host, uint8_t *frames_host, int32_t render_every,
+                      void *stream) {
+  if (!b) return fail(PPB_E_INVALID, "null batch");
+  if (n_steps < 0) return fail(PPB_E_INVALID, "n_steps must be >= 0");
+  if (frames_host) {
+    if (!b->styles_set) return fail(PPB_E_STATE, "ppb_set_styles must be called before rendering");
+    if (render_every < 1) return fail(PPB_E_INVALID, "render_every must be >= 1");
+  } else {
+    render_every = 1;
+  }
+  CU(cudaSetDevice(b->cfg.device));
+  cudaStream_t st = (cudaStream_t)stream;
+  const size_t nW = (size_t)b->cfg.n_worlds, nB = (size_t)b->cfg.n_balls;
+  const size_t frame_bytes = nW * b->RL.W * b->RL.H * 4;
+  const size_t traj_elems = nW * nB * 2;  // per step
+  // chunk = a whole number of render periods, bounded so that the two device staging buffers
+  // stay below ~1 GiB each (but at least one period)
+  int chunk = render_every;
+  {
+    const size_t per_step = (traj_host ? traj_elems * (b->esz + 4) : 0);
+    const size_t per_period = per_step * render_every + (frames_host ? frame_bytes : 0);
+    size_t periods = per_period ? ((size_t)1 << 30) / per_period : 64;
+    if (periods < 1) periods = 1;
+    if (periods > 64) periods = 64;
+    chunk = (int)(periods * render_every);
+  }
+  const size_t need_traj = traj_host ? traj_elems * chunk * b->esz : 0;
+  const size_t need_frames = frames_host ? frame_bytes * (chunk / render_every) : 0;
+  if (chunk != b->scr_chunk || need_traj > b->scr_traj_bytes || need_frames > b->scr_frames_bytes) {
+    CU(cudaDeviceSynchronize());
+    free_scratch(b);
+    for (int i = 0; i < 2; ++i) {
+      if (need_traj) {
+        CU(cudaMalloc(&b->scr_traj[i], need_traj));
+        if (is64(b)) CU(cudaMalloc((void **)&b->scr_traj32[i], need_traj / 2));
+      }
+      if (need_frames) CU(cudaMalloc((void **)&b->scr_frames[i], need_frames));
+      CU(cudaEventCreateWithFlags(&b->ev_done[i], cudaEventDisableTiming));
+      CU(cudaEventCreateWithFlags(&b->ev_copied[i], cudaEventDisableTiming));
+    }
+    CU(cudaStreamCreateWithFlags(&b->copy_stream, cudaStreamNonBlocking));
+    b->scr_traj_bytes = need_traj;
+    b->scr_frames_bytes = need_frames;
+    b->scr_chunk = chunk;
+  }
+  b->ev_used = 0;
+  int done = 0, it = 0;
+  while (done < n_steps) {
+    const int cur = (n_steps - done < chunk) ? (n_steps - done) : chunk;
+    const int buf = it & 1;
+    if (it >= 2) CU(cudaStreamWaitEvent(st, b->ev_copied[buf], 0));  // staging buffer free again
+    for (int s = 0; s < cur; ++s) {
+      uint8_t *frame = nullptr;
+      const int gs = done + s;
+      if (frames_host && ((gs + 1) % render_every) == 0)
+        frame = b->scr_frames[buf] + (size_t)((s + 1) / render_every - 1) * frame_bytes;
+      int rc = step_once(b, s, traj_host ? b->scr_traj[buf] : nullptr, frame, st);
+      if (rc) return rc;
+    }
+    CU(launch_advance_step_base(b->S.step_base, cur, st));
+    ++b->launches;
+    b->host_step += cur;
+    const float *src32 = (const float *)b->scr_traj[buf];
+    if (traj_host && is64(b)) {
+      CU(Launch<double>::traj_to_f32(b->scr_traj[buf], b->scr_traj32[buf], (long long)traj_elems * cur, st));
+      ++b->launches;
+      src32 = b->scr_traj32[buf];
+    }
+    CU(cudaEventRecord(b->ev_done[buf], st));
+    CU(cudaStreamWaitEvent(b->copy_stream, b->ev_done[buf], 0));
+    if (traj_host)
+      CU(cudaMemcpyAsync(traj_host + (size_t)done * traj_elems, src32, traj_elems * cur * 4, cudaMemcpyDeviceToHost,
+                         b->copy_stream));
+    if (frames_host) {
+      const int f0 = done / render_every, nf = (done + cur) / render_every - f0;
+      if (nf > 0)
+        CU(cudaMemcpyAsync(frames_host + (size_t)f0 * frame_bytes, b->scr_frames[buf], frame_bytes * nf,
+                           cudaMemcpyDeviceToHost, b->copy_stream));
+    }
+    CU(cudaEventRecord(b->ev_copied[buf], b->copy_stream));
+    done += cur;
+    ++it;
+  }
+  CU(cudaStreamSynchronize(st));
+  CU(cudaStreamSynchronize(b->copy_stream));
+  return PPB_OK;
+}
+
+int ppb_read_events(ppb_batch *b, ppb_event *out, int64_t cap, int64_t *n_total, void *stream) {
+  if (!b) return fail(PPB_E_INVALID, "null batch");
+  CU(cudaSetDevice(b->cfg.device));
+  cudaStream_t st = (cudaStream_t)stream;
+  unsigned long long n = 0;
+  CU(cudaMemcpyAsync(&n, b->S.counters, sizeof n, cudaMemcpyDeviceToHost, st));
+  CU(cudaStreamSynchronize(st));
+  if (n_total) *n_total = (int64_t)n;
+  int64_t m = (int64_t)n;
+  if (m > b->cfg.event_capacity) m = b->cfg.event_capacity;
+  if (m > cap) m = cap;
+  if (out && m > 0) {
+    CU(cudaMemcpyAsync(out, b->S.events, (size_t)m * sizeof(ppb_event), cudaMemcpyDeviceToHost, st));
+    CU(cudaStreamSynchronize(st));
+  }
+  return PPB_OK;
+}
+
+int ppb_clear_events(ppb_batch *b, void *stream) {
+  if (!b) return fail(PPB_E_INVALID, "null batch");
+  CU(cudaSetDevice(b->cfg.device));
+  CU(cudaMemsetAsync(b->S.counters, 0, sizeof(unsigned long long), (cudaStream_t)stream));
+  CU(cudaStreamSynchronize((cudaStream_t)stream));
+  return PPB_OK;
+}
+
+int ppb_get_counters(ppb_batch *b, int64_t out[4], void *stream) {
+  if (!b || !out) return fail(PPB_E_INVALID, "null argument");
+  CU(cudaSetDevice(b->cfg.device));
+  unsigned long long c[4];
+  CU(cudaMemcpyAsync(c, b->S.counters, sizeof c, cudaMemcpyDeviceToHost, (cudaStream_t)stream));
+  CU(cudaStreamSynchronize((cudaStream_t)stream));
+  out[0] = b->launches;
+  out[1] = (int64_t)c[1];
+  out[2] = (int64_t)c[2];
+  out[3] = (int64_t)c[0];
+  return PPB_OK;
+}
+
+int ppb_device_ptr(ppb_batch *b, int32_t which, void **ptr, int64_t *nbytes) {
+  if (!b || !ptr) return fail(PPB_E_INVALID, "null argument");
+  const size_t nb = (size_t)b->cfg.n_worlds * b->cfg.n_balls;
+  void *p = nullptr;
+  size_t n = 0;
+  switch (which) {
+    case 0: p = b->S.pos; n = nb * 2 * b->esz; break;
+    case 1: p = b->S.tcol; n = nb * b->esz; break;
+    case 2: p = b->S.wall; n = (size_t)b->cfg.n_worlds * b->cfg.n_walls * 8 * b->esz; break;
+    case 3: p = b->S.rm; n = nb * 2 * b->esz; break;
+    case 4: p = b->S.vel; n = nb * 2 * b->esz; break;
+    default: return fail(PPB_E_INVALID, "unknown buffer id %d", which);
+  }
+  *ptr = p;
+  if (nbytes) *nbytes = (int64_t)n;
+  return PPB_OK;
+}
+
+int ppb_set_profiling(ppb_batch *b, int32_t on) {
+  if (!b) return fail(PPB_E_INVALID, "null batch");
+  b->profiling = on != 0;
+  b->ev_used = 0;
+  return PPB_OK;
+}
+
+int ppb_get_kernel_times(ppb_batch *b, float ms[3], int32_t launches[3]) {
+  if (!b || !ms || !launches) return fail(PPB_E_INVALID, "null argument");
+  for (int i = 0; i < 3; ++i) {
+    ms[i] = 0.f;
+    launches[i] = 0;
+  }
+  for (size_t i = 0; i + 1 < b->ev_used; i += 2) {
+    float t = 0.f;
+    CU(cudaEventSynchronize(b->ev_pool[i + 1]));
+    CU(cudaEventElapsedTime(&t, b->ev_pool[i], b->ev_pool[i + 1]));
+    const int kind = b->ev_kind[i / 2];
+    ms[kind] += t;
+    launches[kind] += 1;
+  }
+  return PPB_OK;
+}
+
+}  // extern "C"

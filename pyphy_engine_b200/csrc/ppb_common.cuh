@@ -101,6 +101,7 @@ struct __align__(16) Hdr<double> {
   uint32_t flags;
 };
 #define PPB_FLAG_PENDING 1u
+
 #define PPB_STATUS_OF(flags) (((flags) >> 8) & 0xffu)
 
 // layout shared by all worlds of a batch (kernel parameter, lives in constant bank)
@@ -114,7 +115,8 @@ struct Layout {
 
 // device state of a batch (raw pointers; T-typed views are made in the kernels)
 struct StatePtrs {
-  void *pv;        // [n_worlds][n_balls] {x,y,vx,vy}
+  void *pos;       // [n_worlds][n_balls] {x, y}
+  void *vel;       // [n_worlds][n_balls] {vx, vy}
   void *aux;       // [n_worlds][n_balls] {nrmlCol.x, nrmlCol.y, futureVel.x, futureVel.y}
   void *tcol;      // [n_worlds][n_balls]
   void *rm;        // [n_worlds][n_balls] {radius, mass}
@@ -123,7 +125,7 @@ struct StatePtrs {
   int32_t *partner;   // [n_worlds][n_balls]
   uint32_t *nev;      // [n_worlds] events emitted so far (sequence numbers)
   ppb_event *events;  // [event_capacity]
-  unsigned long long *counters;  // [0] events produced [1] integrate world-steps [2] collide world-steps
+  unsigned long long *counters;  // [0] events produced [1] collide world-steps [2] collide loop iterations [3] rescans
   int32_t *step_base;            // device scalar: step index of the first step of the running launch group
   long long event_capacity;
   int32_t n_worlds;
@@ -132,6 +134,7 @@ struct StatePtrs {
 struct StepParams {
   double dt, gx, gy, friction;
   int32_t step_off;   // this launch advances step (*step_base + step_off)
+  int32_t max_substeps;
 };
 
 // ---- render ----

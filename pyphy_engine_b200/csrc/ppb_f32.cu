@@ -1,0 +1,23 @@
+// fp32 throughput kernels (FMA contraction allowed)
+#include "ppb_launch_impl.cuh"
+namespace ppb {
+template struct Launch<float>;
+
+cudaError_t launch_advance_step_base(int32_t *step_base, int32_t n, cudaStream_t st) {
+  advance_step_base_kernel<<<1, 1, 0, st>>>(step_base, n);
+  return cudaGetLastError();
+}
+cudaError_t launch_build_sprites(uint32_t *atlas, const RenderLayout &RL, int n_balls, const uint32_t *fill8,
+                                 const uint32_t *stroke8, cudaStream_t st) {
+  const int nr = RL.r_max - RL.r_min + 1;
+  int max_sz = 0;
+  for (int b = 0; b < n_balls; ++b) {
+    const int sz = 2 * (RL.r_max + RL.s_thick[b]);
+    if (sz > max_sz) max_sz = sz;
+  }
+  if (nr <= 0 || max_sz <= 0) return cudaSuccess;
+  dim3 grid((max_sz * max_sz + 127) / 128, n_balls, nr);
+  build_ball_sprites_kernel<<<grid, 128, 0, st>>>(atlas, RL, n_balls, fill8, stroke8);
+  return cudaGetLastError();
+}
+}  // namespace ppb

@@ -1,0 +1,28 @@
+// ppb_launch.h -- host-callable launchers, one explicit instantiation per arithmetic
+// (ppb_f32.cu is compiled with FMA contraction, ppb_f64.cu with -fmad=false).
+#pragma once
+#include "ppb_common.cuh"
+
+namespace ppb {
+
+template <typename T>
+struct Launch {
+  static size_t elem_size() { return sizeof(T); }
+  static size_t hdr_size();
+  static cudaError_t integrate(const StatePtrs &S, int n_balls, const StepParams &P, void *traj, cudaStream_t st);
+  static cudaError_t collide(const StatePtrs &S, const Layout &L, const StepParams &P, void *traj, int grid,
+                             cudaStream_t st);
+  static int collide_grid(int n_worlds, int sm_count);
+  static cudaError_t render(const StatePtrs &S, const Layout &L, const RenderLayout &RL, const uint32_t *atlas,
+                            uint8_t *frames, cudaStream_t st);
+  static cudaError_t reset_cache(const StatePtrs &S, int n_balls, int world0, int count, int keep_cache,
+                                 int32_t step_value, cudaStream_t st);
+  // traj (batch dtype) -> float32
+  static cudaError_t traj_to_f32(const void *src, float *dst, long long n, cudaStream_t st);
+};
+
+cudaError_t launch_advance_step_base(int32_t *step_base, int32_t n, cudaStream_t st);
+cudaError_t launch_build_sprites(uint32_t *atlas, const RenderLayout &RL, int n_balls, const uint32_t *fill8,
+                                 const uint32_t *stroke8, cudaStream_t st);
+
+}  // namespace ppb

@@ -1,0 +1,76 @@
+// ppb_launch_impl.cuh -- body of Launch<T>, included by ppb_f32.cu / ppb_f64.cu
+#pragma once
+#include "ppb_kernels.cuh"
+#include "ppb_launch.h"
+#include "ppb_render.cuh"
+
+namespace ppb {
+
+template <typename T>
+size_t Launch<T>::hdr_size() { return sizeof(Hdr<T>); }
+
+template <typename T>
+cudaError_t Launch<T>::integrate(const StatePtrs &S, int n_balls, const StepParams &P, void *traj, cudaStream_t st) {
+  const long long total = (long long)S.n_worlds * n_balls;
+  if (total == 0) return cudaSuccess;
+  if ((n_balls & 1) == 0) {
+    const long long thr = total / 2;
+    integrate_kernel<T, 2><<<(unsigned)((thr + 255) / 256), 256, 0, st>>>(S, n_balls, P, (T *)traj);
+  } else {
+    integrate_kernel<T, 1><<<(unsigned)((total + 255) / 256), 256, 0, st>>>(S, n_balls, P, (T *)traj);
+  }
+  return cudaGetLastError();
+}
+
+template <typename T>
+int Launch<T>::collide_grid(int n_worlds, int sm_count) {
+  int occ = 0;
+  cudaOccupancyMaxActiveBlocksPerMultiprocessor(&occ, collide_kernel<T>, PPB_COLLIDE_WARPS * 32, 0);
+  if (occ < 1) occ = 1;
+  const int groups = (n_worlds + 31) / 32;
+  const int need = (groups + PPB_COLLIDE_WARPS - 1) / PPB_COLLIDE_WARPS;
+  int grid = sm_count * occ;
+  if (grid > need) grid = need;
+  return grid < 1 ? 1 : grid;
+}
+
+template <typename T>
+cudaError_t Launch<T>::collide(const StatePtrs &S, const Layout &L, const StepParams &P, void *traj, int grid,
+                               cudaStream_t st) {
+  collide_kernel<T><<<grid, PPB_COLLIDE_WARPS * 32, 0, st>>>(S, L, P, (T *)traj);
+  return cudaGetLastError();
+}
+
+template <typename T>
+cudaError_t Launch<T>::render(const StatePtrs &S, const Layout &L, const RenderLayout &RL, const uint32_t *atlas,
+                              uint8_t *frames, cudaStream_t st) {
+  const int tiles = ((RL.W + PPB_TILE - 1) / PPB_TILE) * ((RL.H + PPB_TILE - 1) / PPB_TILE);
+  const long long blocks = (long long)S.n_worlds * tiles;
+  if (blocks == 0) return cudaSuccess;
+  if (blocks > 2147483647LL) return cudaErrorInvalidValue;
+  render_kernel<T><<<(unsigned)blocks, 256, 0, st>>>(S, L, RL, atlas, frames);
+  return cudaGetLastError();
+}
+
+template <typename T>
+cudaError_t Launch<T>::reset_cache(const StatePtrs &S, int n_balls, int world0, int count, int keep_cache,
+                                   int32_t step_value, cudaStream_t st) {
+  if (count <= 0) return cudaSuccess;
+  reset_cache_kernel<T><<<(count + 127) / 128, 128, 0, st>>>(S, n_balls, world0, count, keep_cache, step_value);
+  return cudaGetLastError();
+}
+
+template <typename T>
+__global__ void traj_to_f32_kernel(const T *src, float *dst, long long n) {
+  long long i = (long long)blockIdx.x * blockDim.x + threadIdx.x;
+  if (i < n) dst[i] = (float)src[i];
+}
+
+template <typename T>
+cudaError_t Launch<T>::traj_to_f32(const void *src, float *dst, long long n, cudaStream_t st) {
+  if (n <= 0) return cudaSuccess;
+  traj_to_f32_kernel<T><<<(unsigned)((n + 255) / 256), 256, 0, st>>>((const T *)src, dst, n);
+  return cudaGetLastError();
+}
+
+}  // namespace ppb

@@ -1,0 +1,262 @@
+"""WorldBatch -- N independent billiards worlds resident in HBM.
+
+Thin Python view of the C ABI (include/pyphy_b200.h).  This is the batched
+counterpart of ``pm.World`` + ``pm.Dynamics`` (reference primitives.py:535-805,
+856-1008): the façade classes in ``pyphy_engine_b200.primitives`` are the
+``n_worlds == 1`` case of this class, ``pyphy_engine_b200.dataio`` uses it with
+one world per sequence.
+"""
+from __future__ import annotations
+
+import ctypes
+from typing import Optional, Sequence
+
+import numpy as np
+
+from . import _capi
+from ._capi import PPB_F32, PPB_F64, BallStyle, Config, Event, WallStyle, check
+
+_DTYPES = {"f32": PPB_F32, "float32": PPB_F32, "fp32": PPB_F32, "f64": PPB_F64, "float64": PPB_F64, "fp64": PPB_F64}
+
+
+def _dp(a: Optional[np.ndarray]):
+    return None if a is None else a.ctypes.data_as(ctypes.POINTER(ctypes.c_double))
+
+
+def _ip(a: Optional[np.ndarray]):
+    return None if a is None else a.ctypes.data_as(ctypes.POINTER(ctypes.c_int32))
+
+
+def _stream_handle(stream) -> int:
+    """cudaStream_t of a torch stream / raw handle; None = torch's current stream."""
+    if stream is None:
+        import torch
+        return int(torch.cuda.current_stream().cuda_stream)
+    if hasattr(stream, "cuda_stream"):
+        return int(stream.cuda_stream)
+    return int(stream)
+
+
+class WorldBatch:
+    """``n_worlds`` worlds, each with ``n_walls`` wall slots and ``n_balls`` ball slots.
+
+    dtype "f64": the reference's fp64 operation order (bit-exact collision events);
+    dtype "f32": throughput mode.  ``order`` is the object insertion order shared
+    by all worlds (wall q -> q, ball b -> n_walls + b), default walls then balls.
+    """
+
+    def __init__(self, n_worlds: int, n_balls: int, n_walls: int, dtype: str = "f32",
+                 canvas: Sequence[int] = (0, 0), dt: float = 0.01, g: Sequence[float] = (0.0, 0.0),
+                 order: Optional[Sequence[int]] = None, device: int = 0, event_capacity: int = 0,
+                 friction: float = 0.0, max_substeps: int = 0):
+        self._lib = _capi.load()
+        self._h = ctypes.c_void_p()
+        self.n_worlds, self.n_balls, self.n_walls = int(n_worlds), int(n_balls), int(n_walls)
+        self.dtype = dtype
+        self.canvas_w, self.canvas_h = int(canvas[0]), int(canvas[1])
+        self.device = int(device)
+        self.dt = float(dt)
+        cfg = Config()
+        cfg.n_worlds, cfg.n_balls, cfg.n_walls = self.n_worlds, self.n_balls, self.n_walls
+        cfg.dtype = _DTYPES[dtype]
+        cfg.canvas_w, cfg.canvas_h = self.canvas_w, self.canvas_h
+        cfg.device = self.device
+        cfg.dt, cfg.gx, cfg.gy, cfg.friction = float(dt), float(g[0]), float(g[1]), float(friction)
+        cfg.event_capacity = int(event_capacity)
+        cfg.max_substeps = int(max_substeps)
+        self._order = None
+        if order is not None:
+            self._order = np.ascontiguousarray(order, np.int32)
+            if self._order.shape != (self.n_walls + self.n_balls,):
+                raise ValueError("order must have n_walls + n_balls entries")
+            cfg.order = _ip(self._order)
+        check(self._lib.ppb_create(ctypes.byref(cfg), ctypes.byref(self._h)))
+        self.steps_done = 0
+        self._np_dtype = np.float64 if cfg.dtype == PPB_F64 else np.float32
+
+    # ------------------------------------------------------------------ lifetime
+    def close(self):
+        if getattr(self, "_h", None) is not None and self._h.value:
+            self._lib.ppb_destroy(self._h)
+            self._h = ctypes.c_void_p()
+
+    def __del__(self):
+        try:
+            self.close()
+        except Exception:
+            pass
+
+    # ------------------------------------------------------------------ state in
+    def set_walls(self, wall, world0: int = 0, stream=0):
+        """wall: (count, n_walls, 4, 2) vertices (Bbox order, geometry.py:471-505)."""
+        wall = np.ascontiguousarray(wall, np.float64)
+        count = wall.shape[0] if self.n_walls else self.n_worlds - world0
+        if self.n_walls and wall.shape[1:] != (self.n_walls, 4, 2):
+            raise ValueError("wall must be (count, %d, 4, 2)" % self.n_walls)
+        check(self._lib.ppb_set_walls(self._h, world0, count, _dp(wall), stream))
+
+    def set_balls(self, pos, vel, rad, mass, world0: int = 0, stream=0):
+        """pos, vel: (count, n_balls, 2); rad, mass: (count, n_balls) or broadcastable.
+        Resets the collision caches of these worlds (Dynamics._include_object)."""
+        pos = np.ascontiguousarray(pos, np.float64)
+        count = pos.shape[0]
+        shp = (count, self.n_balls)
+        if pos.shape != shp + (2,):
+            raise ValueError("pos must be (count, %d, 2)" % self.n_balls)
+        vel = np.ascontiguousarray(np.broadcast_to(np.asarray(vel, np.float64), shp + (2,)))
+        rad = np.ascontiguousarray(np.broadcast_to(np.asarray(rad, np.float64), shp))
+        mass = np.ascontiguousarray(np.broadcast_to(np.asarray(mass, np.float64), shp))
+        check(self._lib.ppb_set_balls(self._h, world0, count, _dp(pos), _dp(vel), _dp(rad), _dp(mass), stream))
+
+    def update_balls(self, pos=None, vel=None, world0: int = 0, stream=0):
+        """ball.set_position / set_velocity: caches are left alone (primitives.py:462-466)."""
+        ref = pos if pos is not None else vel
+        if ref is None:
+            return
+        count = np.asarray(ref).shape[0]
+        p = None if pos is None else np.ascontiguousarray(pos, np.float64)
+        v = None if vel is None else np.ascontiguousarray(vel, np.float64)
+        for a in (p, v):
+            if a is not None and a.shape != (count, self.n_balls, 2):
+                raise ValueError("expected (count, n_balls, 2)")
+        check(self._lib.ppb_update_balls(self._h, world0, count, _dp(p), _dp(v), stream))
+
+    def requeue(self, world0: int = 0, count: Optional[int] = None, stream=0):
+        """Dynamics.add_all_dynamic_collision_queue (primitives.py:697-700)."""
+        count = self.n_worlds - world0 if count is None else count
+        check(self._lib.ppb_requeue(self._h, world0, count, stream))
+
+    def set_styles(self, ball_styles, wall_styles, r_min: int, r_max: int, stream=0):
+        """ball_styles: per slot (s_thick, fill rgba, stroke rgba); wall_styles: per slot (kind, fill rgba)."""
+        bs = (BallStyle * self.n_balls)()
+        for i, (st, fill, stroke) in enumerate(ball_styles):
+            bs[i].s_thick = int(st)
+            bs[i].fill[:] = [float(c) for c in fill]
+            bs[i].stroke[:] = [float(c) for c in stroke]
+        ws = (WallStyle * max(1, self.n_walls))()
+        for i, (kind, fill) in enumerate(wall_styles):
+            ws[i].kind = int(kind)
+            ws[i].fill[:] = [float(c) for c in fill]
+        check(self._lib.ppb_set_styles(self._h, bs, ws, int(r_min), int(r_max), stream))
+
+    # ------------------------------------------------------------------ state out
+    def get_balls(self, world0: int = 0, count: Optional[int] = None, stream=0):
+        count = self.n_worlds - world0 if count is None else count
+        pos = np.empty((count, self.n_balls, 2), np.float64)
+        vel = np.empty((count, self.n_balls, 2), np.float64)
+        check(self._lib.ppb_get_balls(self._h, world0, count, _dp(pos), _dp(vel), stream))
+        return pos, vel
+
+    def get_collision_cache(self, world0: int = 0, count: Optional[int] = None, stream=0):
+        count = self.n_worlds - world0 if count is None else count
+        tcol = np.empty((count, self.n_balls), np.float64)
+        partner = np.empty((count, self.n_balls), np.int32)
+        check(self._lib.ppb_get_collision_cache(self._h, world0, count, _dp(tcol), _ip(partner), stream))
+        return tcol, partner
+
+    def get_status(self, world0: int = 0, count: Optional[int] = None, stream=0):
+        """(status, steps_done) per world; for a halted world steps_done is the failing step."""
+        count = self.n_worlds - world0 if count is None else count
+        status = np.empty((count,), np.int32)
+        steps = np.empty((count,), np.int32)
+        check(self._lib.ppb_get_status(self._h, world0, count, _ip(status), _ip(steps), stream))
+        return status, steps
+
+    def read_events(self, stream=0):
+        """(k, 4) int32 rows (world, step, ball, partner) sorted by (world, call order)."""
+        n = ctypes.c_int64(0)
+        check(self._lib.ppb_read_events(self._h, None, 0, ctypes.byref(n), stream))
+        total = n.value
+        buf = (Event * max(1, total))()
+        check(self._lib.ppb_read_events(self._h, buf, total, ctypes.byref(n), stream))
+        m = min(total, len(buf))
+        raw = np.frombuffer(buf, dtype=np.dtype([("world", "<i4"), ("seq", "<i4"), ("step", "<i4"),
+                                                  ("ball", "<i2"), ("partner", "<i2")]), count=m)
+        idx = np.lexsort((raw["seq"], raw["world"]))
+        raw = raw[idx]
+        out = np.stack([raw["world"], raw["step"], raw["ball"].astype(np.int32), raw["partner"].astype(np.int32)], 1)
+        return out.astype(np.int32), total
+
+    def clear_events(self, stream=0):
+        check(self._lib.ppb_clear_events(self._h, stream))
+
+    def counters(self, stream=0):
+        """dict(launches, collide_world_steps, collide_iterations, events)."""
+        out = (ctypes.c_int64 * 4)()
+        check(self._lib.ppb_get_counters(self._h, out, stream))
+        return dict(launches=out[0], collide_world_steps=out[1], collide_iterations=out[2], events=out[3])
+
+    # ------------------------------------------------------------------ stepping
+    def step_async(self, n_steps: int = 1, traj=None, frames=None, render_every: int = 1, stream=None):
+        """n_steps x Dynamics.step() on `stream` (default: torch's current stream).
+
+        traj: None or a CUDA tensor (n_steps, n_worlds, n_balls, 2) of the batch dtype;
+        frames: None or a CUDA uint8 tensor (n_steps // render_every, n_worlds, H, W, 4).
+        """
+        tp = ctypes.c_void_p(traj.data_ptr()) if traj is not None else None
+        fp = ctypes.c_void_p(frames.data_ptr()) if frames is not None else None
+        if traj is not None:
+            assert traj.is_cuda and traj.is_contiguous() and tuple(traj.shape) == (n_steps, self.n_worlds, self.n_balls, 2)
+        if frames is not None:
+            assert frames.is_cuda and frames.is_contiguous()
+            assert tuple(frames.shape) == (n_steps // render_every, self.n_worlds, self.canvas_h, self.canvas_w, 4)
+        check(self._lib.ppb_step_async(self._h, int(n_steps), tp, fp, int(render_every), _stream_handle(stream)))
+        self.steps_done += int(n_steps)
+
+    def step(self, n_steps: int = 1, record_traj: bool = False, render_every: int = 0, stream=None):
+        """Synchronous convenience: returns (traj, frames) as CUDA tensors (or None)."""
+        import torch
+        dev = torch.device("cuda", self.device)
+        traj = frames = None
+        if record_traj:
+            traj = torch.empty((n_steps, self.n_worlds, self.n_balls, 2), device=dev,
+                               dtype=torch.float64 if self._np_dtype is np.float64 else torch.float32)
+        if render_every:
+            frames = torch.empty((n_steps // render_every, self.n_worlds, self.canvas_h, self.canvas_w, 4),
+                                 device=dev, dtype=torch.uint8)
+        self.step_async(n_steps, traj, frames, render_every or 1, stream)
+        torch.cuda.synchronize(dev)
+        return traj, frames
+
+    def render(self, out=None, stream=None):
+        """World.generate_image() for every world -> CUDA uint8 tensor (n_worlds, H, W, 4)."""
+        import torch
+        if out is None:
+            out = torch.empty((self.n_worlds, self.canvas_h, self.canvas_w, 4), device=torch.device("cuda", self.device),
+                              dtype=torch.uint8)
+        check(self._lib.ppb_render_async(self._h, ctypes.c_void_p(out.data_ptr()), _stream_handle(stream)))
+        return out
+
+    def simulate_host(self, n_steps: int, traj_host=None, frames_host=None, render_every: int = 1, stream=0):
+        """Host-buffer path (DataSaver.fetch analogue): copies are inside the call.
+
+        traj_host: None or float32 array (n_steps, n_worlds, n_balls, 2);
+        frames_host: None or uint8 array (n_steps // render_every, n_worlds, H, W, 4).
+        numpy arrays or pinned CPU torch tensors are accepted.
+        """
+        def _ptr(a):
+            if a is None:
+                return None
+            if hasattr(a, "data_ptr"):
+                return ctypes.c_void_p(a.data_ptr())
+            return ctypes.c_void_p(a.ctypes.data)
+        check(self._lib.ppb_simulate_host(self._h, int(n_steps), _ptr(traj_host), _ptr(frames_host),
+                                          int(render_every), stream))
+        self.steps_done += int(n_steps)
+
+    # ------------------------------------------------------------------ profiling
+    def set_profiling(self, on: bool):
+        check(self._lib.ppb_set_profiling(self._h, 1 if on else 0))
+
+    def kernel_times(self):
+        """(ms[3], launches[3]) for integrate / collide / render of the last stepping call."""
+        ms = (ctypes.c_float * 3)()
+        n = (ctypes.c_int32 * 3)()
+        check(self._lib.ppb_get_kernel_times(self._h, ms, n))
+        return list(ms), list(n)
+
+    def device_ptr(self, which: int):
+        p = ctypes.c_void_p()
+        n = ctypes.c_int64()
+        check(self._lib.ppb_device_ptr(self._h, which, ctypes.byref(p), ctypes.byref(n)))
+        return p.value, n.value

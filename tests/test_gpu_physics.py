@@ -1,0 +1,201 @@
+"""GPU parity tests (physics): CUDA kernels through the C ABI vs. the oracle and the
+reference goldens.  Run on the B200 box: ``pytest -m gpu``.
+
+Bars:
+  * fp64 batches: bit-identical with the C oracle (portable trig) -- positions after every
+    step, collision event sequences, failure outcomes -- and event-identical with the
+    UNMODIFIED reference over the golden horizons;
+  * fp32 batches: positions within the stated tolerance of the fp64 oracle over a fixed
+    horizon (see FP32_* below).
+"""
+import numpy as np
+import pytest
+
+import oracle
+from conftest import load_golden
+
+pytestmark = pytest.mark.gpu
+
+PHYS = load_golden("physics_golden.npz")
+FAIL = load_golden("failure_golden.npz")
+
+# fp32 tolerance: over the first FP32_HORIZON steps (<= ~2 ball-ball contacts per ball at
+# native speeds) 99% of the balls must be within FP32_ABS px of the fp64 oracle and the
+# median error must be below FP32_MED px.  Billiards amplifies rounding noise by roughly
+# an order of magnitude per ball-ball contact, so a longer horizon is not meaningful.
+FP32_HORIZON = 60
+FP32_ABS = 0.05
+FP32_MED = 2e-3
+
+
+def _batch(case, dtype, n_events=100000, max_substeps=0):
+    from pyphy_engine_b200.engine import WorldBatch
+    nB, nW = case["pos0"].shape[0], case["wall"].shape[0]
+    wb = WorldBatch(1, nB, nW, dtype=dtype, dt=float(case["dt"]), g=tuple(case["g"]), order=case["order"],
+                    event_capacity=n_events, max_substeps=max_substeps)
+    wb.set_walls(case["wall"][None])
+    wb.set_balls(case["pos0"][None], case["vel0"][None], case["rad"][None], case["mass"][None])
+    return wb
+
+
+def _oracle(case, trig_mode=1, n_steps=None):
+    ob = oracle.OracleBatch(case["wall"][None], case["pos0"][None], case["vel0"][None], case["rad"][None],
+                            case["mass"][None], order=case["order"], dt=float(case["dt"]), g=tuple(case["g"]),
+                            trig_mode=trig_mode)
+    traj, ev = ob.step(n_steps or case.n_steps, record_traj=True, max_events=200000)
+    return ob, traj[:, 0], ev[:, 1:]
+
+
+@pytest.mark.parametrize("case", PHYS + FAIL, ids=[c.name for c in PHYS + FAIL])
+def test_f64_bit_exact_with_oracle(case):
+    wb = _batch(case, "f64")
+    traj, _ = wb.step(case.n_steps, record_traj=True)
+    traj = traj.cpu().numpy()[:, 0]
+    ev, total = wb.read_events()
+    ob, otraj, oev = _oracle(case)
+    status, steps = wb.get_status()
+    assert status[0] == ob.status[0]
+    k = case.n_steps
+    if ob.status[0] != 0:
+        assert steps[0] == ob.status_step[0]
+        k = ob.status_step[0]
+    assert np.array_equal(ev[:, 1:], oev), "event sequence differs from the oracle"
+    assert np.array_equal(traj[:k], otraj[:k]), "positions are not bit-identical with the oracle"
+    pos, vel = wb.get_balls()
+    if ob.status[0] == 0:
+        assert np.array_equal(pos[0], ob.pos[0]) and np.array_equal(vel[0], ob.vel[0])
+        tcol, partner = wb.get_collision_cache()
+        assert np.array_equal(tcol[0], ob.tcol[0]) and np.array_equal(partner[0], ob.partner[0])
+
+
+@pytest.mark.parametrize("case", [c for c in PHYS if not c.name.startswith("crowd12")],
+                         ids=[c.name for c in PHYS if not c.name.startswith("crowd12")])
+def test_f64_events_match_reference(case):
+    """Collision event sequences (which ball, which wall/ball, at which step) are identical
+    with the unmodified reference over the whole golden horizon; positions within 1e-6 px."""
+    wb = _batch(case, "f64")
+    traj, _ = wb.step(case.n_steps, record_traj=True)
+    ev, _ = wb.read_events()
+    assert np.array_equal(ev[:, 1:], case["events"])
+    assert np.max(np.abs(traj.cpu().numpy()[:, 0] - case["traj"])) < 1e-6
+
+
+@pytest.mark.parametrize("case", FAIL, ids=[c.name for c in FAIL])
+def test_f64_failure_outcomes_match_reference(case):
+    wb = _batch(case, "f64")
+    wb.step(case.n_steps)
+    status, steps = wb.get_status()
+    assert status[0] == case.status and steps[0] == case.status_step
+    ev, _ = wb.read_events()
+    assert np.array_equal(ev[:, 1:], case["events"])
+
+
+def _random_batch(n_worlds, n_balls, seed, dtype, max_substeps=4096, **kw):
+    from pyphy_engine_b200 import sampler
+    from pyphy_engine_b200.engine import WorldBatch
+    W = sampler.sample_rect_worlds(n_worlds, n_balls, seed=seed, **kw)
+    wb = WorldBatch(n_worlds, n_balls, 4, dtype=dtype, event_capacity=4_000_000, max_substeps=max_substeps)
+    wb.set_walls(W["wall"])
+    wb.set_balls(W["pos"], W["vel"], W["rad"], W["mass"])
+    ob = oracle.OracleBatch(W["wall"], W["pos"], W["vel"], W["rad"], W["mass"], trig_mode=1,
+                            max_substeps=max_substeps)
+    return W, wb, ob
+
+
+@pytest.mark.parametrize("n_worlds,n_balls,kw", [
+    (2048, 4, {}),
+    (1024, 8, dict(arena=1200, mn_wlen=700, mx_wlen=1000)),
+    (257, 3, dict(mn_ball=15, mx_ball=35)),       # ragged: not a multiple of the warp size, odd ball count
+    (64, 32, dict(arena=2400, mn_wlen=1800, mx_wlen=2200)),   # maximum ball count
+    (1, 1, {}),
+])
+def test_f64_random_batches_bit_exact(n_worlds, n_balls, kw):
+    n_steps = 200
+    W, wb, ob = _random_batch(n_worlds, n_balls, 7 + n_balls, "f64", **kw)
+    traj, _ = wb.step(n_steps, record_traj=True)
+    traj = traj.cpu().numpy()
+    otraj, oev = ob.step(n_steps, record_traj=True, max_events=4_000_000)
+    status, steps = wb.get_status()
+    assert np.array_equal(status, ob.status)
+    alive = ob.status == 0
+    assert np.array_equal(steps[~alive], ob.status_step[~alive])
+    assert np.array_equal(traj[:, alive], otraj[:, alive])
+    ev, total = wb.read_events()
+    assert total == len(oev) == len(ev)
+    assert np.array_equal(ev, oev)
+    pos, vel = wb.get_balls()
+    assert np.array_equal(pos[alive], ob.pos[alive]) and np.array_equal(vel[alive], ob.vel[alive])
+
+
+def test_f64_chunking_is_invisible():
+    """n steps in one call == n calls of one step == steps split across calls."""
+    W, wb1, _ = _random_batch(512, 4, 3, "f64")
+    _, wb2, _ = _random_batch(512, 4, 3, "f64")
+    wb1.step(90)
+    for n in (1, 1, 7, 31, 50):
+        wb2.step(n)
+    p1, v1 = wb1.get_balls()
+    p2, v2 = wb2.get_balls()
+    assert np.array_equal(p1, p2) and np.array_equal(v1, v2)
+    assert np.array_equal(wb1.read_events()[0], wb2.read_events()[0])
+
+
+@pytest.mark.parametrize("n_worlds,n_balls,kw", [
+    (4096, 4, {}),
+    (2048, 8, dict(arena=1200, mn_wlen=700, mx_wlen=1000)),
+])
+def test_f32_trajectories_within_tolerance(n_worlds, n_balls, kw):
+    W, wb, ob = _random_batch(n_worlds, n_balls, 11, "f32", **kw)
+    traj, _ = wb.step(FP32_HORIZON, record_traj=True)
+    traj = traj.cpu().numpy().astype(np.float64)
+    otraj, _ = ob.step(FP32_HORIZON, record_traj=True)
+    status, _ = wb.get_status()
+    ok = (status == 0) & (ob.status == 0)
+    err = np.abs(traj[:, ok] - otraj[:, ok]).max(axis=(0, 3))      # per world, per ball
+    assert np.median(err) < FP32_MED, np.median(err)
+    assert np.mean(err < FP32_ABS) > 0.99, np.mean(err < FP32_ABS)
+    # single-ball-contact-free prefix is essentially exact
+    err10 = np.abs(traj[:10, ok] - otraj[:10, ok]).max()
+    assert err10 < 0.02, err10
+
+
+def test_f32_event_counts_statistically_match():
+    """Same algorithm, same quirks: over 200 steps the fp32 engine produces the same number
+    of collision events as the oracle to within 2%."""
+    W, wb, ob = _random_batch(4096, 4, 5, "f32", max_substeps=256)
+    wb.step(200)
+    ob.step(200, n_threads=8)
+    n = wb.counters()["events"]
+    assert abs(n - ob.n_events_total) < 0.02 * ob.n_events_total, (n, ob.n_events_total)
+
+
+def test_energy_and_confinement_properties():
+    """Size-independent properties at a BASELINE-sized batch (65,536 4-ball worlds, fp32):
+    balls stay inside their cage and single-ball worlds conserve speed exactly under wall bounces."""
+    from pyphy_engine_b200 import sampler
+    from pyphy_engine_b200.engine import WorldBatch
+    n = 65536
+    W = sampler.sample_rect_worlds(n, 4, seed=21)
+    wb = WorldBatch(n, 4, 4, dtype="f32", max_substeps=256)
+    wb.set_walls(W["wall"])
+    wb.set_balls(W["pos"], W["vel"], W["rad"], W["mass"])
+    wb.step(300)
+    pos, vel = wb.get_balls()
+    status, _ = wb.get_status()
+    ok = status == 0
+    assert ok.mean() > 0.995
+    pts = W["cage_pts"]
+    lo = pts[:, 0, :][:, None, :] + 30 + W["rad"][..., None] - 0.01
+    hi = np.stack([pts[:, 1, 0], pts[:, 2, 1]], -1)[:, None, :] - 30 - W["rad"][..., None] + 0.01
+    inside = ((pos >= lo) & (pos <= hi)).all(axis=(1, 2))
+    assert inside[ok].mean() > 0.999, inside[ok].mean()
+    # one ball per world: |v| is invariant under reflections
+    W1 = sampler.sample_rect_worlds(8192, 1, seed=22)
+    wb1 = WorldBatch(8192, 1, 4, dtype="f32")
+    wb1.set_walls(W1["wall"])
+    wb1.set_balls(W1["pos"], W1["vel"], W1["rad"], W1["mass"])
+    wb1.step(500)
+    _, v1 = wb1.get_balls()
+    s0 = np.linalg.norm(W1["vel"], axis=-1)
+    s1 = np.linalg.norm(v1, axis=-1)
+    assert np.max(np.abs(s1 - s0) / s0) < 1e-5
