@@ -42,6 +42,8 @@ def lib():
         _lib.oracle_step_batch.restype = ctypes.c_int64
         _lib.oracle_trig.restype = ctypes.c_double
         _lib.oracle_trig.argtypes = [ctypes.c_int, ctypes.c_double, ctypes.c_int]
+        _lib.oracle_disc_box_area.restype = ctypes.c_double
+        _lib.oracle_quad_pixel_area.restype = ctypes.c_double
     return _lib
 
 
@@ -117,6 +119,60 @@ class OracleBatch:
                 raise RuntimeError("event buffer too small: %d > %d" % (n, max_events))
             ev = ev[:n]
         return traj, ev
+
+
+def render_frames(wall, pos, rad, canvas, order=None, wall_kind=None, wall_rgba=None, s_thick=2,
+                  fill=(0.5, 0.5, 0.5, 1.0), stroke=(0.0, 0.0, 0.0, 1.0), n_threads=1):
+    """Restated ``World.generate_image`` (render_oracle.c) -> (n_worlds, H, W, 4) uint8.
+
+    wall (n_worlds, n_walls, 4, 2); pos (n_worlds, n_balls, 2); rad (n_worlds, n_balls);
+    wall_rgba (n_walls, 4) default red; fill / stroke / s_thick per ball slot or shared.
+    """
+    L = lib()
+    wall = np.ascontiguousarray(wall, np.float64)
+    pos = np.ascontiguousarray(pos, np.float64)
+    nw, nb = pos.shape[:2]
+    nwl = wall.shape[1]
+    rad = np.ascontiguousarray(np.broadcast_to(rad, (nw, nb)), np.float64)
+    W, H = int(canvas[0]), int(canvas[1])
+    order = np.ascontiguousarray(np.arange(nwl + nb) if order is None else order, np.int32)
+    wall_kind = np.ascontiguousarray(np.zeros(nwl) if wall_kind is None else wall_kind, np.int32)
+    if wall_rgba is None or nwl == 0:
+        wall_rgba = np.array([1.0, 0.0, 0.0, 1.0])
+    wall_rgba = np.ascontiguousarray(np.broadcast_to(np.asarray(wall_rgba, np.float32), (max(nwl, 1), 4)), np.float32)
+    st = np.ascontiguousarray(np.broadcast_to(s_thick, (nb,)), np.int32)
+    fl = np.ascontiguousarray(np.broadcast_to(np.asarray(fill, np.float32), (nb, 4)), np.float32)
+    sk = np.ascontiguousarray(np.broadcast_to(np.asarray(stroke, np.float32), (nb, 4)), np.float32)
+    out = np.empty((nw, H, W, 4), np.uint8)
+    fp = ctypes.POINTER(ctypes.c_float)
+    L.oracle_render_frames(ctypes.c_int(nw), ctypes.c_int(nb), ctypes.c_int(nwl), _ip(order), _dp(wall),
+                           _ip(wall_kind), wall_rgba.ctypes.data_as(fp), _dp(pos), _dp(rad), _ip(st),
+                           fl.ctypes.data_as(fp), sk.ctypes.data_as(fp), ctypes.c_int(W), ctypes.c_int(H),
+                           out.ctypes.data_as(ctypes.POINTER(ctypes.c_uint8)), ctypes.c_int(n_threads))
+    return out
+
+
+def ball_sprite(r, s_thick=2, fill=(0.5, 0.5, 0.5, 1.0), stroke=(0.0, 0.0, 0.0, 1.0)):
+    """get_ball_im restated: (sz, sz, 4) premultiplied uint8."""
+    L = lib()
+    sz = 2 * (int(r) + int(s_thick))
+    out = np.zeros((sz, sz, 4), np.uint8)
+    fl = np.asarray(fill, np.float32)
+    sk = np.asarray(stroke, np.float32)
+    fp = ctypes.POINTER(ctypes.c_float)
+    L.oracle_ball_sprite(ctypes.c_int(int(r)), ctypes.c_int(int(s_thick)), fl.ctypes.data_as(fp),
+                         sk.ctypes.data_as(fp), out.ctypes.data_as(ctypes.POINTER(ctypes.c_uint8)))
+    return out
+
+
+def disc_box_area(R, x0, x1, y0, y1):
+    return lib().oracle_disc_box_area(ctypes.c_double(R), ctypes.c_double(x0), ctypes.c_double(x1),
+                                      ctypes.c_double(y0), ctypes.c_double(y1))
+
+
+def quad_pixel_area(quad, px, py):
+    q = np.ascontiguousarray(quad, np.float64)
+    return lib().oracle_quad_pixel_area(_dp(q), ctypes.c_double(px), ctypes.c_double(py))
 
 
 def trig(which: str, x: float, mode: int) -> float:

