@@ -1,0 +1,340 @@
+#!/usr/bin/env python
+"""bench.py -- throughput of the simulate-and-render hot path on N B200s of one node.
+
+    python bench.py [--gpus N] [--steps K] [--warmup W] [--impl ours|reference]
+    python -m torch.distributed.run --nnodes=1 --nproc-per-node N --master-addr 127.0.0.1 \
+        --master-port P bench.py --gpus N --steps K --warmup W
+
+Workload (BASELINE.json configs[3], the configuration the 1/2/4/8-GPU metric is quoted on):
+per GPU 131,072 independent 8-ball worlds on a 64x64 canvas, synthetic random-initialised
+rectangular tables; one "step" = Dynamics.step() + World.generate_image() for every world of
+the shard (3 kernel launches: integrate, collide, render).  Weak scaling: the per-GPU shard is
+fixed, 8 GPUs = the full 1,048,576-world config.  Worlds are independent, so there is no
+collective in the step loop; NCCL only carries the final timing/statistics reduction.
+
+Prints ONE JSON line on rank 0 (see the field notes in DESIGN.md "Measurement").
+"""
+from __future__ import annotations
+
+import argparse
+import json
+import os
+import subprocess
+import sys
+import tempfile
+import time
+
+import numpy as np
+
+ROOT = os.path.dirname(os.path.abspath(__file__))
+sys.path.insert(0, ROOT)
+
+WORLDS_PER_GPU = 131072
+N_BALLS = 8
+CANVAS = 64
+SEED0 = 20161
+MAX_SUBSTEPS = 256
+# algorithmic bytes (fp32 state, RGBA8 frames), SURVEY.md 8(d) / DESIGN.md "Kernels"
+BYTES_K1_PER_BALL_STEP = 32
+BYTES_K3_PER_FRAME = CANVAS * CANVAS * 4
+
+
+def _bytes_k2_per_world_step(n_balls, n_seg=16):
+    return 24 * n_balls + 16 * n_seg + 16 * n_balls
+
+
+def load_peaks():
+    p = os.path.join(ROOT, "MEASURED_PEAKS.json")
+    if os.path.exists(p):
+        with open(p) as fh:
+            return float(json.load(fh)["hbm_gbs"]), "measured (MEASURED_PEAKS.json hbm_gbs)"
+    return 6650.0, "fallback (B200_PROFILING.md 6.65 TB/s)"
+
+
+class ClockSampler:
+    """nvidia-smi clocks / throttle reasons sampled every 200 ms while the timed region runs."""
+    Q = ("index,clocks.sm,clocks.max.sm,power.draw,clocks_event_reasons.active,"
+         "clocks_event_reasons.hw_slowdown,clocks_event_reasons.hw_thermal_slowdown,"
+         "clocks_event_reasons.sw_thermal_slowdown,clocks_event_reasons.sw_power_cap")
+
+    def __init__(self, gpu_index):
+        self.gpu_index = gpu_index
+        self.proc = None
+        self.path = None
+
+    def start(self):
+        try:
+            fd, self.path = tempfile.mkstemp(prefix="clocks_", suffix=".csv")
+            os.close(fd)
+            self.proc = subprocess.Popen(["nvidia-smi", "--query-gpu=" + self.Q, "--format=csv,noheader,nounits",
+                                          "-lms", "200", "-i", str(self.gpu_index)],
+                                         stdout=open(self.path, "w"), stderr=subprocess.DEVNULL)
+        except Exception:
+            self.proc = None
+
+    def stop(self):
+        out = {"sm_mhz": None, "sm_max_mhz": None, "reasons": [], "samples": 0}
+        if self.proc is None:
+            return out
+        time.sleep(0.25)
+        self.proc.terminate()
+        try:
+            self.proc.wait(timeout=5)
+        except Exception:
+            self.proc.kill()
+        sm, mx, reasons = [], [], set()
+        try:
+            for line in open(self.path):
+                f = [x.strip() for x in line.split(",")]
+                if len(f) < 9:
+                    continue
+                try:
+                    sm.append(float(f[1]))
+                    mx.append(float(f[2]))
+                except ValueError:
+                    continue
+                for name, val in zip(("hw_slowdown", "hw_thermal_slowdown", "sw_thermal_slowdown", "sw_power_cap"), f[5:9]):
+                    if val.lower().startswith("active"):
+                        reasons.add(name)
+            os.unlink(self.path)
+        except Exception:
+            pass
+        if sm:
+            out.update(sm_mhz=float(np.median(sm)), sm_max_mhz=float(max(mx)), samples=len(sm))
+        out["reasons"] = sorted(reasons)
+        return out
+
+
+def make_worlds(n_worlds, n_balls, seed):
+    from pyphy_engine_b200 import sampler
+    return sampler.sample_rect_worlds(n_worlds, n_balls, seed=seed, **sampler.scaled64_params(n_balls))
+
+
+STYLE_BALL = (1, (0.5, 0.5, 0.5, 1.0), (0.0, 0.0, 0.0, 1.0))   # sThick 1, gray fill, black ring
+STYLE_WALL = (0, (1.0, 0.0, 0.0, 1.0))                          # GenericWall, red
+
+
+# --------------------------------------------------------------------------------------
+# reference arm / cpu baseline: the oracle port (C restatement of the reference) on host cores
+# --------------------------------------------------------------------------------------
+class CpuPort:
+    """The C port (oracle/) stepping + rendering a bounded sample of the workload on host cores."""
+
+    def __init__(self, n_worlds, n_balls, threads, seed):
+        sys.path.insert(0, os.path.join(ROOT, "oracle"))
+        import oracle
+        self.oracle = oracle
+        self.W = make_worlds(n_worlds, n_balls, seed)
+        self.ob = oracle.OracleBatch(self.W["wall"], self.W["pos"], self.W["vel"], self.W["rad"], self.W["mass"],
+                                     trig_mode=0, max_substeps=MAX_SUBSTEPS)
+        self.threads = threads
+        self.n_worlds, self.n_balls = n_worlds, n_balls
+
+    def step(self, render=True):
+        """one Dynamics.step() + generate_image() per world; returns seconds."""
+        t0 = time.perf_counter()
+        self.ob.step(1, n_threads=self.threads)
+        if render:
+            self.oracle.render_frames(self.W["wall"], self.ob.pos, self.W["rad"], (CANVAS, CANVAS),
+                                      s_thick=STYLE_BALL[0], fill=STYLE_BALL[1], stroke=STYLE_BALL[2],
+                                      n_threads=self.threads)
+        return time.perf_counter() - t0
+
+
+def cpu_baseline(threads, target_seconds=12.0, n_worlds=4096):
+    port = CpuPort(n_worlds, N_BALLS, threads, SEED0)
+    for _ in range(3):
+        t1 = port.step()
+    n_steps = int(min(2000, max(5, target_seconds / max(t1, 1e-5))))
+    t = sum(port.step() for _ in range(n_steps))
+    live = int((port.ob.status == 0).sum())
+    return {"value": live * N_BALLS * n_steps / t, "unit": "ball-steps/s", "cores": threads, "kind": "port",
+            "frames_per_sec": live * n_steps / t,
+            "sample": "%d worlds x %d balls x %d steps after 3 warm-up steps, step+render per step, OpenMP over worlds "
+                      "(C restatement of the reference; the Python reference cannot travel to the GPU box)"
+                      % (n_worlds, N_BALLS, n_steps)}
+
+
+def run_reference(args, rank, world_size):
+    if rank != 0:
+        return
+    threads = os.cpu_count() or 1
+    sample_worlds = 4096
+    port = CpuPort(sample_worlds, N_BALLS, threads, SEED0)
+    for _ in range(max(args.warmup, 1)):
+        port.step()
+    t_total = sum(port.step() for _ in range(args.steps))
+    live = int((port.ob.status == 0).sum())
+    value = live * N_BALLS * args.steps / t_total
+    line = {
+        "impl": "reference", "metric": "ball_steps_per_sec", "value": value, "unit": "ball-steps/s",
+        "n_gpus": args.gpus, "steps": args.steps, "warmup": args.warmup,
+        "ms_per_step": 1e3 * t_total / max(args.steps, 1), "higher_is_better": True, "scaling": "weak",
+        "vs_baseline": None, "dtype": "f64", "data": "synthetic",
+        "frames_per_sec": live * args.steps / t_total,
+        "config": {"workload": "configs[3] shard: 131072 worlds/GPU x 8 balls, 64x64 frame rendered every step",
+                   "sample": "each timed step = one step+render of a %d-world sample of that workload" % sample_worlds},
+        "cpu_baseline": {"value": value, "unit": "ball-steps/s", "cores": threads, "kind": "port",
+                         "sample": "%d worlds x %d balls, step+render per timed step, %d steps, OpenMP over worlds; "
+                                   "C restatement of the reference (the Python reference cannot travel to the GPU box)"
+                                   % (sample_worlds, N_BALLS, args.steps)},
+        "e2e": {"value": value, "unit": "ball-steps/s", "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0},
+        "gpu_launches": 0,
+    }
+    print(json.dumps(line), flush=True)
+
+
+# --------------------------------------------------------------------------------------
+# our arm
+# --------------------------------------------------------------------------------------
+def run_ours(args, rank, local_rank, world_size):
+    import torch
+    import torch.distributed as dist
+    from pyphy_engine_b200.engine import WorldBatch
+
+    if not torch.cuda.is_available():
+        raise SystemExit("bench.py: no CUDA device -- the engine has no CPU fallback")
+    torch.cuda.set_device(local_rank)
+    dev = torch.device("cuda", local_rank)
+    distributed = world_size > 1
+    if distributed and not dist.is_initialized():
+        dist.init_process_group("nccl", device_id=dev)
+
+    def barrier():
+        if distributed:
+            dist.barrier(device_ids=[local_rank])
+        torch.cuda.synchronize(dev)
+
+    n_worlds = WORLDS_PER_GPU
+    W = make_worlds(n_worlds, N_BALLS, SEED0 + 7919 * rank)   # shard `rank` of the global world list
+    wb = WorldBatch(n_worlds, N_BALLS, 4, dtype="f32", canvas=(CANVAS, CANVAS), device=local_rank,
+                    max_substeps=MAX_SUBSTEPS)
+    wb.set_walls(W["wall"])
+    wb.set_balls(W["pos"], W["vel"], W["rad"], W["mass"])
+    wb.set_styles([STYLE_BALL] * N_BALLS, [STYLE_WALL] * 4, 3, 3)
+    frames = torch.empty((1, n_worlds, CANVAS, CANVAS, 4), dtype=torch.uint8, device=dev)  # 2 GiB, rewritten every step
+
+    # ---- device-resident throughput: W warm-up steps, K timed steps ----
+    for _ in range(args.warmup):
+        wb.step_async(1, None, frames, 1)
+    barrier()
+    c0 = wb.counters()
+    st0, _ = wb.get_status()
+    wb.set_profiling(True)
+    clocks = ClockSampler(local_rank)
+    clocks.start()
+    e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+    barrier()
+    e0.record()
+    for _ in range(args.steps):
+        wb.step_async(1, None, frames, 1)
+    e1.record()
+    barrier()
+    ms = e0.elapsed_time(e1)
+    clk = clocks.stop()
+    # per-kernel CUDA-event times over the timed region (events recorded on the launch stream)
+    kms, kn = wb.kernel_times()
+    wb.set_profiling(False)
+    c1 = wb.counters()
+    st1, steps_done = wb.get_status()
+    live = int((st1 == 0).sum())
+    launches = c1["launches"] - c0["launches"]
+
+    k_ms, k_n = np.array(kms), np.array(kn)
+    avg_us = 1e3 * k_ms / np.maximum(k_n, 1)
+
+    # ---- end-to-end through the host-buffer API: H2D of the batch state + step + D2H of positions and frames ----
+    traj_host = torch.empty((1, n_worlds, N_BALLS, 2), dtype=torch.float32).pin_memory()
+    frames_host = torch.empty((1, n_worlds, CANVAS, CANVAS, 4), dtype=torch.uint8).pin_memory()
+    e2e_steps = max(3, min(args.steps, 10))
+    h2d = W["pos"].nbytes // 2 + W["vel"].nbytes // 2 + W["rad"].nbytes + W["wall"].nbytes // 2   # fp32 on the wire
+    d2h = traj_host.numel() * 4 + frames_host.numel()
+    wb.set_walls(W["wall"])
+    wb.set_balls(W["pos"], W["vel"], W["rad"], W["mass"])
+    wb.simulate_host(1, traj_host, frames_host, 1)        # warm-up (allocates the staging buffers)
+    barrier()
+    t0 = time.perf_counter()
+    for _ in range(e2e_steps):
+        wb.set_walls(W["wall"])                                       # host -> device: this step's input tables
+        wb.set_balls(W["pos"], W["vel"], W["rad"], W["mass"])
+        wb.simulate_host(1, traj_host, frames_host, 1)                # step + render + device -> host
+    barrier()
+    e2e_s = time.perf_counter() - t0
+    e2e_checksum = int(frames_host[0, :64].sum())
+
+    # ---- reductions: max time over ranks, totals over ranks ----
+    stats = torch.tensor([ms, e2e_s, float(live), float(c1["events"] - c0["events"]), float(launches)],
+                         dtype=torch.float64, device=dev)
+    if distributed:
+        mx = stats.clone()
+        dist.all_reduce(mx, op=dist.ReduceOp.MAX)
+        sm = stats.clone()
+        dist.all_reduce(sm, op=dist.ReduceOp.SUM)
+        ms, e2e_s = float(mx[0]), float(mx[1])
+        live_total, events_total, launches_total = float(sm[2]), float(sm[3]), float(sm[4])
+    else:
+        live_total, events_total, launches_total = float(live), float(stats[3]), float(launches)
+
+    if rank == 0:
+        total_worlds = n_worlds * world_size
+        ball_steps = live_total * N_BALLS * args.steps          # halted worlds do not count
+        value = ball_steps / (ms * 1e-3)
+        fps = live_total * args.steps / (ms * 1e-3)
+        peak, peak_src = load_peaks()
+        # dominant kernel of this workload: render (K3)
+        dom = int(np.argmax(k_ms))
+        names = ["integrate", "collide", "render"]
+        alg_bytes = [BYTES_K1_PER_BALL_STEP * n_worlds * N_BALLS, _bytes_k2_per_world_step(N_BALLS) * n_worlds,
+                     BYTES_K3_PER_FRAME * n_worlds]
+        achieved = [alg_bytes[i] / (avg_us[i] * 1e-6) / 1e9 if avg_us[i] > 0 else 0.0 for i in range(3)]
+        cpu = cpu_baseline(os.cpu_count() or 1)
+        line = {
+            "metric": "ball_steps_per_sec", "value": value, "unit": "ball-steps/s", "n_gpus": world_size,
+            "steps": args.steps, "warmup": args.warmup, "ms_per_step": ms / max(args.steps, 1),
+            "higher_is_better": True, "scaling": "weak", "vs_baseline": None, "dtype": "f32", "data": "synthetic",
+            "frames_per_sec": fps,
+            "config": {"workload": "configs[3] shard: 131072 worlds/GPU x 8 balls, 64x64 frame rendered every step",
+                       "worlds_total": total_worlds, "balls_per_world": N_BALLS, "canvas": [CANVAS, CANVAS],
+                       "l2": "per-step working set (2 GiB of frames + 70 MB of state per GPU) exceeds the 126 MB L2",
+                       "max_substeps": MAX_SUBSTEPS, "halted_worlds": int(total_worlds - live_total),
+                       "events_per_world_step": events_total / (total_worlds * max(args.steps, 1))},
+            "roofline": {"bound": "hbm", "kernel": names[dom], "achieved": achieved[dom], "peak": peak,
+                         "unit": "GB/s", "frac": achieved[dom] / peak, "traffic": None, "peak_source": peak_src,
+                         "avg_launch_us": float(avg_us[dom]),
+                         "all_kernels": {names[i]: {"avg_launch_us": float(avg_us[i]), "achieved_gbs": achieved[i],
+                                                    "frac": achieved[i] / peak, "algorithmic_bytes_per_launch": alg_bytes[i]}
+                                         for i in range(3)}},
+            "cpu_baseline": cpu,
+            "e2e": {"value": live_total * N_BALLS * e2e_steps / e2e_s, "unit": "ball-steps/s",
+                    "frames_per_sec": live_total * e2e_steps / e2e_s,
+                    "h2d_bytes_per_step": int(h2d), "d2h_bytes_per_step": int(d2h), "steps": e2e_steps,
+                    "api": "WorldBatch.set_walls/set_balls + simulate_host (ppb_simulate_host), pinned host buffers"},
+            "gpu_launches": int(launches_total),
+            "clocks": {"sm_mhz": clk["sm_mhz"], "sm_max_mhz": clk["sm_max_mhz"], "reasons": clk["reasons"]},
+        }
+        print(json.dumps(line), flush=True)
+    if distributed:
+        dist.barrier(device_ids=[local_rank])
+        dist.destroy_process_group()
+
+
+def main():
+    ap = argparse.ArgumentParser()
+    ap.add_argument("--gpus", type=int, default=1)
+    ap.add_argument("--steps", type=int, default=50)
+    ap.add_argument("--warmup", type=int, default=5)
+    ap.add_argument("--impl", default="ours", choices=["ours", "reference"])
+    args = ap.parse_args()
+    if args.warmup < 3 and args.impl == "ours":
+        args.warmup = 3
+    rank = int(os.environ.get("RANK", "0"))
+    local_rank = int(os.environ.get("LOCAL_RANK", "0"))
+    world_size = int(os.environ.get("WORLD_SIZE", "1"))
+    if args.impl == "reference":
+        run_reference(args, rank, world_size)
+    else:
+        run_ours(args, rank, local_rank, world_size)
+
+
+if __name__ == "__main__":
+    main()

@@ -203,9 +203,10 @@ PPB_API int ppb_get_counters(ppb_batch *b, int64_t out[4], void *stream);
  *         4: velocities  [n_worlds][n_balls] x {vx, vy}                             */
 PPB_API int ppb_device_ptr(ppb_batch *b, int32_t which, void **ptr, int64_t *nbytes);
 
-/* time (ms) of the integrate / collide / render kernels summed over the last
- * ppb_step_async call, measured with CUDA events on its stream; valid after the
- * stream has been synchronised.  Enabled by ppb_set_profiling(b, 1). */
+/* time (ms) and launch count of the integrate / collide / render kernels, measured with
+ * CUDA events recorded around every launch on the launching stream and summed over all
+ * stepping calls since ppb_set_profiling(b, 1) / the previous ppb_get_kernel_times (which
+ * waits for the recorded events and resets the accumulation). */
 PPB_API int ppb_set_profiling(ppb_batch *b, int32_t on);
 PPB_API int ppb_get_kernel_times(ppb_batch *b, float ms[3], int32_t launches[3]);
 

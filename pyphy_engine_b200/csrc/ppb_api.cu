@@ -480,7 +480,6 @@ int ppb_step_async(ppb_batch *b, int32_t n_steps, void *traj_dev, uint8_t *frame
   }
   CU(cudaSetDevice(b->cfg.device));
   cudaStream_t st = (cudaStream_t)stream;
-  b->ev_used = 0;
   const size_t frame_bytes = (size_t)b->cfg.n_worlds * b->RL.W * b->RL.H * 4;
   for (int s = 0; s < n_steps; ++s) {
     uint8_t *frame = nullptr;
@@ -502,7 +501,6 @@ int ppb_render_async(ppb_batch *b, uint8_t *frames_dev, void *stream) {
   if (b->RL.W < 1 || b->RL.H < 1) return fail(PPB_E_STATE, "batch was created without a canvas");
   CU(cudaSetDevice(b->cfg.device));
   cudaStream_t st = (cudaStream_t)stream;
-  b->ev_used = 0;
   {
     Prof p(b, st, 2);
     CU(is64(b) ? Launch<double>::render(b->S, b->L, b->RL, b->atlas, frames_dev, st)
@@ -557,7 +555,6 @@ int ppb_simulate_host(ppb_batch *b, int32_t n_steps, float *traj_host, uint8_t *
     b->scr_frames_bytes = need_frames;
     b->scr_chunk = chunk;
   }
-  b->ev_used = 0;
   int done = 0, it = 0;
   while (done < n_steps) {
     const int cur = (n_steps - done < chunk) ? (n_steps - done) : chunk;
@@ -678,6 +675,7 @@ int ppb_get_kernel_times(ppb_batch *b, float ms[3], int32_t launches[3]) {
     ms[kind] += t;
     launches[kind] += 1;
   }
+  b->ev_used = 0;
   return PPB_OK;
 }
 
