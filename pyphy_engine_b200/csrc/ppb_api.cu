@@ -272,6 +272,8 @@ int ppb_create(const ppb_config *cfg, ppb_batch **out) {
       {(void **)&b->S.nev, nw * 4},   {(void **)&b->S.events, (size_t)(cfg->event_capacity > 0 ? cfg->event_capacity : 1) * sizeof(ppb_event)},
       {(void **)&b->S.counters, 8 * sizeof(unsigned long long)},
       {(void **)&b->S.step_base, 16},
+      {(void **)&b->S.list, nw * 4},
+      {(void **)&b->S.list_count, 16},
   };
   for (auto &a : allocs) {
     cudaError_t e = cudaMalloc(a.p, a.bytes ? a.bytes : 16);
@@ -316,7 +318,8 @@ int ppb_destroy(ppb_batch *b) {
   cudaDeviceSynchronize();
   free_scratch(b);
   void *ptrs[] = {b->S.pos, b->S.vel, b->S.aux, b->S.tcol, b->S.rm, b->S.wall, b->S.hdr, b->S.partner,
-                  b->S.nev, b->S.events, b->S.counters, b->S.step_base, b->atlas, b->d_fill8, b->d_stroke8};
+                  b->S.nev, b->S.events, b->S.counters, b->S.step_base, b->S.list, b->S.list_count, b->atlas, b->d_fill8,
+                  b->d_stroke8};
   for (void *p : ptrs)
     if (p) cudaFree(p);
   for (cudaEvent_t e : b->ev_pool) cudaEventDestroy(e);

@@ -127,6 +127,8 @@ struct StatePtrs {
   ppb_event *events;  // [event_capacity]
   unsigned long long *counters;  // [0] events produced [1] collide world-steps [2] collide loop iterations [3] rescans
   int32_t *step_base;            // device scalar: step index of the first step of the running launch group
+  int32_t *list;                 // [n_worlds] worlds the collide kernel takes this step (built by integrate)
+  int32_t *list_count;           // [2] list lengths, indexed by step parity
   long long event_capacity;
   int32_t n_worlds;
 };

@@ -25,10 +25,9 @@ cudaError_t Launch<T>::integrate(const StatePtrs &S, int n_balls, const StepPara
 template <typename T>
 int Launch<T>::collide_grid(int n_worlds, int sm_count) {
   int occ = 0;
-  cudaOccupancyMaxActiveBlocksPerMultiprocessor(&occ, collide_kernel<T>, PPB_COLLIDE_WARPS * 32, 0);
+  cudaOccupancyMaxActiveBlocksPerMultiprocessor(&occ, collide_kernel<T, 4>, PPB_COLLIDE_WARPS * 32, 0);
   if (occ < 1) occ = 1;
-  const int groups = (n_worlds + 31) / 32;
-  const int need = (groups + PPB_COLLIDE_WARPS - 1) / PPB_COLLIDE_WARPS;
+  const int need = (n_worlds + PPB_COLLIDE_WARPS - 1) / PPB_COLLIDE_WARPS;   // at most one world per warp (LW = 32)
   int grid = sm_count * occ;
   if (grid > need) grid = need;
   return grid < 1 ? 1 : grid;
@@ -37,7 +36,14 @@ int Launch<T>::collide_grid(int n_worlds, int sm_count) {
 template <typename T>
 cudaError_t Launch<T>::collide(const StatePtrs &S, const Layout &L, const StepParams &P, void *traj, int grid,
                                cudaStream_t st) {
-  collide_kernel<T><<<grid, PPB_COLLIDE_WARPS * 32, 0, st>>>(S, L, P, (T *)traj);
+  const int nb = L.n_balls;
+  const dim3 blk(PPB_COLLIDE_WARPS * 32);
+  if (nb <= 1) collide_kernel<T, 1><<<grid, blk, 0, st>>>(S, L, P, (T *)traj);
+  else if (nb <= 2) collide_kernel<T, 2><<<grid, blk, 0, st>>>(S, L, P, (T *)traj);
+  else if (nb <= 4) collide_kernel<T, 4><<<grid, blk, 0, st>>>(S, L, P, (T *)traj);
+  else if (nb <= 8) collide_kernel<T, 8><<<grid, blk, 0, st>>>(S, L, P, (T *)traj);
+  else if (nb <= 16) collide_kernel<T, 16><<<grid, blk, 0, st>>>(S, L, P, (T *)traj);
+  else collide_kernel<T, 32><<<grid, blk, 0, st>>>(S, L, P, (T *)traj);
   return cudaGetLastError();
 }
 
@@ -45,10 +51,29 @@ template <typename T>
 cudaError_t Launch<T>::render(const StatePtrs &S, const Layout &L, const RenderLayout &RL, const uint32_t *atlas,
                               uint8_t *frames, cudaStream_t st) {
   const int tiles = ((RL.W + PPB_TILE - 1) / PPB_TILE) * ((RL.H + PPB_TILE - 1) / PPB_TILE);
-  const long long blocks = (long long)S.n_worlds * tiles;
-  if (blocks == 0) return cudaSuccess;
-  if (blocks > 2147483647LL) return cudaErrorInvalidValue;
-  render_kernel<T><<<(unsigned)blocks, 256, 0, st>>>(S, L, RL, atlas, frames);
+  const long long jobs = (long long)S.n_worlds * tiles;
+  if (jobs == 0) return cudaSuccess;
+  // fast path: every wall precedes every ball in the insertion order and rows are 16-byte multiples
+  bool walls_first = true;
+  for (int k = 0; k < L.n_obj; ++k)
+    if (L.order[k] < L.n_walls && k >= L.n_walls) walls_first = false;
+  if (walls_first && (RL.W & 3) == 0) {
+    static int sm_count = 0, occ = 0;
+    if (!sm_count) {
+      int dev = 0;
+      cudaGetDevice(&dev);
+      cudaDeviceGetAttribute(&sm_count, cudaDevAttrMultiProcessorCount, dev);
+      cudaOccupancyMaxActiveBlocksPerMultiprocessor(&occ, render_tile_kernel<T>, PPB_RENDER_WARPS * 32, 0);
+      if (occ < 1) occ = 1;
+    }
+    long long blocks = (jobs + PPB_RENDER_WARPS - 1) / PPB_RENDER_WARPS;
+    const long long cap = (long long)sm_count * occ * 4;   // a few waves: tiles differ in cost
+    if (blocks > cap) blocks = cap;
+    render_tile_kernel<T><<<(unsigned)blocks, PPB_RENDER_WARPS * 32, 0, st>>>(S, L, RL, atlas, frames);
+  } else {
+    if (jobs > 2147483647LL) return cudaErrorInvalidValue;
+    render_general_kernel<T><<<(unsigned)jobs, 256, 0, st>>>(S, L, RL, atlas, frames);
+  }
   return cudaGetLastError();
 }
 

@@ -186,11 +186,28 @@ __device__ inline float quad_pixel_area(const float *qv /*8*/, float px, float p
   return s > 1.f ? 1.f : s;
 }
 
+// ---- packed 8-bit arithmetic (two channels per 32-bit multiply, as pixman does) ----
+__device__ __forceinline__ uint32_t mul_un8x4(uint32_t x, uint32_t a) {
+  uint32_t rb = (x & 0x00ff00ffu) * a + 0x00800080u;
+  rb = ((rb + ((rb >> 8) & 0x00ff00ffu)) >> 8) & 0x00ff00ffu;
+  uint32_t ag = ((x >> 8) & 0x00ff00ffu) * a + 0x00800080u;
+  ag = (ag + ((ag >> 8) & 0x00ff00ffu)) & 0xff00ff00u;
+  return rb | ag;
+}
+// src OVER dst for premultiplied pixels: every channel of the sum is <= 255 because
+// src.c <= src.a and mul(dst.c, 255 - src.a) <= 255 - src.a, so a plain add cannot carry
+__device__ __forceinline__ uint32_t over_fast(uint32_t src, uint32_t dst) {
+  const uint32_t ia = 255u - (src >> 24);
+  if (dst == 0xffffffffu) return src + ia * 0x01010101u;   // white, opaque canvas: mul(255, ia) = ia
+  return src + mul_un8x4(dst, ia);
+}
+
 struct SWall {
   float v[8];        // quad vertices
   float x0, x1, y0, y1;   // bounding box of the quad
   int bx0, bx1, by0, by1; // integer rectangle the reference pastes the sprite into
   int axis;          // 1 = axis-aligned rectangle (coverage separable)
+  int fast;          // axis-aligned with integral y edges: the row pattern is constant between them
   uint32_t col;
 };
 struct SBall {
@@ -202,9 +219,91 @@ struct SBall {
 #define PPB_TILE 64
 
 template <typename T>
-__global__ void __launch_bounds__(256) render_kernel(StatePtrs S, Layout L, RenderLayout RL, const uint32_t *atlas,
-                                                     uint8_t *frames) {
+__device__ __forceinline__ void setup_wall(SWall &s, const T *wv, const RenderWall &rw) {
+  float x0 = 1e30f, x1 = -1e30f, y0 = 1e30f, y1 = -1e30f;
+  double dx0 = 1e300, dy0 = 1e300, dx1 = -1e300, dy1 = -1e300;
+#pragma unroll
+  for (int i = 0; i < 4; ++i) {
+    const double vx = (double)wv[2 * i], vy = (double)wv[2 * i + 1];
+    s.v[2 * i] = (float)vx;
+    s.v[2 * i + 1] = (float)vy;
+    x0 = fminf(x0, (float)vx); x1 = fmaxf(x1, (float)vx);
+    y0 = fminf(y0, (float)vy); y1 = fmaxf(y1, (float)vy);
+    dx0 = fmin(dx0, vx); dx1 = fmax(dx1, vx);
+    dy0 = fmin(dy0, vy); dy1 = fmax(dy1, vy);
+  }
+  s.x0 = x0; s.x1 = x1; s.y0 = y0; s.y1 = y1;
+  int ax = 1;  // axis-aligned when every edge is horizontal or vertical
+#pragma unroll
+  for (int i = 0; i < 4; ++i) {
+    const int j = (i + 1) & 3;
+    if (s.v[2 * i] != s.v[2 * j] && s.v[2 * i + 1] != s.v[2 * j + 1]) ax = 0;
+  }
+  s.axis = ax;
+  s.fast = ax && floorf(y0) == y0 && floorf(y1) == y1;
+  if (rw.kind == 1) {  // Wall.imprint: srcIm[y : y+sz.y, x : x+sz.x] (primitives.py:310-312)
+    s.bx0 = (int)dx0; s.by0 = (int)dy0;
+    s.bx1 = (int)dx1; s.by1 = (int)dy1;
+  } else {             // GenericWall: pos_ rounded, sprite ceil-sized (primitives.py:148-149, 242-245)
+    s.bx0 = (int)round(dx0); s.by0 = (int)round(dy0);
+    s.bx1 = s.bx0 + (int)ceil(dx1 - dx0);
+    s.by1 = s.by0 + (int)ceil(dy1 - dy0);
+  }
+  s.col = rw.rgba8;
+}
+
+template <typename T>
+__device__ __forceinline__ void setup_ball(SBall &s, const StatePtrs &S, const RenderLayout &RL, const uint32_t *atlas,
+                                           int w, int nB, int b) {
   typedef typename Vec2<T>::type T2;
+  const T2 p = reinterpret_cast<const T2 *>(S.pos)[(long long)w * nB + b];
+  const T rad = reinterpret_cast<const T2 *>(S.rm)[(long long)w * nB + b].x;
+  s.sz = 0; s.x0 = 0; s.y0 = 0; s.tex = atlas;
+  const int r = (int)rad;
+  if (rad >= T(0) && r >= RL.r_min && r <= RL.r_max) {
+    const int off = r + RL.s_thick[b];     // floor(sz/2), primitives.py:420
+    s.sz = 2 * off;
+    s.x0 = (int)round((double)p.x) - off;  // x_asint: round half away from zero (geometry.py:25-29)
+    s.y0 = (int)round((double)p.y) - off;
+    s.tex = reinterpret_cast<const uint32_t *>(reinterpret_cast<const uint8_t *>(atlas) +
+                                               (size_t)b * RL.sprite_slot_stride +
+                                               (size_t)(r - RL.r_min) * RL.sprite_stride);
+  }
+}
+
+// 8-bit mask of wall s on pixel (x, y)
+__device__ __forceinline__ uint32_t wall_mask(const SWall &s, int x, int y) {
+  if (x < s.bx0 || x >= s.bx1 || y < s.by0 || y >= s.by1) return 0u;
+  float a;
+  if (s.axis) {
+    const float ox = fminf((float)(x + 1), s.x1) - fmaxf((float)x, s.x0);
+    const float oy = fminf((float)(y + 1), s.y1) - fmaxf((float)y, s.y0);
+    if (ox <= 0.f || oy <= 0.f) return 0u;
+    a = ox * oy;
+  } else {
+    if ((float)(x + 1) <= s.x0 || (float)x >= s.x1 || (float)(y + 1) <= s.y0 || (float)y >= s.y1) return 0u;
+    a = quad_pixel_area(s.v, (float)x, (float)y);
+  }
+  return (uint32_t)floorf(255.f * a + 0.5f);
+}
+__device__ __forceinline__ uint32_t put_wall(const SWall &s, int x, int y, uint32_t c) {
+  const uint32_t m = wall_mask(s, x, y);
+  if (!m) return c;
+  return over_fast(m == 255u ? s.col : mul_un8x4(s.col, m), c);
+}
+__device__ __forceinline__ uint32_t put_ball(const SBall &s, int x, int y, uint32_t c) {
+  const int dy = y - s.y0, dx = x - s.x0;
+  if ((unsigned)dy >= (unsigned)s.sz || (unsigned)dx >= (unsigned)s.sz) return c;
+  const uint32_t t = __ldg(s.tex + dy * s.sz + dx);
+  return (t >> 24) ? over_fast(t, c) : c;
+}
+
+// ------------------------------------------------------------------------------------
+// general rasteriser: any insertion order, any canvas width; one CTA per 64x64 tile
+// ------------------------------------------------------------------------------------
+template <typename T>
+__global__ void __launch_bounds__(256) render_general_kernel(StatePtrs S, Layout L, RenderLayout RL,
+                                                             const uint32_t *atlas, uint8_t *frames) {
   __shared__ SWall sw[PPB_MAX_WALLS];
   __shared__ SBall sb[PPB_MAX_BALLS];
   const int tiles_x = (RL.W + PPB_TILE - 1) / PPB_TILE;
@@ -214,117 +313,111 @@ __global__ void __launch_bounds__(256) render_kernel(StatePtrs S, Layout L, Rend
   const int tile = blockIdx.x - w * tiles;
   const int tx0 = (tile % tiles_x) * PPB_TILE, ty0 = (tile / tiles_x) * PPB_TILE;
   const int nB = L.n_balls, nWl = L.n_walls;
-
-  if (threadIdx.x < nWl) {
-    const int q = threadIdx.x;
-    const T *wv = reinterpret_cast<const T *>(S.wall) + ((long long)w * nWl + q) * 8;
-    SWall s;
-    float x0 = 1e30f, x1 = -1e30f, y0 = 1e30f, y1 = -1e30f;
-    double dx0 = 1e300, dy0 = 1e300, dx1 = -1e300, dy1 = -1e300;
-    for (int i = 0; i < 4; ++i) {
-      const double vx = (double)wv[2 * i], vy = (double)wv[2 * i + 1];
-      s.v[2 * i] = (float)vx;
-      s.v[2 * i + 1] = (float)vy;
-      x0 = fminf(x0, (float)vx); x1 = fmaxf(x1, (float)vx);
-      y0 = fminf(y0, (float)vy); y1 = fmaxf(y1, (float)vy);
-      dx0 = fmin(dx0, vx); dx1 = fmax(dx1, vx);
-      dy0 = fmin(dy0, vy); dy1 = fmax(dy1, vy);
-    }
-    s.x0 = x0; s.x1 = x1; s.y0 = y0; s.y1 = y1;
-    // axis-aligned when every edge is horizontal or vertical
-    int ax = 1;
-    for (int i = 0; i < 4; ++i) {
-      const int j = (i + 1) & 3;
-      if (s.v[2 * i] != s.v[2 * j] && s.v[2 * i + 1] != s.v[2 * j + 1]) ax = 0;
-    }
-    s.axis = ax;
-    if (RL.wall[q].kind == 1) {  // Wall.imprint: srcIm[y : y+sz.y, x : x+sz.x] (primitives.py:310-312)
-      s.bx0 = (int)dx0; s.by0 = (int)dy0;
-      s.bx1 = (int)dx1; s.by1 = (int)dy1;
-    } else {                     // GenericWall: pos_ rounded, sprite ceil-sized (primitives.py:148-149, 242-245)
-      s.bx0 = (int)round(dx0); s.by0 = (int)round(dy0);
-      s.bx1 = s.bx0 + (int)ceil(dx1 - dx0);
-      s.by1 = s.by0 + (int)ceil(dy1 - dy0);
-    }
-    s.col = RL.wall[q].rgba8;
-    sw[q] = s;
-  }
-  if (threadIdx.x >= 32 && threadIdx.x < 32 + nB) {
-    const int b = threadIdx.x - 32;
-    const T2 p = reinterpret_cast<const T2 *>(S.pos)[(long long)w * nB + b];
-    const T rad = reinterpret_cast<const T2 *>(S.rm)[(long long)w * nB + b].x;
-    SBall s;
-    s.sz = 0; s.x0 = 0; s.y0 = 0; s.tex = atlas;
-    const int r = (int)rad;
-    if (rad >= T(0) && r >= RL.r_min && r <= RL.r_max) {
-      const int off = r + RL.s_thick[b];   // floor(sz/2), primitives.py:420
-      s.sz = 2 * off;
-      s.x0 = (int)round((double)p.x) - off;  // x_asint: round half away from zero (geometry.py:25-29)
-      s.y0 = (int)round((double)p.y) - off;
-      s.tex = reinterpret_cast<const uint32_t *>(reinterpret_cast<const uint8_t *>(atlas) +
-                                                 (size_t)b * RL.sprite_slot_stride +
-                                                 (size_t)(r - RL.r_min) * RL.sprite_stride);
-    }
-    sb[b] = s;
-  }
+  if (threadIdx.x < nWl)
+    setup_wall<T>(sw[threadIdx.x], reinterpret_cast<const T *>(S.wall) + ((long long)w * nWl + threadIdx.x) * 8,
+                  RL.wall[threadIdx.x]);
+  if (threadIdx.x >= 32 && threadIdx.x < 32 + nB) setup_ball<T>(sb[threadIdx.x - 32], S, RL, atlas, w, nB, threadIdx.x - 32);
   __syncthreads();
-
-  uint8_t *out = frames + (size_t)w * RL.W * RL.H * 4;
-  const bool vec_ok = (RL.W & 3) == 0;
-  // 64x64 tile = 64 rows x 16 groups of 4 px; 256 threads -> 4 groups each
-  for (int it = 0; it < 4; ++it) {
-    const int gidx = it * 256 + threadIdx.x;
-    const int gy = ty0 + (gidx >> 4);
-    const int gx = tx0 + ((gidx & 15) << 2);
-    if (gy >= RL.H || gx >= RL.W) continue;
-    uint32_t c[4] = {0xffffffffu, 0xffffffffu, 0xffffffffu, 0xffffffffu};
+  uint32_t *out = reinterpret_cast<uint32_t *>(frames) + (size_t)w * RL.W * RL.H;
+  for (int it = threadIdx.x; it < PPB_TILE * PPB_TILE; it += 256) {
+    const int y = ty0 + (it >> 6), x = tx0 + (it & 63);
+    if (y >= RL.H || x >= RL.W) continue;
+    uint32_t c = 0xffffffffu;
     for (int k = 0; k < L.n_obj; ++k) {
       const int q = L.order[k];
-      if (q < nWl) {
-        const SWall &s = sw[q];
-        if ((float)(gy + 1) <= s.y0 || (float)gy >= s.y1 || (float)(gx + 4) <= s.x0 || (float)gx >= s.x1) continue;
-        if (gy < s.by0 || gy >= s.by1) continue;
-        if (s.axis) {
-          const float oy = fminf((float)(gy + 1), s.y1) - fmaxf((float)gy, s.y0);
-#pragma unroll
-          for (int p = 0; p < 4; ++p) {
-            const int x = gx + p;
-            if (x < s.bx0 || x >= s.bx1) continue;
-            const float ox = fminf((float)(x + 1), s.x1) - fmaxf((float)x, s.x0);
-            if (ox <= 0.f) continue;
-            const uint32_t m = (uint32_t)floorf(255.f * ox * oy + 0.5f);
-            if (m) c[p] = over_px(m == 255u ? s.col : in_mask(s.col, m), c[p]);
+      if (q < nWl) c = put_wall(sw[q], x, y, c);
+      else c = put_ball(sb[q - nWl], x, y, c);
+    }
+    out[(size_t)y * RL.W + x] = c;
+  }
+}
+
+// ------------------------------------------------------------------------------------
+// K3 fast path: walls inserted before balls (every DataSaver world) and W % 4 == 0.
+// One warp rasterises one 64x64 tile: lane -> 4 consecutive pixels of one row (128-bit
+// store), 16 lanes per row, two rows per warp store.  The background (white + walls) of a
+// lane's 4 pixels only changes where a wall's y range starts or ends, so it is recomputed
+// at those rows only; balls are composited from the sprite atlas on the rows they cover.
+// ------------------------------------------------------------------------------------
+#define PPB_RENDER_WARPS 8
+struct RenderWarpSmem {
+  SWall w[PPB_MAX_WALLS];
+  SBall b[PPB_MAX_BALLS];
+};
+
+template <typename T>
+__global__ void __launch_bounds__(PPB_RENDER_WARPS * 32) render_tile_kernel(StatePtrs S, Layout L, RenderLayout RL,
+                                                                           const uint32_t *atlas, uint8_t *frames) {
+  __shared__ RenderWarpSmem smem[PPB_RENDER_WARPS];
+  const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
+  RenderWarpSmem &sm = smem[warp];
+  const int tiles_x = (RL.W + PPB_TILE - 1) / PPB_TILE;
+  const int tiles_y = (RL.H + PPB_TILE - 1) / PPB_TILE;
+  const int tiles = tiles_x * tiles_y;
+  const long long total = (long long)S.n_worlds * tiles;
+  const int nB = L.n_balls, nWl = L.n_walls;
+  const int cg = lane & 15, rp = lane >> 4;
+  int w_prev = -1;
+  for (long long job = (long long)blockIdx.x * PPB_RENDER_WARPS + warp; job < total;
+       job += (long long)gridDim.x * PPB_RENDER_WARPS) {
+    const int w = (int)(job / tiles);
+    const int tile = (int)(job - (long long)w * tiles);
+    const int tx0 = (tile % tiles_x) * PPB_TILE, ty0 = (tile / tiles_x) * PPB_TILE;
+    if (w != w_prev) {
+      __syncwarp();
+      if (lane < nWl)
+        setup_wall<T>(sm.w[lane], reinterpret_cast<const T *>(S.wall) + ((long long)w * nWl + lane) * 8, RL.wall[lane]);
+      for (int b = lane; b < nB; b += 32) setup_ball<T>(sm.b[b], S, RL, atlas, w, nB, b);
+      __syncwarp();
+      w_prev = w;
+    }
+    const int x = tx0 + (cg << 2);
+    if (x >= RL.W) continue;
+    // balls whose sprite overlaps this lane's 4 columns
+    uint32_t bmask = 0u;
+    for (int b = 0; b < nB; ++b) {
+      const SBall &s = sm.b[b];
+      if (s.sz > 0 && s.x0 < x + 4 && s.x0 + s.sz > x) bmask |= 1u << b;
+    }
+    uint32_t bg0 = 0xffffffffu, bg1 = bg0, bg2 = bg0, bg3 = bg0;
+    int next_change = -0x7fffffff;
+    uint32_t *out = reinterpret_cast<uint32_t *>(frames) + (size_t)w * RL.W * RL.H;
+    const int y_end = min(ty0 + PPB_TILE, RL.H);
+    for (int y = ty0 + rp; y < y_end; y += 2) {
+      if (y >= next_change) {  // a wall starts or ends at or before this row: rebuild the background
+        bg0 = bg1 = bg2 = bg3 = 0xffffffffu;
+        next_change = 0x7fffffff;
+        for (int q = 0; q < nWl; ++q) {
+          const SWall &s = sm.w[q];
+          int lo, hi;   // rows [lo, hi) can be touched by this wall
+          if (s.fast) { lo = (int)s.y0; hi = (int)s.y1; }
+          else { lo = (int)floorf(s.y0); hi = (int)ceilf(s.y1); }
+          if (y < lo) next_change = min(next_change, lo);
+          else if (y < hi) {
+            next_change = min(next_change, s.fast ? hi : y + 1);
+            bg0 = put_wall(s, x, y, bg0);
+            bg1 = put_wall(s, x + 1, y, bg1);
+            bg2 = put_wall(s, x + 2, y, bg2);
+            bg3 = put_wall(s, x + 3, y, bg3);
           }
-        } else {
-#pragma unroll 1
-          for (int p = 0; p < 4; ++p) {
-            const int x = gx + p;
-            if (x < s.bx0 || x >= s.bx1) continue;
-            const float a = quad_pixel_area(s.v, (float)x, (float)gy);
-            const uint32_t m = (uint32_t)floorf(255.f * a + 0.5f);
-            if (m) c[p] = over_px(m == 255u ? s.col : in_mask(s.col, m), c[p]);
-          }
-        }
-      } else {
-        const SBall &s = sb[q - nWl];
-        const int dy = gy - s.y0;
-        const int dx0 = gx - s.x0;
-        if (dy < 0 || dy >= s.sz || dx0 + 3 < 0 || dx0 >= s.sz) continue;
-        const uint32_t *row = s.tex + dy * s.sz;
-#pragma unroll
-        for (int p = 0; p < 4; ++p) {
-          const int dx = dx0 + p;
-          if (dx < 0 || dx >= s.sz) continue;
-          const uint32_t t = __ldg(row + dx);
-          if (t >> 24) c[p] = over_px(t, c[p]);
         }
       }
-    }
-    uint8_t *dst = out + ((size_t)gy * RL.W + gx) * 4;
-    if (vec_ok) {
-      *reinterpret_cast<uint4 *>(dst) = make_uint4(c[0], c[1], c[2], c[3]);
-    } else {
-      for (int p = 0; p < 4 && gx + p < RL.W; ++p) reinterpret_cast<uint32_t *>(dst)[p] = c[p];
+      uint32_t c0 = bg0, c1 = bg1, c2 = bg2, c3 = bg3;
+      uint32_t m = bmask;
+      while (m) {
+        const int b = __ffs(m) - 1;
+        m &= m - 1;
+        const SBall &s = sm.b[b];
+        const int dy = y - s.y0;
+        if ((unsigned)dy >= (unsigned)s.sz) continue;
+        const uint32_t *row = s.tex + dy * s.sz;
+        const int dx = x - s.x0;
+        if ((unsigned)dx < (unsigned)s.sz) { const uint32_t t = __ldg(row + dx); if (t >> 24) c0 = over_fast(t, c0); }
+        if ((unsigned)(dx + 1) < (unsigned)s.sz) { const uint32_t t = __ldg(row + dx + 1); if (t >> 24) c1 = over_fast(t, c1); }
+        if ((unsigned)(dx + 2) < (unsigned)s.sz) { const uint32_t t = __ldg(row + dx + 2); if (t >> 24) c2 = over_fast(t, c2); }
+        if ((unsigned)(dx + 3) < (unsigned)s.sz) { const uint32_t t = __ldg(row + dx + 3); if (t >> 24) c3 = over_fast(t, c3); }
+      }
+      *reinterpret_cast<uint4 *>(out + (size_t)y * RL.W + x) = make_uint4(c0, c1, c2, c3);
     }
   }
 }

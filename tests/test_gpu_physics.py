@@ -19,13 +19,21 @@ pytestmark = pytest.mark.gpu
 PHYS = load_golden("physics_golden.npz")
 FAIL = load_golden("failure_golden.npz")
 
-# fp32 tolerance: over the first FP32_HORIZON steps (<= ~2 ball-ball contacts per ball at
-# native speeds) 99% of the balls must be within FP32_ABS px of the fp64 oracle and the
-# median error must be below FP32_MED px.  Billiards amplifies rounding noise by roughly
-# an order of magnitude per ball-ball contact, so a longer horizon is not meaningful.
+# fp32 tolerance.  Two populations must be told apart:
+#  (1) worlds in which the fp64 reference itself runs into its freeze quirk (a ball-ball
+#      re-contact whose time of impact is computed as exactly 0, primitives.py:647-650) --
+#      1.4% of 4-ball worlds within 60 steps, 6.4% within 300.  Whether that happens hinges on
+#      the last bit of the fp64 trig evaluation, so no fp32 computation can follow it; the
+#      fp32 engine keeps simulating those worlds.  They are identified from the oracle
+#      (min tCol_ <= 0 at the end of the horizon) and excluded; their share is bounded.
+#  (2) all other worlds: over the first FP32_HORIZON steps 99% of them must stay within
+#      FP32_ABS px of the fp64 oracle (max over balls and steps) and the median error must be
+#      below FP32_MED px.  Billiards amplifies rounding noise by about an order of magnitude
+#      per ball-ball contact, so longer horizons are not meaningful for any fp32 code.
 FP32_HORIZON = 60
-FP32_ABS = 0.25
+FP32_ABS = 0.05
 FP32_MED = 5e-3
+FP32_MAX_FROZEN = 0.03
 
 
 def _batch(case, dtype, n_events=100000, max_substeps=0):
@@ -150,14 +158,17 @@ def test_f32_trajectories_within_tolerance(n_worlds, n_balls, kw):
     traj = traj.cpu().numpy().astype(np.float64)
     otraj, _ = ob.step(FP32_HORIZON, record_traj=True)
     status, _ = wb.get_status()
-    ok = (status == 0) & (ob.status == 0)
-    err = np.abs(traj[:, ok] - otraj[:, ok]).max(axis=(0, 3))      # per world, per ball
+    frozen = ob.tcol.min(axis=1) <= 0                      # the reference's freeze quirk struck
+    assert frozen.mean() < FP32_MAX_FROZEN, frozen.mean()
+    ok = (status == 0) & (ob.status == 0) & ~frozen
+    err = np.abs(traj[:, ok] - otraj[:, ok]).max(axis=(0, 2, 3))      # per world
+    print("fp32 error percentiles (px) p50/p90/p99/p99.9:", np.percentile(err, [50, 90, 99, 99.9]),
+          "frozen in the reference: %.4f" % frozen.mean())
     assert np.median(err) < FP32_MED, np.median(err)
     assert np.mean(err < FP32_ABS) > 0.99, np.mean(err < FP32_ABS)
-    print("fp32 error percentiles (px) p50/p90/p99/p99.9:", np.percentile(err, [50, 90, 99, 99.9]))
-    # single-ball-contact-free prefix is essentially exact
-    err10 = np.abs(traj[:10, ok] - otraj[:10, ok]).max()
-    assert err10 < 0.02, err10
+    # before any ball-ball contact can have been amplified the agreement is at rounding level
+    err10 = np.abs(traj[:10, ok] - otraj[:10, ok]).max(axis=(0, 2, 3))
+    assert np.percentile(err10, 99.5) < 0.01, np.percentile(err10, 99.5)
 
 
 def test_f32_event_counts_statistically_match():

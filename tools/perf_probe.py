@@ -69,9 +69,10 @@ if __name__ == "__main__":
     ap.add_argument("--render", action="store_true")
     ap.add_argument("--native", action="store_true")
     ap.add_argument("--dtype", default="f32")
+    ap.add_argument("--warm", type=int, default=100)
     a = ap.parse_args()
     if a.worlds:
-        run(a.worlds, a.balls, a.steps, a.render, a.dtype, not a.native)
+        run(a.worlds, a.balls, a.steps, a.render, a.dtype, not a.native, a.warm)
     else:
         run(65536, 4, 200, False, "f32", False)
         run(65536, 4, 200, False, "f32", True)
