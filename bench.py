@@ -33,7 +33,7 @@ WORLDS_PER_GPU = 131072
 N_BALLS = 8
 CANVAS = 64
 SEED0 = 20161
-MAX_SUBSTEPS = 256
+MAX_SUBSTEPS = 64
 # algorithmic bytes (fp32 state, RGBA8 frames), SURVEY.md 8(d) / DESIGN.md "Kernels"
 BYTES_K1_PER_BALL_STEP = 32
 BYTES_K3_PER_FRAME = CANVAS * CANVAS * 4

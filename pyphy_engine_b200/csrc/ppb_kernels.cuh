@@ -174,21 +174,10 @@ __device__ __forceinline__ void scan_ball(const WarpSmem<T> &sm, int segbase, in
         wv[2 * j] = u.x;
         wv[2 * j + 1] = u.y;
       }
-      T tw = INF;
-      V2<T> nw = mk<T>(0, 0);
-#pragma unroll
-      for (int e = 0; e < 4; ++e) {
-        const int e1 = (e + 1) & 3;
-        const Toc<T> r = M::edge(pos, vel, rad, mk<T>(wv[2 * e], wv[2 * e + 1]), mk<T>(wv[2 * e1], wv[2 * e1 + 1]));
-        if (r.err) {
-          err = r.err;
-          return;
-        }
-        if (r.t < tw) {
-          tw = r.t;
-          nw = r.n;
-        }
-      }
+      T tw;
+      V2<T> nw;
+      M::wall(pos, vel, rad, wv, tw, nw, err);
+      if (err) return;
       if (tw < tc) {  // primitives.py:729
         tc = tw;
         partner = q;

@@ -132,6 +132,25 @@ struct Compat {
     return o;
   }
 
+  // dynamics.get_toc_ball_wall: the four edges in Bbox order, strict '<' (dynamics.py:17-63)
+  __device__ static void wall(P pos, P vel, T r, const T *wv, T &tw, P &nw, int &err) {
+    tw = Lim<T>::inf();
+    nw = mk<T>(0, 0);
+#pragma unroll 1
+    for (int e = 0; e < 4; ++e) {
+      const int e1 = (e + 1) & 3;
+      const Toc<T> o = edge(pos, vel, r, mk<T>(wv[2 * e], wv[2 * e + 1]), mk<T>(wv[2 * e1], wv[2 * e1 + 1]));
+      if (o.err) {
+        err = o.err;
+        return;
+      }
+      if (o.t < tw) {
+        tw = o.t;
+        nw = o.n;
+      }
+    }
+  }
+
   // dynamics.get_toc_ball_ball (dynamics.py:67-136) + Circle.intersect_moving_circle
   // (geometry.py:400-466)
   __device__ static Toc<T> ball(P pos1, P vel1, T r1, T m1, P pos2, P vel2, T r2, T m2) {
@@ -225,87 +244,85 @@ struct Fast {
     return mk<T>(v.x - k * nrml.x, v.y - k * nrml.y);
   }
 
-  // dynamics.py:20-59 for one edge v0->v1
-  __device__ static Toc<T> edge(P pos, P vel, T r, P v0, P v1) {
-    Toc<T> o;
-    o.t = Lim<T>::inf();
-    o.err = 0;
-    o.has_fv = 0;
-    o.n = mk<T>(0.f, 0.f);
-    o.fv = o.n;
-    float ex = v1.x - v0.x, ey = v1.y - v0.y;
-    float L2 = ex * ex + ey * ey;
-    if (!(L2 > 0.f)) return o;
-    float invL = rsqrtf(L2);
-    float L = L2 * invL;
-    float ux = ex * invL, uy = ey * invL;   // edge direction
-    float px = pos.x - v0.x, py = pos.y - v0.y;
-    float s = px * uy - py * ux;            // signed distance of the centre from the line
-    // unit normal from the ball towards the line; a centre exactly on the line keeps
-    // -get_normal() as the reference does (geometry.py:258-266)
-    float sg = (s < 0.f) ? 1.f : -1.f;
-    float nx = sg * uy, ny = -sg * ux;
-    float speed = vel.x * nx + vel.y * ny;
-    if (speed <= 0.f) return o;
-    if (s == 0.f) {                         // dynamics.py:34
-      o.err = PPB_ST_ASSERT_INTPOINT;
-      return o;
+  // dynamics.get_toc_ball_wall (dynamics.py:8-63) for the four edges of one wall, straight-line
+  // code so that the four edges overlap in the pipeline.  Quantities are kept multiplied by the
+  // edge length L (no normalisation of the edge direction is needed):
+  //   s_un = L * signed distance of the centre from the line,  spu = L * (v . n) with n the
+  //   unit normal from the ball towards the line,  num = L * (|dist| - r),  t = num / spu,
+  //   ufL / ucL = L * (foot / contact point measured along the edge from its first vertex).
+  // The returned normal is not normalised (reflect() divides by its squared length).
+  __device__ __forceinline__ static void wall(P pos, P vel, T r, const T *wv, T &tw, P &nw, int &err) {
+    tw = Lim<T>::inf();
+    nw = mk<T>(0.f, 0.f);
+    int e_err = 0;
+#pragma unroll
+    for (int e = 0; e < 4; ++e) {
+      const int e1 = (e + 1) & 3;
+      const float ex = wv[2 * e1] - wv[2 * e], ey = wv[2 * e1 + 1] - wv[2 * e + 1];
+      const float px = pos.x - wv[2 * e], py = pos.y - wv[2 * e + 1];
+      const float s_un = px * ey - py * ex;
+      const float vn_un = vel.x * ey - vel.y * ex;
+      // a centre exactly on the line keeps -get_normal() as the reference does (geometry.py:258-266)
+      const float sg = (s_un < 0.f) ? 1.f : -1.f;
+      const float spu = sg * vn_un;
+      const float L2 = ex * ex + ey * ey;
+      const float L = sqrtf(L2);
+      const float num = fabsf(s_un) - r * L;
+      const float t = __fdividef(num, spu);
+      const float ufL = px * ex + py * ey;
+      const float ucL = ufL + t * (vel.x * ex + vel.y * ey);
+      const float epsL = 1e-4f * L;
+      const bool appr = (spu > 0.f) && (L2 > 0.f);              // speed <= 0: dynamics.py:25
+      const bool foot_on = (ufL >= -epsL) && (ufL <= L2 + epsL);
+      const bool hit_on = (ucL >= -epsL) && (ucL <= L2 + epsL);  // dynamics.py:52
+      if (e_err == 0 && appr) {
+        if (s_un == 0.f) e_err = PPB_ST_ASSERT_INTPOINT;          // dynamics.py:34
+        else if (num < 0.f && foot_on) e_err = PPB_ST_TRAP_AMISS;  // dynamics.py:38-45
+      }
+      if (e_err == 0 && appr && num >= 0.f && hit_on && t < tw) {
+        tw = t;
+        nw = mk<T>(-sg * ey, sg * ex);
+      }
     }
-    float dc = fabsf(s);
-    float dist = dc - r;
-    float uf = px * ux + py * uy;           // foot of the perpendicular, along the edge
-    const float eps = 1e-4f;
-    if (dist < 0.f) {                       // dynamics.py:38-47
-      if (uf >= -eps && uf <= L + eps) o.err = PPB_ST_TRAP_AMISS;
-      return o;
-    }
-    float t = dist / speed;
-    float uc = uf + t * (vel.x * ux + vel.y * uy);   // contact point along the edge
-    if (!(uc >= -eps && uc <= L + eps)) return o;
-    o.t = t;
-    o.n = mk<T>(-nx, -ny);
-    return o;
+    if (e_err) err = e_err;
   }
 
   // dynamics.py:67-136 + geometry.py:400-466 (smaller root of |p + v t| = R)
-  __device__ static Toc<T> ball(P pos1, P vel1, T r1, T m1, P pos2, P vel2, T r2, T m2) {
+  __device__ __forceinline__ static Toc<T> ball(P pos1, P vel1, T r1, T m1, P pos2, P vel2, T r2, T m2) {
     Toc<T> o;
     o.t = Lim<T>::inf();
     o.err = 0;
     o.has_fv = 0;
     o.n = mk<T>(0.f, 0.f);
     o.fv = o.n;
-    float px = pos2.x - pos1.x, py = pos2.y - pos1.y;
-    float vx = vel2.x - vel1.x, vy = vel2.y - vel1.y;
-    float pv = px * vx + py * vy;
-    if (!(pv < 0.f)) return o;              // speed = -relVel . colDir <= 0
-    float R = r1 + r2;
-    float D2 = px * px + py * py;
-    float D = sqrtf(D2);
-    float gap = D - R;
-    if (gap <= 0.f) {
-      if (gap >= -0.1f) gap = 1e-6f;        // geometry.py:411-412 nudge
-      else {
-        o.err = PPB_ST_ASSERT_OVERLAP;      // geometry.py:413
-        return o;
-      }
+    const float px = pos2.x - pos1.x, py = pos2.y - pos1.y;
+    const float vx = vel2.x - vel1.x, vy = vel2.y - vel1.y;
+    const float pv = px * vx + py * vy;
+    if (!(pv < 0.f)) return o;              // speed = -relVel . colDir <= 0   (dynamics.py:86)
+    const float R = r1 + r2;
+    const float D2 = px * px + py * py;
+    if (D2 < (R - 0.1f) * (R - 0.1f)) {     // geometry.py:413
+      o.err = PPB_ST_ASSERT_OVERLAP;
+      return o;
     }
-    float vv = vx * vx + vy * vy;
-    float cr = px * vy - py * vx;           // |p x v| = (distance of the path from centre 1) * |v|
-    if (cr * cr > R * R * vv) return o;     // geometry.py:416-418 (misses the big circle)
-    // |p|^2 - R^2 with the nudged gap, no cancellation
-    float c = gap * (D + R);
-    float disc = R * R * vv - cr * cr;      // = pv^2 - vv (D^2 - R^2) >= 0 after the test above
-    float t = c / (-pv + sqrtf(disc));
+    const float vv = vx * vx + vy * vy;
+    const float cr = px * vy - py * vx;     // |p x v| = (distance of the path from centre 1) * |v|
+    const float disc = R * R * vv - cr * cr;  // = pv^2 - vv (D^2 - R^2)
+    if (disc < 0.f) return o;               // geometry.py:416-418 (misses the big circle)
+    const float D = sqrtf(D2);
+    float gap = D - R;
+    if (gap <= 0.f) gap = 1e-6f;            // geometry.py:411-412 nudge
+    const float c = gap * (D + R);          // |p|^2 - R^2 without cancellation
+    const float t = c / (-pv + sqrtf(disc));
     // contact: centre of ball 2 relative to ball 1 at time t; unit centre line
     float cx = px + vx * t, cy = py + vy * t;
-    float inv = rsqrtf(cx * cx + cy * cy);
+    const float inv = rsqrtf(cx * cx + cy * cy);
     cx *= inv;
     cy *= inv;
     // exchange of the centre-line components (dynamics.py:97-129)
-    float a1 = vel1.x * cx + vel1.y * cy;
-    float a2 = vel2.x * cx + vel2.y * cy;
-    float k = (2.f * m2 / (m1 + m2)) * (a2 - a1);
+    const float a1 = vel1.x * cx + vel1.y * cy;
+    const float a2 = vel2.x * cx + vel2.y * cy;
+    const float k = (2.f * m2 / (m1 + m2)) * (a2 - a1);
     o.fv = mk<T>(vel1.x + k * cx, vel1.y + k * cy);
     o.has_fv = 1;
     o.n = mk<T>(-cy, cx);

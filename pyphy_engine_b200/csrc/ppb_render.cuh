@@ -146,7 +146,7 @@ static __global__ void build_ball_sprites_kernel(uint32_t *atlas, RenderLayout R
 }
 
 // ---- exact area of (convex quad ∩ pixel [px,px+1]x[py,py+1]) by Sutherland-Hodgman ----
-__device__ inline float quad_pixel_area(const float *qv /*8*/, float px, float py) {
+static __device__ __noinline__ float quad_pixel_area(const float *qv /*8*/, float px, float py) {
   float ax[10], ay[10], bx[10], by[10];
   int n = 4;
   for (int i = 0; i < 4; ++i) {
@@ -298,6 +298,26 @@ __device__ __forceinline__ uint32_t put_ball(const SBall &s, int x, int y, uint3
   return (t >> 24) ? over_fast(t, c) : c;
 }
 
+// wall s composited onto the 4 pixels (x..x+3, y)
+__device__ __forceinline__ void put_wall4(const SWall &s, int x, int y, uint32_t &c0, uint32_t &c1, uint32_t &c2,
+                                          uint32_t &c3) {
+  if (y < s.by0 || y >= s.by1 || x + 4 <= s.bx0 || x >= s.bx1) return;
+  if (s.axis) {
+    const float oy = fminf((float)(y + 1), s.y1) - fmaxf((float)y, s.y0);
+    if (oy <= 0.f) return;
+    if (oy == 1.f && (float)x >= s.x0 && (float)(x + 4) <= s.x1 && x >= s.bx0 && x + 4 <= s.bx1) {
+      // all four pixels fully covered (the common case for an axis-aligned cage)
+      if ((s.col >> 24) == 255u) { c0 = c1 = c2 = c3 = s.col; }
+      else { c0 = over_fast(s.col, c0); c1 = over_fast(s.col, c1); c2 = over_fast(s.col, c2); c3 = over_fast(s.col, c3); }
+      return;
+    }
+  }
+  c0 = put_wall(s, x, y, c0);
+  c1 = put_wall(s, x + 1, y, c1);
+  c2 = put_wall(s, x + 2, y, c2);
+  c3 = put_wall(s, x + 3, y, c3);
+}
+
 // ------------------------------------------------------------------------------------
 // general rasteriser: any insertion order, any canvas width; one CTA per 64x64 tile
 // ------------------------------------------------------------------------------------
@@ -346,7 +366,7 @@ struct RenderWarpSmem {
 };
 
 template <typename T>
-__global__ void __launch_bounds__(PPB_RENDER_WARPS * 32) render_tile_kernel(StatePtrs S, Layout L, RenderLayout RL,
+__global__ void __launch_bounds__(PPB_RENDER_WARPS * 32, 3) render_tile_kernel(StatePtrs S, Layout L, RenderLayout RL,
                                                                            const uint32_t *atlas, uint8_t *frames) {
   __shared__ RenderWarpSmem smem[PPB_RENDER_WARPS];
   const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
@@ -372,52 +392,53 @@ __global__ void __launch_bounds__(PPB_RENDER_WARPS * 32) render_tile_kernel(Stat
       w_prev = w;
     }
     const int x = tx0 + (cg << 2);
-    if (x >= RL.W) continue;
-    // balls whose sprite overlaps this lane's 4 columns
-    uint32_t bmask = 0u;
-    for (int b = 0; b < nB; ++b) {
-      const SBall &s = sm.b[b];
-      if (s.sz > 0 && s.x0 < x + 4 && s.x0 + s.sz > x) bmask |= 1u << b;
-    }
+    // ---- pass 1: background (white + walls), two rows per warp store ----
     uint32_t bg0 = 0xffffffffu, bg1 = bg0, bg2 = bg0, bg3 = bg0;
     int next_change = -0x7fffffff;
     uint32_t *out = reinterpret_cast<uint32_t *>(frames) + (size_t)w * RL.W * RL.H;
     const int y_end = min(ty0 + PPB_TILE, RL.H);
-    for (int y = ty0 + rp; y < y_end; y += 2) {
-      if (y >= next_change) {  // a wall starts or ends at or before this row: rebuild the background
-        bg0 = bg1 = bg2 = bg3 = 0xffffffffu;
-        next_change = 0x7fffffff;
-        for (int q = 0; q < nWl; ++q) {
-          const SWall &s = sm.w[q];
-          int lo, hi;   // rows [lo, hi) can be touched by this wall
-          if (s.fast) { lo = (int)s.y0; hi = (int)s.y1; }
-          else { lo = (int)floorf(s.y0); hi = (int)ceilf(s.y1); }
-          if (y < lo) next_change = min(next_change, lo);
-          else if (y < hi) {
-            next_change = min(next_change, s.fast ? hi : y + 1);
-            bg0 = put_wall(s, x, y, bg0);
-            bg1 = put_wall(s, x + 1, y, bg1);
-            bg2 = put_wall(s, x + 2, y, bg2);
-            bg3 = put_wall(s, x + 3, y, bg3);
+    const int x_end = min(tx0 + PPB_TILE, RL.W);
+    if (x < RL.W) {
+      for (int y = ty0 + rp; y < y_end; y += 2) {
+        if (y >= next_change) {  // a wall starts or ends at or before this row: rebuild the background
+          bg0 = bg1 = bg2 = bg3 = 0xffffffffu;
+          next_change = 0x7fffffff;
+          for (int q = 0; q < nWl; ++q) {
+            const SWall &s = sm.w[q];
+            int lo, hi;   // rows [lo, hi) can be touched by this wall
+            if (s.fast) { lo = (int)s.y0; hi = (int)s.y1; }
+            else { lo = (int)floorf(s.y0); hi = (int)ceilf(s.y1); }
+            if (y < lo) next_change = min(next_change, lo);
+            else if (y < hi) {
+              next_change = min(next_change, s.fast ? hi : y + 1);
+              put_wall4(s, x, y, bg0, bg1, bg2, bg3);
+            }
           }
         }
+        *reinterpret_cast<uint4 *>(out + (size_t)y * RL.W + x) = make_uint4(bg0, bg1, bg2, bg3);
       }
-      uint32_t c0 = bg0, c1 = bg1, c2 = bg2, c3 = bg3;
-      uint32_t m = bmask;
-      while (m) {
-        const int b = __ffs(m) - 1;
-        m &= m - 1;
-        const SBall &s = sm.b[b];
-        const int dy = y - s.y0;
-        if ((unsigned)dy >= (unsigned)s.sz) continue;
-        const uint32_t *row = s.tex + dy * s.sz;
-        const int dx = x - s.x0;
-        if ((unsigned)dx < (unsigned)s.sz) { const uint32_t t = __ldg(row + dx); if (t >> 24) c0 = over_fast(t, c0); }
-        if ((unsigned)(dx + 1) < (unsigned)s.sz) { const uint32_t t = __ldg(row + dx + 1); if (t >> 24) c1 = over_fast(t, c1); }
-        if ((unsigned)(dx + 2) < (unsigned)s.sz) { const uint32_t t = __ldg(row + dx + 2); if (t >> 24) c2 = over_fast(t, c2); }
-        if ((unsigned)(dx + 3) < (unsigned)s.sz) { const uint32_t t = __ldg(row + dx + 3); if (t >> 24) c3 = over_fast(t, c3); }
+    }
+    __syncwarp();
+    // ---- pass 2: ball sprites, composited over what pass 1 wrote (all lanes share one sprite) ----
+    for (int b = 0; b < nB; ++b) {
+      const SBall s = sm.b[b];
+      if (s.sz == 0) continue;
+      const int ax0 = max(s.x0, tx0), ay0 = max(s.y0, ty0);
+      const int ax1 = min(s.x0 + s.sz, x_end), ay1 = min(s.y0 + s.sz, y_end);
+      const int aw = ax1 - ax0, ah = ay1 - ay0;
+      if (aw <= 0 || ah <= 0) continue;
+      const int npx = aw * ah;
+      const float inv_aw = 1.0f / (float)aw;
+      for (int i = lane; i < npx; i += 32) {
+        const int sy = (int)(((float)i + 0.5f) * inv_aw);
+        const int sx = i - sy * aw;
+        const uint32_t t = __ldg(s.tex + (ay0 - s.y0 + sy) * s.sz + (ax0 - s.x0 + sx));
+        if (t >> 24) {
+          uint32_t *p = out + (size_t)(ay0 + sy) * RL.W + (ax0 + sx);
+          *p = over_fast(t, *p);
+        }
       }
-      *reinterpret_cast<uint4 *>(out + (size_t)y * RL.W + x) = make_uint4(c0, c1, c2, c3);
+      __syncwarp();
     }
   }
 }

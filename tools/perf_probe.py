@@ -15,13 +15,13 @@ from pyphy_engine_b200 import sampler  # noqa: E402
 from pyphy_engine_b200.engine import WorldBatch  # noqa: E402
 
 
-def run(n_worlds, n_balls, steps, render, dtype="f32", px64=True, warm=100):
+def run(n_worlds, n_balls, steps, render, dtype="f32", px64=True, warm=100, max_substeps=256):
     kw = sampler.scaled64_params(n_balls) if px64 else {}
     t0 = time.time()
     W = sampler.sample_rect_worlds(n_worlds, n_balls, seed=1, **kw)
     t_sample = time.time() - t0
     canvas = (64, 64) if px64 else (700, 700)
-    wb = WorldBatch(n_worlds, n_balls, 4, dtype=dtype, canvas=canvas, max_substeps=256)
+    wb = WorldBatch(n_worlds, n_balls, 4, dtype=dtype, canvas=canvas, max_substeps=max_substeps)
     wb.set_walls(W["wall"])
     wb.set_balls(W["pos"], W["vel"], W["rad"], W["mass"])
     st = 1 if px64 else 2
@@ -53,11 +53,11 @@ def run(n_worlds, n_balls, steps, render, dtype="f32", px64=True, warm=100):
     cw = c1["collide_world_steps"] - c0["collide_world_steps"]
     it = c1["collide_iterations"] - c0["collide_iterations"]
     print("worlds %d balls %d dtype %s render %d: %.3f ms/step  %.3e ball-steps/s  | K1 %.1f us K2 %.1f us K3 %.1f us | "
-          "collide worlds/step %.1f%%  iters/collide-world %.2f  events/world-step %.3f  halted %d (sample %.1fs)" % (
+          "collide worlds/step %.1f%%  iters/collide-world %.2f  events/world-step %.3f  halted %d %s (sample %.1fs)" % (
               n_worlds, n_balls, dtype, render, ms / steps, n_worlds * n_balls * steps / ms * 1e3,
               1e3 * kms[0] / max(kn[0], 1), 1e3 * kms[1] / max(kn[1], 1), 1e3 * kms[2] / max(kn[2], 1),
               100.0 * cw / (n_worlds * steps), it / max(cw, 1), (c1["events"] - c0["events"]) / (n_worlds * steps),
-              int((status != 0).sum()), t_sample), flush=True)
+              int((status != 0).sum()), np.bincount(status, minlength=10).tolist(), t_sample), flush=True)
     wb.close()
 
 
@@ -70,14 +70,14 @@ if __name__ == "__main__":
     ap.add_argument("--native", action="store_true")
     ap.add_argument("--dtype", default="f32")
     ap.add_argument("--warm", type=int, default=100)
+    ap.add_argument("--max-substeps", type=int, default=256)
     a = ap.parse_args()
     if a.worlds:
-        run(a.worlds, a.balls, a.steps, a.render, a.dtype, not a.native, a.warm)
+        run(a.worlds, a.balls, a.steps, a.render, a.dtype, not a.native, a.warm, a.max_substeps)
     else:
-        run(65536, 4, 200, False, "f32", False)
-        run(65536, 4, 200, False, "f32", True)
-        run(1048576, 4, 100, False, "f32", True)
-        run(131072, 8, 100, False, "f32", True)
-        run(131072, 8, 50, True, "f32", True)
-        run(65536, 4, 100, False, "f64", False)
-        run(16384, 32, 50, False, "f32", False)
+        run(65536, 4, 200, False, "f32", False, 100, 64)
+        run(1048576, 4, 100, False, "f32", True, 100, 64)
+        run(131072, 8, 100, False, "f32", True, 100, 64)
+        run(131072, 8, 100, False, "f32", True, 100, 16)
+        run(131072, 8, 50, True, "f32", True, 100, 64)
+        run(65536, 4, 100, False, "f64", False, 100, 4096)
