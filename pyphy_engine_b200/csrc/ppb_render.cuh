@@ -208,6 +208,7 @@ struct SWall {
   int bx0, bx1, by0, by1; // integer rectangle the reference pastes the sprite into
   int axis;          // 1 = axis-aligned rectangle (coverage separable)
   int fast;          // axis-aligned with integral y edges: the row pattern is constant between them
+  int lo, hi;        // rows [lo, hi) can be touched by this wall
   uint32_t col;
 };
 struct SBall {
@@ -250,6 +251,8 @@ __device__ __forceinline__ void setup_wall(SWall &s, const T *wv, const RenderWa
     s.by1 = s.by0 + (int)ceil(dy1 - dy0);
   }
   s.col = rw.rgba8;
+  s.lo = max((int)floorf(y0), s.by0);
+  s.hi = min((int)ceilf(y1), s.by1);
 }
 
 template <typename T>
@@ -363,7 +366,18 @@ __global__ void __launch_bounds__(256) render_general_kernel(StatePtrs S, Layout
 struct RenderWarpSmem {
   SWall w[PPB_MAX_WALLS];
   SBall b[PPB_MAX_BALLS];
+  uint32_t xm[PPB_MAX_WALLS][32];   // per lane: 8-bit x-coverage of its 4 pixels for every `fast` wall
 };
+
+// solid colour through four packed 8-bit masks
+__device__ __forceinline__ void apply_masks4(uint32_t col, uint32_t xm, uint32_t &c0, uint32_t &c1, uint32_t &c2,
+                                             uint32_t &c3) {
+  uint32_t m;
+  m = xm & 255u;         if (m) c0 = over_fast(m == 255u ? col : mul_un8x4(col, m), c0);
+  m = (xm >> 8) & 255u;  if (m) c1 = over_fast(m == 255u ? col : mul_un8x4(col, m), c1);
+  m = (xm >> 16) & 255u; if (m) c2 = over_fast(m == 255u ? col : mul_un8x4(col, m), c2);
+  m = xm >> 24;          if (m) c3 = over_fast(m == 255u ? col : mul_un8x4(col, m), c3);
+}
 
 template <typename T>
 __global__ void __launch_bounds__(PPB_RENDER_WARPS * 32, 3) render_tile_kernel(StatePtrs S, Layout L, RenderLayout RL,
@@ -393,25 +407,50 @@ __global__ void __launch_bounds__(PPB_RENDER_WARPS * 32, 3) render_tile_kernel(S
     }
     const int x = tx0 + (cg << 2);
     // ---- pass 1: background (white + walls), two rows per warp store ----
-    uint32_t bg0 = 0xffffffffu, bg1 = bg0, bg2 = bg0, bg3 = bg0;
-    int next_change = -0x7fffffff;
     uint32_t *out = reinterpret_cast<uint32_t *>(frames) + (size_t)w * RL.W * RL.H;
     const int y_end = min(ty0 + PPB_TILE, RL.H);
     const int x_end = min(tx0 + PPB_TILE, RL.W);
     if (x < RL.W) {
+      // walls that can touch this lane's 4 columns at all, and for the `fast` ones (axis-aligned,
+      // integral y edges: full row coverage between them) the x-coverage of the 4 pixels
+      uint32_t wmask = 0u;
+      for (int q = 0; q < nWl; ++q) {
+        const SWall &s = sm.w[q];
+        if (s.lo >= s.hi || x + 4 <= s.bx0 || x >= s.bx1 || (float)(x + 4) <= s.x0 || (float)x >= s.x1) continue;
+        wmask |= 1u << q;
+        if (s.fast) {
+          uint32_t xm = 0u;
+#pragma unroll
+          for (int p = 0; p < 4; ++p) {
+            const int xp = x + p;
+            const float ox = fminf((float)(xp + 1), s.x1) - fmaxf((float)xp, s.x0);
+            if (xp >= s.bx0 && xp < s.bx1 && ox > 0.f) xm |= (uint32_t)floorf(255.f * ox + 0.5f) << (8 * p);
+          }
+          sm.xm[q][lane] = xm;
+        }
+      }
+      uint32_t bg0 = 0xffffffffu, bg1 = bg0, bg2 = bg0, bg3 = bg0;
+      int next_change = -0x7fffffff;
       for (int y = ty0 + rp; y < y_end; y += 2) {
         if (y >= next_change) {  // a wall starts or ends at or before this row: rebuild the background
           bg0 = bg1 = bg2 = bg3 = 0xffffffffu;
           next_change = 0x7fffffff;
-          for (int q = 0; q < nWl; ++q) {
+          uint32_t m = wmask;
+          while (m) {
+            const int q = __ffs(m) - 1;
+            m &= m - 1;
             const SWall &s = sm.w[q];
-            int lo, hi;   // rows [lo, hi) can be touched by this wall
-            if (s.fast) { lo = (int)s.y0; hi = (int)s.y1; }
-            else { lo = (int)floorf(s.y0); hi = (int)ceilf(s.y1); }
-            if (y < lo) next_change = min(next_change, lo);
-            else if (y < hi) {
-              next_change = min(next_change, s.fast ? hi : y + 1);
-              put_wall4(s, x, y, bg0, bg1, bg2, bg3);
+            if (y < s.lo) next_change = min(next_change, s.lo);
+            else if (y < s.hi) {
+              if (s.fast) {
+                next_change = min(next_change, s.hi);
+                const uint32_t xm = sm.xm[q][lane];
+                if (xm == 0xffffffffu && (s.col >> 24) == 255u) { bg0 = bg1 = bg2 = bg3 = s.col; }
+                else apply_masks4(s.col, xm, bg0, bg1, bg2, bg3);
+              } else {
+                next_change = y + 1;
+                put_wall4(s, x, y, bg0, bg1, bg2, bg3);
+              }
             }
           }
         }
