@@ -57,19 +57,26 @@ cudaError_t Launch<T>::render(const StatePtrs &S, const Layout &L, const RenderL
   bool walls_first = true;
   for (int k = 0; k < L.n_obj; ++k)
     if (L.order[k] < L.n_walls && k >= L.n_walls) walls_first = false;
-  if (walls_first && (RL.W & 3) == 0) {
-    static int sm_count = 0, occ = 0;
+  if (walls_first && (RL.W & 3) == 0 && (reinterpret_cast<uintptr_t>(frames) & 15u) == 0) {
+    static int sm_count = 0;
+    static_assert(PPB_RENDER_WARPS * sizeof(RenderWarpSmem) <= 227 * 1024, "render tiles exceed the 227 KB of shared memory per CTA");
+    static_assert(sizeof(RenderWarpSmem) % 16 == 0, "tile buffers must stay 16-byte aligned for cp.async.bulk");
+    const int smem = (int)(PPB_RENDER_WARPS * sizeof(RenderWarpSmem));
     if (!sm_count) {
       int dev = 0;
       cudaGetDevice(&dev);
       cudaDeviceGetAttribute(&sm_count, cudaDevAttrMultiProcessorCount, dev);
-      cudaOccupancyMaxActiveBlocksPerMultiprocessor(&occ, render_tile_kernel<T>, PPB_RENDER_WARPS * 32, 0);
-      if (occ < 1) occ = 1;
     }
+    static bool attr_set = false;   // per instantiation (T)
+    if (!attr_set) {
+      cudaError_t e = cudaFuncSetAttribute(render_tile_kernel<T>, cudaFuncAttributeMaxDynamicSharedMemorySize, smem);
+      if (e != cudaSuccess) return e;
+      attr_set = true;
+    }
+    // persistent: one CTA of PPB_RENDER_WARPS warps per SM, every warp walks the tile list
     long long blocks = (jobs + PPB_RENDER_WARPS - 1) / PPB_RENDER_WARPS;
-    const long long cap = (long long)sm_count * occ * 4;   // a few waves: tiles differ in cost
-    if (blocks > cap) blocks = cap;
-    render_tile_kernel<T><<<(unsigned)blocks, PPB_RENDER_WARPS * 32, 0, st>>>(S, L, RL, atlas, frames);
+    if (blocks > sm_count) blocks = sm_count;
+    render_tile_kernel<T><<<(unsigned)blocks, PPB_RENDER_WARPS * 32, smem, st>>>(S, L, RL, atlas, frames);
   } else {
     if (jobs > 2147483647LL) return cudaErrorInvalidValue;
     render_general_kernel<T><<<(unsigned)jobs, 256, 0, st>>>(S, L, RL, atlas, frames);

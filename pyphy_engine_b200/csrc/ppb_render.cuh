@@ -202,11 +202,13 @@ __device__ __forceinline__ uint32_t over_fast(uint32_t src, uint32_t dst) {
   return src + mul_un8x4(dst, ia);
 }
 
-struct SWall {
+struct SWallGeom {
   float v[8];        // quad vertices
   float x0, x1, y0, y1;   // bounding box of the quad
   int bx0, bx1, by0, by1; // integer rectangle the reference pastes the sprite into
   int axis;          // 1 = axis-aligned rectangle (coverage separable)
+};
+struct SWall : SWallGeom {
   int fast;          // axis-aligned with integral y edges: the row pattern is constant between them
   int lo, hi;        // rows [lo, hi) can be touched by this wall
   uint32_t col;
@@ -275,7 +277,7 @@ __device__ __forceinline__ void setup_ball(SBall &s, const StatePtrs &S, const R
 }
 
 // 8-bit mask of wall s on pixel (x, y)
-__device__ __forceinline__ uint32_t wall_mask(const SWall &s, int x, int y) {
+__device__ __forceinline__ uint32_t wall_mask(const SWallGeom &s, int x, int y) {
   if (x < s.bx0 || x >= s.bx1 || y < s.by0 || y >= s.by1) return 0u;
   float a;
   if (s.axis) {
@@ -289,10 +291,10 @@ __device__ __forceinline__ uint32_t wall_mask(const SWall &s, int x, int y) {
   }
   return (uint32_t)floorf(255.f * a + 0.5f);
 }
-__device__ __forceinline__ uint32_t put_wall(const SWall &s, int x, int y, uint32_t c) {
+__device__ __forceinline__ uint32_t put_wall(const SWallGeom &s, uint32_t col, int x, int y, uint32_t c) {
   const uint32_t m = wall_mask(s, x, y);
   if (!m) return c;
-  return over_fast(m == 255u ? s.col : mul_un8x4(s.col, m), c);
+  return over_fast(m == 255u ? col : mul_un8x4(col, m), c);
 }
 __device__ __forceinline__ uint32_t put_ball(const SBall &s, int x, int y, uint32_t c) {
   const int dy = y - s.y0, dx = x - s.x0;
@@ -302,23 +304,23 @@ __device__ __forceinline__ uint32_t put_ball(const SBall &s, int x, int y, uint3
 }
 
 // wall s composited onto the 4 pixels (x..x+3, y)
-__device__ __forceinline__ void put_wall4(const SWall &s, int x, int y, uint32_t &c0, uint32_t &c1, uint32_t &c2,
-                                          uint32_t &c3) {
+__device__ __forceinline__ void put_wall4(const SWallGeom &s, uint32_t col, int x, int y, uint32_t &c0, uint32_t &c1,
+                                          uint32_t &c2, uint32_t &c3) {
   if (y < s.by0 || y >= s.by1 || x + 4 <= s.bx0 || x >= s.bx1) return;
   if (s.axis) {
     const float oy = fminf((float)(y + 1), s.y1) - fmaxf((float)y, s.y0);
     if (oy <= 0.f) return;
     if (oy == 1.f && (float)x >= s.x0 && (float)(x + 4) <= s.x1 && x >= s.bx0 && x + 4 <= s.bx1) {
-      // all four pixels fully covered (the common case for an axis-aligned cage)
-      if ((s.col >> 24) == 255u) { c0 = c1 = c2 = c3 = s.col; }
-      else { c0 = over_fast(s.col, c0); c1 = over_fast(s.col, c1); c2 = over_fast(s.col, c2); c3 = over_fast(s.col, c3); }
+      // all four pixels fully covered
+      if ((col >> 24) == 255u) { c0 = c1 = c2 = c3 = col; }
+      else { c0 = over_fast(col, c0); c1 = over_fast(col, c1); c2 = over_fast(col, c2); c3 = over_fast(col, c3); }
       return;
     }
   }
-  c0 = put_wall(s, x, y, c0);
-  c1 = put_wall(s, x + 1, y, c1);
-  c2 = put_wall(s, x + 2, y, c2);
-  c3 = put_wall(s, x + 3, y, c3);
+  c0 = put_wall(s, col, x, y, c0);
+  c1 = put_wall(s, col, x + 1, y, c1);
+  c2 = put_wall(s, col, x + 2, y, c2);
+  c3 = put_wall(s, col, x + 3, y, c3);
 }
 
 // ------------------------------------------------------------------------------------
@@ -348,7 +350,7 @@ __global__ void __launch_bounds__(256) render_general_kernel(StatePtrs S, Layout
     uint32_t c = 0xffffffffu;
     for (int k = 0; k < L.n_obj; ++k) {
       const int q = L.order[k];
-      if (q < nWl) c = put_wall(sw[q], x, y, c);
+      if (q < nWl) c = put_wall(sw[q], sw[q].col, x, y, c);
       else c = put_ball(sb[q - nWl], x, y, c);
     }
     out[(size_t)y * RL.W + x] = c;
@@ -356,130 +358,274 @@ __global__ void __launch_bounds__(256) render_general_kernel(StatePtrs S, Layout
 }
 
 // ------------------------------------------------------------------------------------
-// K3 fast path: walls inserted before balls (every DataSaver world) and W % 4 == 0.
-// One warp rasterises one 64x64 tile: lane -> 4 consecutive pixels of one row (128-bit
-// store), 16 lanes per row, two rows per warp store.  The background (white + walls) of a
-// lane's 4 pixels only changes where a wall's y range starts or ends, so it is recomputed
-// at those rows only; balls are composited from the sprite atlas on the rows they cover.
+// K3 fast path: walls inserted before balls (every DataSaver world), W % 4 == 0 and a 16-byte
+// aligned frame buffer.
+//
+// One warp owns one 64x64 tile (a whole frame on the 64x64 canvas) at a time and builds it in
+// its private 16 KB of shared memory:
+//   pass 1  background (white + walls): lane -> 4 consecutive pixels of a row (one 128-bit
+//           st.shared, two rows per warp store, conflict-free).  The 4-pixel pattern only
+//           changes where a wall's y range starts or ends, so it is rebuilt at those rows only;
+//   pass 2  ball sprites from the atlas (L1-resident), OVER-composited in place, one ball at a
+//           time in insertion order;
+//   pass 3  the finished tile leaves through the TMA: one cp.async.bulk shared->global of the
+//           whole frame when the tile is the frame (16 KB contiguous), else one bulk copy per
+//           tile row.  The warp starts on its next tile's geometry while the copy engine reads
+//           the buffer, and only waits (cp.async.bulk.wait_group.read) before overwriting it.
+// HBM sees exactly one full-line write per frame byte and a few hundred bytes of state reads.
 // ------------------------------------------------------------------------------------
-#define PPB_RENDER_WARPS 8
+#define PPB_RENDER_WARPS 12
+struct RTBall {      // one ball inside the current tile, already clipped to it (32 bytes)
+  uint32_t tex;      // atlas element index of the first visible sprite pixel
+  uint32_t dst_sz;   // tile element offset of that pixel | sprite side << 16
+  uint32_t aw_ah;    // visible width | visible height << 16   (0 = nothing to draw)
+  float inv_aw;      // 1 / visible width
+  uint32_t dti, ddi; // atlas / tile index step for +32 pixels (dq rows + dr columns)
+  uint32_t wti_wdi;  // extra atlas | tile << 16 step when the column wraps into the next row
+  uint32_t dq_dr;    // 32 / aw | 32 % aw << 16
+};
+// how pass 1 paints a wall inside the current tile
+#define PPB_WM_SKIP 0    // does not touch the tile
+#define PPB_WM_SOLID 1   // axis-aligned, integral edges, opaque colour: every pixel is either the colour or untouched
+#define PPB_WM_FAST 2    // axis-aligned with integral y edges: coverage depends on the column only
+#define PPB_WM_SLOW 3    // anything else: coverage evaluated per pixel
 struct RenderWarpSmem {
-  SWall w[PPB_MAX_WALLS];
-  SBall b[PPB_MAX_BALLS];
-  uint32_t xm[PPB_MAX_WALLS][32];   // per lane: 8-bit x-coverage of its 4 pixels for every `fast` wall
+  uint32_t tile[PPB_TILE * PPB_TILE];   // 16 KB, source of the bulk store
+  int4 wpaint[PPB_MAX_WALLS];           // {PPB_WM_*, colour, first tile row | rows << 16, first column group | groups << 16}
+  int2 wspan[PPB_MAX_WALLS];            // SOLID: tile-local pixel columns [x0, x1)
+  SWallGeom w[PPB_MAX_WALLS];
+  RTBall b[PPB_MAX_BALLS];
 };
 
-// solid colour through four packed 8-bit masks
-__device__ __forceinline__ void apply_masks4(uint32_t col, uint32_t xm, uint32_t &c0, uint32_t &c1, uint32_t &c2,
-                                             uint32_t &c3) {
-  uint32_t m;
-  m = xm & 255u;         if (m) c0 = over_fast(m == 255u ? col : mul_un8x4(col, m), c0);
-  m = (xm >> 8) & 255u;  if (m) c1 = over_fast(m == 255u ? col : mul_un8x4(col, m), c1);
-  m = (xm >> 16) & 255u; if (m) c2 = over_fast(m == 255u ? col : mul_un8x4(col, m), c2);
-  m = xm >> 24;          if (m) c3 = over_fast(m == 255u ? col : mul_un8x4(col, m), c3);
+__device__ __forceinline__ void bulk_store_s2g(void *gdst, const void *ssrc, uint32_t bytes) {
+  asm volatile("cp.async.bulk.global.shared::cta.bulk_group [%0], [%1], %2;" ::"l"(gdst),
+               "r"((uint32_t)__cvta_generic_to_shared(ssrc)), "r"(bytes)
+               : "memory");
 }
+__device__ __forceinline__ void bulk_commit() { asm volatile("cp.async.bulk.commit_group;" ::: "memory"); }
+__device__ __forceinline__ void bulk_wait_read0() { asm volatile("cp.async.bulk.wait_group.read 0;" ::: "memory"); }
+__device__ __forceinline__ void bulk_wait0() { asm volatile("cp.async.bulk.wait_group 0;" ::: "memory"); }
+__device__ __forceinline__ void fence_async_smem() { asm volatile("fence.proxy.async.shared::cta;" ::: "memory"); }
+
+__device__ __forceinline__ int round_half_away_to_int(float v) { return (int)roundf(v); }
+__device__ __forceinline__ int round_half_away_to_int(double v) { return (int)round(v); }
+
+// src OVER dst without the white-canvas shortcut (branch-free; a transparent src leaves dst unchanged)
+__device__ __forceinline__ uint32_t over_nb(uint32_t src, uint32_t dst) { return src + mul_un8x4(dst, 255u - (src >> 24)); }
 
 template <typename T>
-__global__ void __launch_bounds__(PPB_RENDER_WARPS * 32, 3) render_tile_kernel(StatePtrs S, Layout L, RenderLayout RL,
+__global__ void __launch_bounds__(PPB_RENDER_WARPS * 32, 1) render_tile_kernel(StatePtrs S, Layout L, RenderLayout RL,
                                                                            const uint32_t *atlas, uint8_t *frames) {
-  __shared__ RenderWarpSmem smem[PPB_RENDER_WARPS];
+  typedef typename Vec2<T>::type T2;
+  extern __shared__ __align__(128) unsigned char render_smem_raw[];
   const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
-  RenderWarpSmem &sm = smem[warp];
+  RenderWarpSmem &sm = reinterpret_cast<RenderWarpSmem *>(render_smem_raw)[warp];
   const int tiles_x = (RL.W + PPB_TILE - 1) / PPB_TILE;
   const int tiles_y = (RL.H + PPB_TILE - 1) / PPB_TILE;
   const int tiles = tiles_x * tiles_y;
   const long long total = (long long)S.n_worlds * tiles;
   const int nB = L.n_balls, nWl = L.n_walls;
-  const int cg = lane & 15, rp = lane >> 4;
-  int w_prev = -1;
-  for (long long job = (long long)blockIdx.x * PPB_RENDER_WARPS + warp; job < total;
-       job += (long long)gridDim.x * PPB_RENDER_WARPS) {
-    const int w = (int)(job / tiles);
-    const int tile = (int)(job - (long long)w * tiles);
-    const int tx0 = (tile % tiles_x) * PPB_TILE, ty0 = (tile / tiles_x) * PPB_TILE;
-    if (w != w_prev) {
-      __syncwarp();
-      if (lane < nWl)
-        setup_wall<T>(sm.w[lane], reinterpret_cast<const T *>(S.wall) + ((long long)w * nWl + lane) * 8, RL.wall[lane]);
-      for (int b = lane; b < nB; b += 32) setup_ball<T>(sm.b[b], S, RL, atlas, w, nB, b);
-      __syncwarp();
-      w_prev = w;
-    }
-    const int x = tx0 + (cg << 2);
-    // ---- pass 1: background (white + walls), two rows per warp store ----
-    uint32_t *out = reinterpret_cast<uint32_t *>(frames) + (size_t)w * RL.W * RL.H;
-    const int y_end = min(ty0 + PPB_TILE, RL.H);
-    const int x_end = min(tx0 + PPB_TILE, RL.W);
-    if (x < RL.W) {
-      // walls that can touch this lane's 4 columns at all, and for the `fast` ones (axis-aligned,
-      // integral y edges: full row coverage between them) the x-coverage of the 4 pixels
-      uint32_t wmask = 0u;
-      for (int q = 0; q < nWl; ++q) {
-        const SWall &s = sm.w[q];
-        if (s.lo >= s.hi || x + 4 <= s.bx0 || x >= s.bx1 || (float)(x + 4) <= s.x0 || (float)x >= s.x1) continue;
-        wmask |= 1u << q;
-        if (s.fast) {
-          uint32_t xm = 0u;
+  const bool whole_rows = (RL.W == PPB_TILE);   // tile rows are contiguous in the frame
+  // raw state of the world of the current / next tile, held in registers: lane q < nWl keeps wall q's
+  // vertices, lane b keeps ball b's position and radius.  The next tile's loads are issued before the
+  // current tile is drawn, so their latency hides behind the drawing.
+  T wv[8];
+  T2 bp;
+  T brad = T(-1);
 #pragma unroll
-          for (int p = 0; p < 4; ++p) {
-            const int xp = x + p;
-            const float ox = fminf((float)(xp + 1), s.x1) - fmaxf((float)xp, s.x0);
-            if (xp >= s.bx0 && xp < s.bx1 && ox > 0.f) xm |= (uint32_t)floorf(255.f * ox + 0.5f) << (8 * p);
-          }
-          sm.xm[q][lane] = xm;
-        }
-      }
-      uint32_t bg0 = 0xffffffffu, bg1 = bg0, bg2 = bg0, bg3 = bg0;
-      int next_change = -0x7fffffff;
-      for (int y = ty0 + rp; y < y_end; y += 2) {
-        if (y >= next_change) {  // a wall starts or ends at or before this row: rebuild the background
-          bg0 = bg1 = bg2 = bg3 = 0xffffffffu;
-          next_change = 0x7fffffff;
-          uint32_t m = wmask;
-          while (m) {
-            const int q = __ffs(m) - 1;
-            m &= m - 1;
-            const SWall &s = sm.w[q];
-            if (y < s.lo) next_change = min(next_change, s.lo);
-            else if (y < s.hi) {
-              if (s.fast) {
-                next_change = min(next_change, s.hi);
-                const uint32_t xm = sm.xm[q][lane];
-                if (xm == 0xffffffffu && (s.col >> 24) == 255u) { bg0 = bg1 = bg2 = bg3 = s.col; }
-                else apply_masks4(s.col, xm, bg0, bg1, bg2, bg3);
-              } else {
-                next_change = y + 1;
-                put_wall4(s, x, y, bg0, bg1, bg2, bg3);
-              }
-            }
-          }
-        }
-        *reinterpret_cast<uint4 *>(out + (size_t)y * RL.W + x) = make_uint4(bg0, bg1, bg2, bg3);
-      }
+  for (int i = 0; i < 8; ++i) wv[i] = T(0);
+  bp.x = bp.y = T(0);
+  const long long job0 = (long long)blockIdx.x * PPB_RENDER_WARPS + warp;
+  const long long jstride = (long long)gridDim.x * PPB_RENDER_WARPS;
+  if (job0 < total) {
+    const int w0 = (tiles == 1) ? (int)job0 : (int)(job0 / tiles);
+    if (lane < nWl) {
+      const T2 *src = reinterpret_cast<const T2 *>(S.wall) + ((long long)w0 * nWl + lane) * 4;
+#pragma unroll
+      for (int i = 0; i < 4; ++i) { const T2 u = src[i]; wv[2 * i] = u.x; wv[2 * i + 1] = u.y; }
     }
-    __syncwarp();
-    // ---- pass 2: ball sprites, composited over what pass 1 wrote (all lanes share one sprite) ----
-    for (int b = 0; b < nB; ++b) {
-      const SBall s = sm.b[b];
-      if (s.sz == 0) continue;
-      const int ax0 = max(s.x0, tx0), ay0 = max(s.y0, ty0);
-      const int ax1 = min(s.x0 + s.sz, x_end), ay1 = min(s.y0 + s.sz, y_end);
-      const int aw = ax1 - ax0, ah = ay1 - ay0;
-      if (aw <= 0 || ah <= 0) continue;
-      const int npx = aw * ah;
-      const float inv_aw = 1.0f / (float)aw;
-      for (int i = lane; i < npx; i += 32) {
-        const int sy = (int)(((float)i + 0.5f) * inv_aw);
-        const int sx = i - sy * aw;
-        const uint32_t t = __ldg(s.tex + (ay0 - s.y0 + sy) * s.sz + (ax0 - s.x0 + sx));
-        if (t >> 24) {
-          uint32_t *p = out + (size_t)(ay0 + sy) * RL.W + (ax0 + sx);
-          *p = over_fast(t, *p);
-        }
-      }
-      __syncwarp();
+    if (lane < nB) {
+      bp = reinterpret_cast<const T2 *>(S.pos)[(long long)w0 * nB + lane];
+      brad = reinterpret_cast<const T2 *>(S.rm)[(long long)w0 * nB + lane].x;
     }
   }
+  for (long long job = job0; job < total; job += jstride) {
+    int w = (int)job, tx0 = 0, ty0 = 0;
+    if (tiles != 1) {
+      w = (int)(job / tiles);
+      const int tile = (int)(job - (long long)w * tiles);
+      const int tyi = tile / tiles_x;
+      tx0 = (tile - tyi * tiles_x) * PPB_TILE;
+      ty0 = tyi * PPB_TILE;
+    }
+    const int y_end = min(ty0 + PPB_TILE, RL.H);
+    const int x_end = min(tx0 + PPB_TILE, RL.W);
+    // ---- geometry of this tile from the registers, then the loads of the next tile's world ----
+    T cwv[8];
+#pragma unroll
+    for (int i = 0; i < 8; ++i) cwv[i] = wv[i];
+    const T2 cbp = bp;
+    const T cbrad = brad;
+    {
+      const long long nj = job + jstride;
+      if (nj < total) {
+        const int wn = (tiles == 1) ? (int)nj : (int)(nj / tiles);
+        if (wn != w) {
+          if (lane < nWl) {
+            const T2 *src = reinterpret_cast<const T2 *>(S.wall) + ((long long)wn * nWl + lane) * 4;
+#pragma unroll
+            for (int i = 0; i < 4; ++i) { const T2 u = src[i]; wv[2 * i] = u.x; wv[2 * i + 1] = u.y; }
+          }
+          if (lane < nB) {
+            bp = reinterpret_cast<const T2 *>(S.pos)[(long long)wn * nB + lane];
+            brad = reinterpret_cast<const T2 *>(S.rm)[(long long)wn * nB + lane].x;
+          }
+        }
+      }
+    }
+    if (lane < nWl) {
+      SWall s;
+      setup_wall<T>(s, cwv, RL.wall[lane]);
+      // pixels of this tile the wall can touch
+      const int px0 = max(max(s.bx0, (int)floorf(s.x0)), tx0), px1 = min(min(s.bx1, (int)ceilf(s.x1)), x_end);
+      const int r0 = max(s.lo, ty0), r1 = min(s.hi, y_end);
+      int mode = PPB_WM_SLOW;
+      if (px0 >= px1 || r0 >= r1) mode = PPB_WM_SKIP;
+      else if (s.fast)
+        mode = ((s.col >> 24) == 255u && floorf(s.x0) == s.x0 && floorf(s.x1) == s.x1) ? PPB_WM_SOLID : PPB_WM_FAST;
+      const int c0 = (px0 - tx0) >> 2, c1 = (px1 - tx0 + 3) >> 2;
+      sm.w[lane] = static_cast<const SWallGeom &>(s);
+      sm.wpaint[lane] = make_int4(mode, (int)s.col, (r0 - ty0) | ((r1 - r0) << 16), c0 | ((c1 - c0) << 16));
+      sm.wspan[lane] = make_int2(px0 - tx0, px1 - tx0);
+    }
+    if (lane < nB) {
+      const int b = lane;
+      RTBall rec;
+      rec.tex = 0u; rec.dst_sz = 0u; rec.aw_ah = 0u; rec.inv_aw = 0.f;
+      rec.dti = rec.ddi = rec.wti_wdi = rec.dq_dr = 0u;
+      const int r = (int)cbrad;
+      if (cbrad >= T(0) && r >= RL.r_min && r <= RL.r_max) {
+        const int off = r + RL.s_thick[b];                      // floor(sz/2), primitives.py:420
+        const int sz = 2 * off;
+        const int sx0 = round_half_away_to_int(cbp.x) - off;    // x_asint (geometry.py:25-29)
+        const int sy0 = round_half_away_to_int(cbp.y) - off;
+        const int ax0 = max(sx0, tx0), ay0 = max(sy0, ty0);
+        const int aw = min(sx0 + sz, x_end) - ax0, ah = min(sy0 + sz, y_end) - ay0;
+        if (aw > 0 && ah > 0) {
+          rec.tex = (uint32_t)(((size_t)b * RL.sprite_slot_stride + (size_t)(r - RL.r_min) * RL.sprite_stride) >> 2) +
+                    (uint32_t)((ay0 - sy0) * sz + (ax0 - sx0));
+          rec.dst_sz = (uint32_t)((ay0 - ty0) * PPB_TILE + (ax0 - tx0)) | ((uint32_t)sz << 16);
+          rec.aw_ah = (uint32_t)aw | ((uint32_t)ah << 16);
+          const int dq = 32 / aw, dr = 32 - dq * aw;
+          rec.inv_aw = 1.0f / (float)aw;
+          rec.dti = (uint32_t)(dq * sz + dr);
+          rec.ddi = (uint32_t)(dq * PPB_TILE + dr);
+          rec.wti_wdi = (uint32_t)(sz - aw) | ((uint32_t)(PPB_TILE - aw) << 16);
+          rec.dq_dr = (uint32_t)dq | ((uint32_t)dr << 16);
+        }
+      }
+      sm.b[b] = rec;
+    }
+    bulk_wait_read0();   // the copy engine is done reading the tile buffer
+    __syncwarp();
+    // ---- pass 1: background.  White everywhere (rows / columns of the 64x64 buffer outside the
+    //      canvas are written too, they never leave shared memory), then every wall is painted over
+    //      the pixels of its bounding box in insertion order: lane -> (row, 4-pixel group) items ----
+    {
+      uint4 *t4 = reinterpret_cast<uint4 *>(sm.tile) + lane;
+      const uint4 white = make_uint4(0xffffffffu, 0xffffffffu, 0xffffffffu, 0xffffffffu);
+#pragma unroll 8
+      for (int i = 0; i < PPB_TILE / 2; ++i) t4[i * 32] = white;
+    }
+    __syncwarp();
+    for (int q = 0; q < nWl; ++q) {
+      const int4 h = sm.wpaint[q];
+      if (h.x == PPB_WM_SKIP) continue;
+      const uint32_t col = (uint32_t)h.y;
+      const int r0 = h.z & 0xffff, nrows = h.z >> 16, c0 = h.w & 0xffff, ncg = h.w >> 16;
+      const int items = nrows * ncg;
+      const float inv_ncg = __frcp_rn((float)ncg);
+      uint4 *base = reinterpret_cast<uint4 *>(sm.tile) + r0 * 16 + c0;
+      if (h.x == PPB_WM_SOLID) {
+        const int2 span = sm.wspan[q];
+        const uint32_t width = (uint32_t)(span.y - span.x);
+        for (int i = lane; i < items; i += 32) {
+          const int r = (int)(((float)i + 0.5f) * inv_ncg);
+          const int c = i - r * ncg;
+          uint4 *p = base + r * 16 + c;
+          const uint32_t d = (uint32_t)(((c0 + c) << 2) - span.x);   // pixel k of the group is inside iff d + k < width
+          uint4 v = *p;
+          v.x = (d < width) ? col : v.x;
+          v.y = (d + 1u < width) ? col : v.y;
+          v.z = (d + 2u < width) ? col : v.z;
+          v.w = (d + 3u < width) ? col : v.w;
+          *p = v;
+        }
+      } else {
+        const SWallGeom &g = sm.w[q];
+        for (int i = lane; i < items; i += 32) {
+          const int r = (int)(((float)i + 0.5f) * inv_ncg);
+          const int c = i - r * ncg;
+          uint4 *p = base + r * 16 + c;
+          const int x = tx0 + ((c0 + c) << 2), y = ty0 + r0 + r;
+          uint4 v = *p;
+          if (h.x == PPB_WM_FAST) {
+            // full row coverage: the mask of a pixel is its x-overlap with the wall
+            uint32_t m[4];
+#pragma unroll
+            for (int k = 0; k < 4; ++k) {
+              const int xp = x + k;
+              const float ox = fminf((float)(xp + 1), g.x1) - fmaxf((float)xp, g.x0);
+              m[k] = (xp >= g.bx0 && xp < g.bx1 && ox > 0.f) ? (uint32_t)floorf(255.f * ox + 0.5f) : 0u;
+            }
+            v.x = over_nb(mul_un8x4(col, m[0]), v.x);
+            v.y = over_nb(mul_un8x4(col, m[1]), v.y);
+            v.z = over_nb(mul_un8x4(col, m[2]), v.z);
+            v.w = over_nb(mul_un8x4(col, m[3]), v.w);
+          } else {
+            put_wall4(g, col, x, y, v.x, v.y, v.z, v.w);
+          }
+          *p = v;
+        }
+      }
+      __syncwarp();
+    }
+    // ---- pass 2: ball sprites, composited in place in insertion order.  All lanes work on one
+    //      sprite: lane -> pixel (sy, sx) of its visible part, then +32 pixels per iteration ----
+    for (int b = 0; b < nB; ++b) {
+      const uint4 ra = reinterpret_cast<const uint4 *>(&sm.b[b])[0];   // tex, dst_sz, aw_ah, inv_aw
+      if (ra.z == 0u) continue;
+      const uint4 rb = reinterpret_cast<const uint4 *>(&sm.b[b])[1];   // dti, ddi, wti_wdi, dq_dr
+      const int aw = (int)(ra.z & 0xffffu), ah = (int)(ra.z >> 16);
+      const int sz = (int)(ra.y >> 16);
+      int sy = (int)(((float)lane + 0.5f) * __uint_as_float(ra.w));
+      int sx = lane - sy * aw;
+      const int dq = (int)(rb.w & 0xffffu), dr = (int)(rb.w >> 16);
+      uint32_t ti = ra.x + (uint32_t)(sy * sz + sx);                      // atlas element index
+      uint32_t di = (ra.y & 0xffffu) + (uint32_t)(sy * PPB_TILE + sx);    // tile element index
+      const uint32_t wti = rb.z & 0xffffu, wdi = rb.z >> 16;
+      while (sy < ah) {
+        const uint32_t t = __ldg(atlas + ti);
+        sm.tile[di] = over_nb(t, sm.tile[di]);
+        sx += dr; sy += dq; ti += rb.x; di += rb.y;
+        if (sx >= aw) { sx -= aw; ++sy; ti += wti; di += wdi; }
+      }
+      __syncwarp();
+    }
+    // ---- pass 3: tile -> HBM through the copy engine ----
+    fence_async_smem();   // this lane's generic-proxy writes become visible to the async proxy
+    __syncwarp();
+    uint32_t *out = reinterpret_cast<uint32_t *>(frames) + (size_t)w * RL.W * RL.H;
+    if (whole_rows) {
+      if (lane == 0) bulk_store_s2g(out + (size_t)ty0 * RL.W, sm.tile, (uint32_t)(y_end - ty0) * PPB_TILE * 4u);
+    } else {
+      const uint32_t row_bytes = (uint32_t)(x_end - tx0) * 4u;
+      for (int r = lane; r < y_end - ty0; r += 32)
+        bulk_store_s2g(out + (size_t)(ty0 + r) * RL.W + tx0, sm.tile + r * PPB_TILE, row_bytes);
+    }
+    bulk_commit();
+  }
+  bulk_wait0();   // smem must stay valid until the copy engine has read it; writes complete before exit
 }
 
 }  // namespace ppb
