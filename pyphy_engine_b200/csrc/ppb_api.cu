@@ -241,6 +241,14 @@ int ppb_create(const ppb_config *cfg, ppb_batch **out) {
     if (q < nW) b->L.rank_wall[q] = (int16_t)k;
     else b->L.rank_ball[q - nW] = (int16_t)k;
   }
+  b->L.n_items = 0;
+  for (int k = 0; k < nO; ++k) {
+    const int q = b->L.order[k];
+    if (q < nW)
+      for (int e = 0; e < 4; ++e) b->L.item[b->L.n_items++] = (int16_t)((q << 2) | e);
+    else
+      b->L.item[b->L.n_items++] = (int16_t)(0x8000 | (q - nW));
+  }
   // Dynamics.step walks the dynamic objects in ball insertion order (primitives.py:642, 653);
   // slot numbers are that order, so ball ranks must be increasing
   for (int i = 1; i < nB; ++i)

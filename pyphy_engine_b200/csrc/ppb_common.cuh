@@ -111,6 +111,10 @@ struct Layout {
   int16_t order[PPB_MAX_WALLS + PPB_MAX_BALLS];      // insertion sequence -> object index
   int16_t rank_wall[PPB_MAX_WALLS];                  // object -> position in the sequence
   int16_t rank_ball[PPB_MAX_BALLS];
+  // scan items of one ball's time_to_collide_all in visiting order (primitives.py:724-733,
+  // dynamics.py:20): a wall contributes its four edges (wall << 2 | edge), a ball 0x8000 | slot
+  int32_t n_items;
+  int16_t item[PPB_MAX_WALLS * 4 + PPB_MAX_BALLS];
 };
 
 // device state of a batch (raw pointers; T-typed views are made in the kernels)
@@ -128,7 +132,7 @@ struct StatePtrs {
   unsigned long long *counters;  // [0] events produced [1] collide world-steps [2] collide loop iterations [3] rescans
   int32_t *step_base;            // device scalar: step index of the first step of the running launch group
   int32_t *list;                 // [n_worlds] worlds the collide kernel takes this step (built by integrate)
-  int32_t *list_count;           // [2] list lengths, indexed by step parity
+  int32_t *list_count;           // [0..1] list lengths, [2..3] collide work tickets, indexed by step parity
   long long event_capacity;
   int32_t n_worlds;
 };

@@ -126,20 +126,30 @@ __global__ void __launch_bounds__(256) integrate_kernel(StatePtrs S, int n_balls
 // ------------------------------------------------------------------------------------
 // K2: collide
 //
-// One lane per ball, LW = next power of two >= n_balls lanes per world, 32 / LW worlds per
-// warp.  Every lane runs the reference's sequential scan (time_to_collide_all) for its own
-// ball -- objects in insertion order, strict '<', futureVel_ overwritten by every partner --
-// so no cross-lane arg-min is needed; the lanes of a world only exchange ball states
-// (through shared memory) and the step-loop scalars (segmented warp shuffles).
+// One warp advances one world.  The 32 lanes are LB x G: LB = next power of two >= n_balls
+// ball columns, G = 32 / LB groups.  Ball state is replicated in the registers of the G lanes
+// of its column; the time-of-collision scan of a ball (Dynamics.time_to_collide_all,
+// primitives.py:720-733) is spread over its G lanes -- lane (ball i, group g) tests the scan
+// items g, g + G, g + 2G, ... (an item = one wall edge or one other ball, numbered in the
+// reference's visiting order) -- and merged with xor-shuffles:
+//   * collision time: lexicographic (t, item number) minimum == the reference's strict '<'
+//     running minimum (first object / first edge in order wins ties);
+//   * futureVel_: the ball-ball item with the largest number that got as far as writing it
+//     (dynamics.py:129: every candidate partner overwrites it);
+//   * a raised assertion: the item with the smallest number.
+// All step-loop control flow is warp-uniform (one world per warp).  Worlds are handed out
+// through an atomic counter so that a world with a long chain of sub-steps delays only itself.
 // ------------------------------------------------------------------------------------
 template <typename T>
 struct WarpSmem {
   typename Vec2<T>::type pos[32];
   typename Vec2<T>::type vel[32];
   typename Vec2<T>::type rm[32];
+  typename MathOf<T>::type::Edge edge[PPB_MAX_WALLS * 4];
 };
 
 #define PPB_COLLIDE_WARPS 4
+#define PPB_K_NONE 0x7fff
 
 template <typename T, int LW>
 __device__ __forceinline__ T seg_min(T v) {
@@ -151,59 +161,29 @@ __device__ __forceinline__ T seg_min(T v) {
   return v;
 }
 
-// Dynamics.time_to_collide_all (primitives.py:720-733) for the ball held by this lane
-template <typename T>
-__device__ __forceinline__ void scan_ball(const WarpSmem<T> &sm, int segbase, int bi, const Layout &L,
-                                          const T *__restrict__ wallp, V2<T> pos, V2<T> vel, T rad, T mass, T &tc,
-                                          int &partner, V2<T> &nrm, V2<T> &fv, int &err) {
-  typedef typename MathOf<T>::type M;
-  typedef typename Vec2<T>::type T2;
-  const T INF = Lim<T>::inf();
-  const int nWl = L.n_walls;
-  tc = INF;
-  partner = -1;
-  for (int k = 0; k < L.n_obj; ++k) {
-    const int q = L.order[k];
-    if (q < nWl) {
-      // dynamics.get_toc_ball_wall: the four edges of the wall, strict '<' (dynamics.py:20-59)
-      T wv[8];
-      const T2 *wp = reinterpret_cast<const T2 *>(wallp + q * 8);
-#pragma unroll
-      for (int j = 0; j < 4; ++j) {
-        const T2 u = __ldg(wp + j);
-        wv[2 * j] = u.x;
-        wv[2 * j + 1] = u.y;
-      }
-      T tw;
-      V2<T> nw;
-      M::wall(pos, vel, rad, wv, tw, nw, err);
-      if (err) return;
-      if (tw < tc) {  // primitives.py:729
-        tc = tw;
-        partner = q;
-        nrm = nw;
-      }
-    } else {
-      const int b2 = q - nWl;
-      const T2 q2 = sm.rm[segbase + b2];
-      if (b2 == bi || q2.x < T(0)) continue;
-      const T2 p2 = sm.pos[segbase + b2], v2 = sm.vel[segbase + b2];
-      const Toc<T> r = M::ball(pos, vel, rad, mass, mk<T>(p2.x, p2.y), mk<T>(v2.x, v2.y), q2.x, q2.y);
-      if (r.err) {
-        err = r.err;
-        return;
-      }
-      if (r.has_fv) fv = r.fv;  // futureVel_: the last partner in world order wins (dynamics.py:129)
-      if (r.t < tc) {
-        tc = r.t;
-        partner = q;
-        nrm = r.n;
-      }
-    }
-  }
+// minimum over the warp.  fp32: one redux.sync on an order-preserving integer image of the floats
+// (sm_80+); fp64: xor-shuffle tree.  Inputs are never NaN.
+__device__ __forceinline__ float warp_min_all(float v) {
+  const uint32_t b = __float_as_uint(v);
+  const uint32_t key = (b & 0x80000000u) ? ~b : (b | 0x80000000u);
+  const uint32_t m = __reduce_min_sync(0xffffffffu, key);
+  return __uint_as_float((m & 0x80000000u) ? (m & 0x7fffffffu) : ~m);
+}
+__device__ __forceinline__ double warp_min_all(double v) { return seg_min<double, 32>(v); }
+
+// status of the first ball (in order) that raised: every lane of a ball column holds the same err,
+// lanes 0..LB-1 are the balls in order
+template <int LB>
+__device__ __forceinline__ int first_error(int err) {
+  const unsigned em = __ballot_sync(0xffffffffu, err != 0) & (LB == 32 ? 0xffffffffu : ((1u << LB) - 1u));
+  if (em == 0u) return 0;
+  return __shfl_sync(0xffffffffu, err, __ffs(em) - 1);
 }
 
-template <typename T, int LW>
+__device__ __forceinline__ float shfl_xor_t(float v, int o) { return __shfl_xor_sync(0xffffffffu, v, o); }
+__device__ __forceinline__ double shfl_xor_t(double v, int o) { return __shfl_xor_sync(0xffffffffu, v, o); }
+
+template <typename T, int LB>
 __global__ void __launch_bounds__(PPB_COLLIDE_WARPS * 32)
 collide_kernel(StatePtrs S, Layout L, StepParams P, T *traj) {
   typedef typename MathOf<T>::type M;
@@ -214,17 +194,20 @@ collide_kernel(StatePtrs S, Layout L, StepParams P, T *traj) {
   const int warp = threadIdx.x >> 5;
   WarpSmem<T> &sm = smem[warp];
   const unsigned FULL = 0xffffffffu;
-  constexpr int WPW = 32 / LW;                 // worlds per warp
-  const int seg = lane / LW, bi = lane % LW, segbase = seg * LW;
-  const unsigned segmask = (LW == 32 ? FULL : ((1u << LW) - 1u)) << segbase;
-  const int nB = L.n_balls, nWl = L.n_walls;
+  constexpr int G = 32 / LB;                   // lanes per ball
+  const int bi = lane & (LB - 1), grp = lane / LB;
+  const int nB = L.n_balls, nWl = L.n_walls, nItems = L.n_items;
   const uint32_t k = (uint32_t)(*S.step_base + P.step_off);
   const T dt = (T)P.dt;
   const V2<T> g = mk<T>((T)P.gx, (T)P.gy);
   const T INF = Lim<T>::inf();
 
-  if (blockIdx.x == 0 && threadIdx.x == 0) S.list_count[(k + 1u) & 1u] = 0;   // next step's list starts empty
+  if (blockIdx.x == 0 && threadIdx.x == 0) {   // next step's list and ticket counter start empty
+    S.list_count[(k + 1u) & 1u] = 0;
+    S.list_count[2 + ((k + 1u) & 1u)] = 0;
+  }
   const int count = S.list_count[k & 1u];
+  int *ticket = S.list_count + 2 + (k & 1u);
 
   Hdr<T> *hdr = reinterpret_cast<Hdr<T> *>(S.hdr);
   T2 *gpos = reinterpret_cast<T2 *>(S.pos);
@@ -232,28 +215,29 @@ collide_kernel(StatePtrs S, Layout L, StepParams P, T *traj) {
   T2 *grm = reinterpret_cast<T2 *>(S.rm);
   T4 *gaux = reinterpret_cast<T4 *>(S.aux);
   T *gtcol = reinterpret_cast<T *>(S.tcol);
-  const T *gwall = reinterpret_cast<const T *>(S.wall);
+  const T2 *gwall = reinterpret_cast<const T2 *>(S.wall);
 
-  const int n_chunks = (count + WPW - 1) / WPW;
   unsigned long long cnt_iters = 0, cnt_rescans = 0;
+  int idx = 0;
+  if (lane == 0) idx = atomicAdd(ticket, 1);
+  idx = __shfl_sync(FULL, idx, 0);
 
-  for (int chunk = blockIdx.x * PPB_COLLIDE_WARPS + warp; chunk < n_chunks; chunk += gridDim.x * PPB_COLLIDE_WARPS) {
-    const int idx = chunk * WPW + seg;
-    const int w = idx < count ? S.list[idx] : -1;
-    const bool has_ball = w >= 0 && bi < nB;
-    const long long base = (long long)(w < 0 ? 0 : w) * nB;
+  while (idx < count) {
+    int idx_next = 0;
+    if (lane == 0) idx_next = atomicAdd(ticket, 1);   // its latency hides behind this world's work
+    const int w = S.list[idx];
+    const bool has_ball = bi < nB;
+    const long long base = (long long)w * nB;
 
-    // ---- stage the worlds of this warp ----
+    // ---- stage the world: ball state replicated over the G lanes of a ball, wall edges in smem ----
     V2<T> pos = mk<T>(0, 0), vel = pos, nrm = pos, fv = pos;
     T tc = INF, rad = T(-1), mass = T(1);
     int partner = -1;
     uint32_t flags = 0u, nev_base = 0u;
-    if (w >= 0 && bi == 0) {
+    if (lane == 0) {
       flags = hdr[w].flags;
       nev_base = S.nev[w];
     }
-    flags = __shfl_sync(FULL, flags, segbase);
-    nev_base = __shfl_sync(FULL, nev_base, segbase);
     if (has_ball) {
       const T2 p = gpos[base + bi], v = gvel[base + bi], q = grm[base + bi];
       const T4 a = ld4(gaux + base + bi);
@@ -266,15 +250,22 @@ collide_kernel(StatePtrs S, Layout L, StepParams P, T *traj) {
       tc = gtcol[base + bi];
       partner = S.partner[base + bi];
     }
-    {
+    __syncwarp();   // the previous world's readers of sm are done
+    for (int e = lane; e < nWl * 4; e += 32) {
+      const T2 *wp = gwall + ((long long)w * nWl + (e >> 2)) * 4;
+      const T2 a = wp[e & 3], b = wp[(e + 1) & 3];
+      sm.edge[e] = M::make_edge(mk<T>(a.x, a.y), mk<T>(b.x, b.y));
+    }
+    flags = __shfl_sync(FULL, flags, 0);
+    nev_base = __shfl_sync(FULL, nev_base, 0);
+    if (grp == 0) {
       T2 q;
       q.x = rad; q.y = mass;
-      sm.rm[lane] = q;
+      sm.rm[bi] = q;
     }
     const bool active = has_ball && rad >= T(0);
-    const T *wallp = gwall + (long long)(w < 0 ? 0 : w) * nWl * 8;
 
-    bool done = w < 0;
+    bool done = false;
     bool pending = (flags & PPB_FLAG_PENDING) != 0u;
     bool rescanned = false;
     int err = 0, status = 0;
@@ -283,30 +274,80 @@ collide_kernel(StatePtrs S, Layout L, StepParams P, T *traj) {
     int iters = 0;
 
     for (;;) {
-      const bool do_scan = !done && pending;
-      if (__any_sync(FULL, do_scan)) {
+      if (pending) {
         // colQueue_ drain: time_to_collide_all for every ball of the world (primitives.py:634-638)
-        T2 p, v;
-        p.x = pos.x; p.y = pos.y; v.x = vel.x; v.y = vel.y;
         __syncwarp();
-        sm.pos[lane] = p;
-        sm.vel[lane] = v;
-        __syncwarp();
-        if (do_scan) {
-          if (active) scan_ball<T>(sm, segbase, bi, L, wallp, pos, vel, rad, mass, tc, partner, nrm, fv, err);
-          rescanned = true;
-          pending = false;
-          if (bi == 0) ++cnt_rescans;
+        if (grp == 0) {
+          T2 p, v;
+          p.x = pos.x; p.y = pos.y; v.x = vel.x; v.y = vel.y;
+          sm.pos[bi] = p;
+          sm.vel[bi] = v;
         }
+        __syncwarp();
+        tc = INF;
+        partner = -1;
+        int kbest = PPB_K_NONE, kfv = -1, kerr = PPB_K_NONE;
+        V2<T> nb = nrm, fb = fv;
+        if (active) {
+          for (int it = grp; it < nItems; it += G) {
+            const int item = L.item[it];
+            if (item >= 0) {
+              // one edge of dynamics.get_toc_ball_wall (dynamics.py:20-59)
+              T te;
+              V2<T> ne;
+              const int ee = M::edge_toc(pos, vel, rad, sm.edge[item], te, ne);
+              if (ee) {
+                if (kerr == PPB_K_NONE) { kerr = it; err = ee; }
+              } else if (te < tc) {
+                tc = te; kbest = it; partner = item >> 2; nb = ne;
+              }
+            } else {
+              const int b2 = item & 0xff;
+              const T2 q2 = sm.rm[b2];
+              if (b2 == bi || q2.x < T(0)) continue;
+              const T2 p2 = sm.pos[b2], v2 = sm.vel[b2];
+              const Toc<T> r = M::ball(pos, vel, rad, mass, mk<T>(p2.x, p2.y), mk<T>(v2.x, v2.y), q2.x, q2.y);
+              if (r.err) {
+                if (kerr == PPB_K_NONE) { kerr = it; err = r.err; }
+                continue;
+              }
+              if (r.has_fv) { fb = r.fv; kfv = it; }   // futureVel_ (dynamics.py:129)
+              if (r.t < tc) {
+                tc = r.t; kbest = it; partner = nWl + b2; nb = r.n;
+              }
+            }
+          }
+        }
+        // merge the G partial scans of every ball
+#pragma unroll
+        for (int o = LB; o < 32; o <<= 1) {
+          const T ot = shfl_xor_t(tc, o);
+          const int ok = __shfl_xor_sync(FULL, kbest, o), op = __shfl_xor_sync(FULL, partner, o);
+          const T onx = shfl_xor_t(nb.x, o), ony = shfl_xor_t(nb.y, o);
+          if (ot < tc || (ot == tc && ok < kbest)) {
+            tc = ot; kbest = ok; partner = op; nb = mk<T>(onx, ony);
+          }
+          const int okf = __shfl_xor_sync(FULL, kfv, o);
+          const T ofx = shfl_xor_t(fb.x, o), ofy = shfl_xor_t(fb.y, o);
+          if (okf > kfv) { kfv = okf; fb = mk<T>(ofx, ofy); }
+          const int oke = __shfl_xor_sync(FULL, kerr, o), oe = __shfl_xor_sync(FULL, err, o);
+          if (oke < kerr) { kerr = oke; err = oe; }
+        }
+        // an item after a raising one is never visited by the reference; the world halts anyway
+        if (kbest != PPB_K_NONE) nrm = nb;
+        if (kfv >= 0) fv = fb;
+        rescanned = true;
+        pending = false;
+        ++cnt_rescans;
         // the first ball (in order) whose scan raised decides the status
-        const int e = seg_min<int, LW>(err ? ((bi << 8) | err) : 0x7fffffff);
-        if (!done && e != 0x7fffffff) {
-          status = e & 0xff;
+        const int e = first_error<LB>(err);
+        if (e) {
+          status = e;
           done = true;
         }
       }
       // mntCol / t  (primitives.py:641-650)
-      const T m = seg_min<T, LW>(active ? tc : INF);
+      const T m = warp_min_all(active ? tc : INF);   // every group holds the same ball columns
       T t = T(0);
       if (!done) {
         mnt = m;
@@ -318,21 +359,23 @@ collide_kernel(StatePtrs S, Layout L, StepParams P, T *traj) {
           done = true;
         }
       }
-      if (__all_sync(FULL, done)) break;
-      const bool hit = !done && active && (tc <= t);   // step_object, primitives.py:617
-      const unsigned evm = __ballot_sync(FULL, hit);
+      if (done) break;
+      const bool hit = active && (tc <= t);   // step_object, primitives.py:617
+      const unsigned evm = __ballot_sync(FULL, hit && grp == 0);
       if (evm) {
-        // one record per resolve_collision call, in ball order inside each world
-        unsigned long long slot0 = 0;
+        // one record per resolve_collision call, in ball order
+        const int n_ev = __popc(evm);
         if (S.event_capacity > 0) {
-          if (lane == 0) slot0 = atomicAdd(S.counters + 0, (unsigned long long)__popc(evm));
+          unsigned long long slot0 = 0;
+          if (lane == 0) slot0 = atomicAdd(S.counters + 0, (unsigned long long)n_ev);
           slot0 = __shfl_sync(FULL, slot0, 0);
-          if (hit) {
-            const unsigned long long slot = slot0 + __popc(evm & ((1u << lane) - 1u));
+          if (hit && grp == 0) {
+            const int ord = __popc(evm & ((1u << lane) - 1u));
+            const unsigned long long slot = slot0 + ord;
             if ((long long)slot < S.event_capacity) {
               ppb_event ev;
               ev.world = w;
-              ev.seq = (int32_t)(nev_base + nev_local + __popc(evm & segmask & ((1u << lane) - 1u)));
+              ev.seq = (int32_t)(nev_base + nev_local + ord);
               ev.step = (int32_t)k;
               ev.ball = (int16_t)bi;
               ev.partner = (int16_t)partner;
@@ -340,11 +383,10 @@ collide_kernel(StatePtrs S, Layout L, StepParams P, T *traj) {
             }
           }
         }
-        const int n_seg = __popc(evm & segmask);
-        nev_local += n_seg;
-        if (n_seg) pending = true;   // add_all_dynamic_collision_queue, primitives.py:697-700
+        nev_local += n_ev;
+        pending = true;   // add_all_dynamic_collision_queue, primitives.py:697-700
       }
-      if (!done && active) {
+      if (active) {
         if (hit) {  // resolve_collision, primitives.py:659-681
           if (!(tc == t)) err = PPB_ST_ASSERT_TCOL_EQ;
           move_ball(pos, vel, tc, g);
@@ -359,20 +401,18 @@ collide_kernel(StatePtrs S, Layout L, StepParams P, T *traj) {
         }
       }
       {
-        const int e = seg_min<int, LW>(err ? ((bi << 8) | err) : 0x7fffffff);
-        if (!done && e != 0x7fffffff) {
-          status = e & 0xff;
-          done = true;
+        const int e = first_error<LB>(err);
+        if (e) {
+          status = e;
+          break;
         }
       }
-      if (!done) {
-        tStep += t;
-        if (bi == 0) ++cnt_iters;
-      }
+      tStep += t;
+      ++cnt_iters;
     }
 
-    // ---- write back ----
-    if (has_ball) {
+    // ---- write back (the group-0 lane of every ball) ----
+    if (has_ball && grp == 0) {
       T2 p, v;
       p.x = pos.x; p.y = pos.y; v.x = vel.x; v.y = vel.y;
       gpos[base + bi] = p;
@@ -386,7 +426,7 @@ collide_kernel(StatePtrs S, Layout L, StepParams P, T *traj) {
       }
       if (traj) reinterpret_cast<T2 *>(traj)[((long long)P.step_off * S.n_worlds + w) * nB + bi] = p;
     }
-    if (w >= 0 && bi == 0) {
+    if (lane == 0) {
       Hdr<T> o;
       memset(&o, 0, sizeof o);
       o.tmin = mnt;
@@ -396,15 +436,9 @@ collide_kernel(StatePtrs S, Layout L, StepParams P, T *traj) {
       if (nev_local) S.nev[w] = nev_base + nev_local;
       if (S.event_capacity <= 0 && nev_local) atomicAdd(S.counters + 0, (unsigned long long)nev_local);
     }
-    __syncwarp();
+    idx = __shfl_sync(FULL, idx_next, 0);
   }
-  // per-warp statistics
-  cnt_iters = cnt_iters;
-#pragma unroll
-  for (int o = 16; o > 0; o >>= 1) {
-    cnt_iters += __shfl_xor_sync(FULL, cnt_iters, o);
-    cnt_rescans += __shfl_xor_sync(FULL, cnt_rescans, o);
-  }
+  // per-warp statistics (every lane counted the same)
   if (lane == 0 && (cnt_iters | cnt_rescans)) {
     atomicAdd(S.counters + 2, cnt_iters);
     atomicAdd(S.counters + 3, cnt_rescans);

@@ -25,9 +25,9 @@ cudaError_t Launch<T>::integrate(const StatePtrs &S, int n_balls, const StepPara
 template <typename T>
 int Launch<T>::collide_grid(int n_worlds, int sm_count) {
   int occ = 0;
-  cudaOccupancyMaxActiveBlocksPerMultiprocessor(&occ, collide_kernel<T, 4>, PPB_COLLIDE_WARPS * 32, 0);
+  cudaOccupancyMaxActiveBlocksPerMultiprocessor(&occ, collide_kernel<T, 8>, PPB_COLLIDE_WARPS * 32, 0);
   if (occ < 1) occ = 1;
-  const int need = (n_worlds + PPB_COLLIDE_WARPS - 1) / PPB_COLLIDE_WARPS;   // at most one world per warp (LW = 32)
+  const int need = (n_worlds + PPB_COLLIDE_WARPS - 1) / PPB_COLLIDE_WARPS;   // one world per warp at a time
   int grid = sm_count * occ;
   if (grid > need) grid = need;
   return grid < 1 ? 1 : grid;

@@ -151,6 +151,24 @@ struct Compat {
     }
   }
 
+  // one scan item of the collide kernel = one wall edge, staged in shared memory
+  struct Edge {
+    P v0, v1;
+  };
+  __device__ __forceinline__ static Edge make_edge(P v0, P v1) {
+    Edge e;
+    e.v0 = v0;
+    e.v1 = v1;
+    return e;
+  }
+  // returns the PPB_ST_* the reference would raise (0 = none); t = +inf when the edge is not hit
+  __device__ __forceinline__ static int edge_toc(P pos, P vel, T r, const Edge &e, T &t, P &n) {
+    const Toc<T> o = edge(pos, vel, r, e.v0, e.v1);
+    t = o.t;
+    n = o.n;
+    return o.err;
+  }
+
   // dynamics.get_toc_ball_ball (dynamics.py:67-136) + Circle.intersect_moving_circle
   // (geometry.py:400-466)
   __device__ static Toc<T> ball(P pos1, P vel1, T r1, T m1, P pos2, P vel2, T r2, T m2) {
@@ -285,6 +303,49 @@ struct Fast {
       }
     }
     if (e_err) err = e_err;
+  }
+
+  // one scan item of the collide kernel = one wall edge, staged in shared memory with the
+  // quantities that do not depend on the ball
+  struct __align__(16) Edge {
+    float x0, y0;    // first vertex
+    float ex, ey;    // edge vector
+    float L, L2;     // its length and squared length
+    float epsL;      // on-segment tolerance scaled by L (1e-4 L)
+    float pad;
+  };
+  __device__ __forceinline__ static Edge make_edge(P v0, P v1) {
+    Edge e;
+    e.x0 = v0.x; e.y0 = v0.y;
+    e.ex = v1.x - v0.x; e.ey = v1.y - v0.y;
+    e.L2 = e.ex * e.ex + e.ey * e.ey;
+    e.L = sqrtf(e.L2);
+    e.epsL = 1e-4f * e.L;
+    e.pad = 0.f;
+    return e;
+  }
+  // same arithmetic as one iteration of wall() above
+  __device__ __forceinline__ static int edge_toc(P pos, P vel, T r, const Edge &e, T &t_out, P &n) {
+    const float px = pos.x - e.x0, py = pos.y - e.y0;
+    const float s_un = px * e.ey - py * e.ex;
+    const float vn_un = vel.x * e.ey - vel.y * e.ex;
+    const float sg = (s_un < 0.f) ? 1.f : -1.f;
+    const float spu = sg * vn_un;
+    const float num = fabsf(s_un) - r * e.L;
+    const float t = __fdividef(num, spu);
+    const float ufL = px * e.ex + py * e.ey;
+    const float ucL = ufL + t * (vel.x * e.ex + vel.y * e.ey);
+    const bool appr = (spu > 0.f) && (e.L2 > 0.f);                    // speed <= 0: dynamics.py:25
+    const bool foot_on = (ufL >= -e.epsL) && (ufL <= e.L2 + e.epsL);
+    const bool hit_on = (ucL >= -e.epsL) && (ucL <= e.L2 + e.epsL);    // dynamics.py:52
+    t_out = Lim<T>::inf();
+    n = mk<T>(-sg * e.ey, sg * e.ex);
+    if (appr) {
+      if (s_un == 0.f) return PPB_ST_ASSERT_INTPOINT;          // dynamics.py:34
+      if (num < 0.f && foot_on) return PPB_ST_TRAP_AMISS;      // dynamics.py:38-45
+      if (num >= 0.f && hit_on) t_out = t;
+    }
+    return 0;
   }
 
   // dynamics.py:67-136 + geometry.py:400-466 (smaller root of |p + v t| = R)
