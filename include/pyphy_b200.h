@@ -164,6 +164,16 @@ PPB_API int ppb_get_status(ppb_batch *b, int32_t world0, int32_t count, int32_t 
 PPB_API int ppb_set_styles(ppb_batch *b, const ppb_ball_style *balls /*[n_balls]*/,
                    const ppb_wall_style *walls /*[n_walls]*/, int32_t r_min, int32_t r_max, void *stream);
 
+/* get_ball_im (primitives.py:33-61): copies the pre-rendered sprite of ball slot `slot` at integer
+ * radius `radius` to `out_host`: [sz][sz][4] uint8 with sz = 2*(radius + s_thick), premultiplied
+ * alpha, channel order Color.r, Color.g, Color.b, alpha.  *sz_out receives sz. */
+PPB_API int ppb_read_sprite(ppb_batch *b, int32_t slot, int32_t radius, uint8_t *out_host, int64_t cap_bytes,
+                    int32_t *sz_out, void *stream);
+
+/* Dynamics.set_g (primitives.py:566): replaces the gravity vector; collision caches are left alone
+ * exactly as the reference does. */
+PPB_API int ppb_set_gravity(ppb_batch *b, double gx, double gy);
+
 /* n_steps x Dynamics.step() (primitives.py:628-656) for every world, asynchronous.
  *   traj_dev   : NULL or [n_steps][n_worlds][n_balls][2] in the batch dtype -- the
  *                positions after each step (what dataio.py:123-128 records)
@@ -172,6 +182,18 @@ PPB_API int ppb_set_styles(ppb_batch *b, const ppb_ball_style *balls /*[n_balls]
  *                (primitives.py:991-1008, dataio.py:119-120)                       */
 PPB_API int ppb_step_async(ppb_batch *b, int32_t n_steps, void *traj_dev, uint8_t *frames_dev,
                    int32_t render_every, void *stream);
+
+/* Drains the collision queue without stepping: Dynamics.time_to_collide_all (primitives.py:720-733)
+ * for every ball of every world whose queue is non-empty (after ppb_set_balls / ppb_requeue), i.e.
+ * dynamics.get_toc_ball_wall / get_toc_ball_ball (dynamics.py:8-136) against every other object.
+ * Positions, velocities and step counters are unchanged; results are read with
+ * ppb_get_collision_cache / ppb_get_collision_response.  Asynchronous. */
+PPB_API int ppb_scan_async(ppb_batch *b, void *stream);
+
+/* Dynamics.nrmlCol_ (primitives.py:550; for a ball partner the contact tangent, dynamics.py:95) and
+ * Ball.futureVel_ (dynamics.py:129): [count][n_balls][2] each, may be NULL */
+PPB_API int ppb_get_collision_response(ppb_batch *b, int32_t world0, int32_t count, double *nrml, double *future_vel,
+                               void *stream);
 
 /* World.generate_image() of the current state: [n_worlds][H][W][4] uint8, asynchronous */
 PPB_API int ppb_render_async(ppb_batch *b, uint8_t *frames_dev, void *stream);

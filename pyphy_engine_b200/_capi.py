@@ -74,7 +74,11 @@ SIGNATURES = {
     "ppb_get_collision_cache": (ctypes.c_int, [_vp, _i32, _i32, _dp, _ip, _vp]),
     "ppb_get_status": (ctypes.c_int, [_vp, _i32, _i32, _ip, _ip, _vp]),
     "ppb_set_styles": (ctypes.c_int, [_vp, ctypes.POINTER(BallStyle), ctypes.POINTER(WallStyle), _i32, _i32, _vp]),
+    "ppb_read_sprite": (ctypes.c_int, [_vp, _i32, _i32, _vp, _i64, _ip, _vp]),
+    "ppb_set_gravity": (ctypes.c_int, [_vp, ctypes.c_double, ctypes.c_double]),
     "ppb_step_async": (ctypes.c_int, [_vp, _i32, _vp, _vp, _i32, _vp]),
+    "ppb_scan_async": (ctypes.c_int, [_vp, _vp]),
+    "ppb_get_collision_response": (ctypes.c_int, [_vp, _i32, _i32, _dp, _dp, _vp]),
     "ppb_render_async": (ctypes.c_int, [_vp, _vp, _vp]),
     "ppb_simulate_host": (ctypes.c_int, [_vp, _i32, _vp, _vp, _i32, _vp]),
     "ppb_read_events": (ctypes.c_int, [_vp, ctypes.POINTER(Event), _i64, ctypes.POINTER(_i64), _vp]),

@@ -261,6 +261,7 @@ int ppb_create(const ppb_config *cfg, ppb_batch **out) {
   b->P.gy = cfg->gy;
   b->P.friction = cfg->friction;
   b->P.step_off = 0;
+  b->P.scan_only = 0;
   b->P.max_substeps = cfg->max_substeps > 0 ? cfg->max_substeps : (1 << 20);
   b->esz = is64(b) ? 8 : 4;
   CU(cudaDeviceGetAttribute(&b->sm_count, cudaDevAttrMultiProcessorCount, cfg->device));
@@ -480,6 +481,35 @@ int ppb_set_styles(ppb_batch *b, const ppb_ball_style *balls, const ppb_wall_sty
   return PPB_OK;
 }
 
+int ppb_read_sprite(ppb_batch *b, int32_t slot, int32_t radius, uint8_t *out_host, int64_t cap_bytes, int32_t *sz_out,
+                    void *stream) {
+  if (!b) return fail(PPB_E_INVALID, "null batch");
+  if (!b->styles_set) return fail(PPB_E_STATE, "ppb_set_styles must be called first");
+  if (slot < 0 || slot >= b->cfg.n_balls) return fail(PPB_E_INVALID, "ball slot %d out of range", slot);
+  if (radius < b->RL.r_min || radius > b->RL.r_max)
+    return fail(PPB_E_INVALID, "radius %d outside the sprite range [%d, %d]", radius, b->RL.r_min, b->RL.r_max);
+  const int sz = 2 * (radius + b->RL.s_thick[slot]);
+  if (sz_out) *sz_out = sz;
+  const size_t bytes = (size_t)sz * sz * 4;
+  if (!out_host) return PPB_OK;
+  if ((int64_t)bytes > cap_bytes) return fail(PPB_E_INVALID, "sprite needs %zu bytes, buffer has %lld", bytes, (long long)cap_bytes);
+  CU(cudaSetDevice(b->cfg.device));
+  const uint8_t *src = reinterpret_cast<const uint8_t *>(b->atlas) + (size_t)slot * b->RL.sprite_slot_stride +
+                       (size_t)(radius - b->RL.r_min) * b->RL.sprite_stride;
+  CU(cudaMemcpyAsync(out_host, src, bytes, cudaMemcpyDeviceToHost, (cudaStream_t)stream));
+  CU(cudaStreamSynchronize((cudaStream_t)stream));
+  return PPB_OK;
+}
+
+int ppb_set_gravity(ppb_batch *b, double gx, double gy) {
+  if (!b) return fail(PPB_E_INVALID, "null batch");
+  b->P.gx = gx;
+  b->P.gy = gy;
+  b->cfg.gx = gx;
+  b->cfg.gy = gy;
+  return PPB_OK;
+}
+
 int ppb_step_async(ppb_batch *b, int32_t n_steps, void *traj_dev, uint8_t *frames_dev, int32_t render_every,
                    void *stream) {
   if (!b) return fail(PPB_E_INVALID, "null batch");
@@ -502,6 +532,38 @@ int ppb_step_async(ppb_batch *b, int32_t n_steps, void *traj_dev, uint8_t *frame
     CU(launch_advance_step_base(b->S.step_base, n_steps, st));
     ++b->launches;
     b->host_step += n_steps;
+  }
+  return PPB_OK;
+}
+
+int ppb_scan_async(ppb_batch *b, void *stream) {
+  if (!b) return fail(PPB_E_INVALID, "null batch");
+  CU(cudaSetDevice(b->cfg.device));
+  cudaStream_t st = (cudaStream_t)stream;
+  StepParams P = b->P;
+  P.step_off = 0;
+  P.scan_only = 1;
+  CU(is64(b) ? Launch<double>::list_pending(b->S, st) : Launch<float>::list_pending(b->S, st));
+  CU(is64(b) ? Launch<double>::collide(b->S, b->L, P, nullptr, b->collide_grid, st)
+             : Launch<float>::collide(b->S, b->L, P, nullptr, b->collide_grid, st));
+  // the collide kernel zeroed the other parity's list; this one must be empty again for the next step
+  CU(cudaMemsetAsync(b->S.list_count, 0, 4 * sizeof(int32_t), st));
+  b->launches += 2;
+  return PPB_OK;
+}
+
+int ppb_get_collision_response(ppb_batch *b, int32_t world0, int32_t count, double *nrml, double *future_vel,
+                               void *stream) {
+  int rc = check_range(b, world0, count);
+  if (rc) return rc;
+  CU(cudaSetDevice(b->cfg.device));
+  cudaStream_t st = (cudaStream_t)stream;
+  const size_t nB = (size_t)b->cfg.n_balls, n = (size_t)count * nB, off = (size_t)world0 * nB;
+  std::vector<double> aux(n * 4);
+  if ((rc = download(b, b->S.aux, off * 4, aux.data(), n * 4, st))) return rc;
+  for (size_t i = 0; i < n; ++i) {
+    if (nrml) { nrml[2 * i] = aux[4 * i]; nrml[2 * i + 1] = aux[4 * i + 1]; }
+    if (future_vel) { future_vel[2 * i] = aux[4 * i + 2]; future_vel[2 * i + 1] = aux[4 * i + 3]; }
   }
   return PPB_OK;
 }

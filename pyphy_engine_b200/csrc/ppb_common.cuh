@@ -141,6 +141,7 @@ struct StepParams {
   double dt, gx, gy, friction;
   int32_t step_off;   // this launch advances step (*step_base + step_off)
   int32_t max_substeps;
+  int32_t scan_only;  // collide kernel: drain the collision queue (rescan every ball) and stop; nothing moves
 };
 
 // ---- render ----

@@ -346,6 +346,10 @@ collide_kernel(StatePtrs S, Layout L, StepParams P, T *traj) {
           done = true;
         }
       }
+      if (P.scan_only) {   // ppb_scan_async: the caches are up to date, nothing moves
+        if (!done) mnt = warp_min_all(active ? tc : INF);
+        break;
+      }
       // mntCol / t  (primitives.py:641-650)
       const T m = warp_min_all(active ? tc : INF);   // every group holds the same ball columns
       T t = T(0);
@@ -430,7 +434,7 @@ collide_kernel(StatePtrs S, Layout L, StepParams P, T *traj) {
       Hdr<T> o;
       memset(&o, 0, sizeof o);
       o.tmin = mnt;
-      o.step = status ? k : k + 1u;  // a halted world keeps the index of the step it raised in
+      o.step = (status || P.scan_only) ? k : k + 1u;  // a halted world keeps the index of the step it raised in
       o.flags = status ? ((uint32_t)status << 8) : (pending ? PPB_FLAG_PENDING : 0u);
       hdr[w] = o;
       if (nev_local) S.nev[w] = nev_base + nev_local;
@@ -444,6 +448,17 @@ collide_kernel(StatePtrs S, Layout L, StepParams P, T *traj) {
     atomicAdd(S.counters + 3, cnt_rescans);
   }
   if (blockIdx.x == 0 && threadIdx.x == 0 && count > 0) atomicAdd(S.counters + 1, (unsigned long long)count);
+}
+
+// ppb_scan_async: every running world whose collision queue is non-empty goes on the collide list
+template <typename T>
+__global__ void list_pending_kernel(StatePtrs S, int step_off) {
+  const int w = blockIdx.x * blockDim.x + threadIdx.x;
+  if (w >= S.n_worlds) return;
+  const Hdr<T> h = reinterpret_cast<const Hdr<T> *>(S.hdr)[w];
+  const uint32_t k = (uint32_t)(*S.step_base + step_off);
+  if (PPB_STATUS_OF(h.flags) == 0u && (h.flags & PPB_FLAG_PENDING) && h.step == k)
+    S.list[atomicAdd(S.list_count + (k & 1u), 1)] = w;
 }
 
 // advance the device-side step counter after a group of step launches

@@ -13,6 +13,7 @@ struct Launch {
   static cudaError_t collide(const StatePtrs &S, const Layout &L, const StepParams &P, void *traj, int grid,
                              cudaStream_t st);
   static int collide_grid(int n_worlds, int sm_count);
+  static cudaError_t list_pending(const StatePtrs &S, cudaStream_t st);
   static cudaError_t render(const StatePtrs &S, const Layout &L, const RenderLayout &RL, const uint32_t *atlas,
                             uint8_t *frames, cudaStream_t st);
   static cudaError_t reset_cache(const StatePtrs &S, int n_balls, int world0, int count, int keep_cache,

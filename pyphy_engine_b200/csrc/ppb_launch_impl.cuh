@@ -48,6 +48,12 @@ cudaError_t Launch<T>::collide(const StatePtrs &S, const Layout &L, const StepPa
 }
 
 template <typename T>
+cudaError_t Launch<T>::list_pending(const StatePtrs &S, cudaStream_t st) {
+  list_pending_kernel<T><<<(S.n_worlds + 255) / 256, 256, 0, st>>>(S, 0);
+  return cudaGetLastError();
+}
+
+template <typename T>
 cudaError_t Launch<T>::render(const StatePtrs &S, const Layout &L, const RenderLayout &RL, const uint32_t *atlas,
                               uint8_t *frames, cudaStream_t st) {
   const int tiles = ((RL.W + PPB_TILE - 1) / PPB_TILE) * ((RL.H + PPB_TILE - 1) / PPB_TILE);

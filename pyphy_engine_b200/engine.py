@@ -16,6 +16,16 @@ import numpy as np
 from . import _capi
 from ._capi import PPB_F32, PPB_F64, BallStyle, Config, Event, WallStyle, check
 
+def premul_rgba8(rgba):
+    """Colour -> premultiplied 8-bit (r, g, b, a) the way cairo/pixman quantise: 16-bit then >> 8
+    (same arithmetic as h_premul_rgba8 in csrc/ppb_api.cu)."""
+    def q(v):
+        v = min(1.0, max(0.0, float(v)))
+        return int(v * 65535.0 + 0.5) >> 8
+    a = float(np.float32(rgba[3]))
+    return tuple(q(float(np.float32(c)) * a) for c in rgba[:3]) + (q(a),)
+
+
 _DTYPES = {"f32": PPB_F32, "float32": PPB_F32, "fp32": PPB_F32, "f64": PPB_F64, "float64": PPB_F64, "fp64": PPB_F64}
 
 
@@ -139,6 +149,19 @@ class WorldBatch:
             ws[i].fill[:] = [float(c) for c in fill]
         check(self._lib.ppb_set_styles(self._h, bs, ws, int(r_min), int(r_max), stream))
 
+    def set_gravity(self, gx: float, gy: float):
+        """Dynamics.set_g (primitives.py:566); collision caches are left alone."""
+        check(self._lib.ppb_set_gravity(self._h, float(gx), float(gy)))
+
+    def read_sprite(self, slot: int, radius: int, stream=0):
+        """get_ball_im (primitives.py:33-61) as built on the device: (sz, sz, 4) uint8, premultiplied."""
+        sz = ctypes.c_int32(0)
+        check(self._lib.ppb_read_sprite(self._h, int(slot), int(radius), None, 0, ctypes.byref(sz), stream))
+        out = np.empty((sz.value, sz.value, 4), np.uint8)
+        check(self._lib.ppb_read_sprite(self._h, int(slot), int(radius), ctypes.c_void_p(out.ctypes.data), out.nbytes,
+                                        ctypes.byref(sz), stream))
+        return out
+
     # ------------------------------------------------------------------ state out
     def get_balls(self, world0: int = 0, count: Optional[int] = None, stream=0):
         count = self.n_worlds - world0 if count is None else count
@@ -153,6 +176,18 @@ class WorldBatch:
         partner = np.empty((count, self.n_balls), np.int32)
         check(self._lib.ppb_get_collision_cache(self._h, world0, count, _dp(tcol), _ip(partner), stream))
         return tcol, partner
+
+    def scan(self, stream=None):
+        """Drain the collision queue without stepping (time_to_collide_all for every queued ball)."""
+        check(self._lib.ppb_scan_async(self._h, _stream_handle(stream)))
+
+    def get_collision_response(self, world0: int = 0, count: Optional[int] = None, stream=0):
+        """(nrmlCol_, futureVel_) per ball: (count, n_balls, 2) each."""
+        count = self.n_worlds - world0 if count is None else count
+        nrml = np.empty((count, self.n_balls, 2), np.float64)
+        fv = np.empty((count, self.n_balls, 2), np.float64)
+        check(self._lib.ppb_get_collision_response(self._h, world0, count, _dp(nrml), _dp(fv), stream))
+        return nrml, fv
 
     def get_status(self, world0: int = 0, count: Optional[int] = None, stream=0):
         """(status, steps_done) per world; for a halted world steps_done is the failing step."""
