@@ -43,6 +43,19 @@ def _bytes_k2_per_world_step(n_balls, n_seg=16):
     return 24 * n_balls + 16 * n_seg + 16 * n_balls
 
 
+def load_traffic(kernel):
+    """DRAM bytes per launch of `kernel` from the committed ncu --set full capture (profiles/traffic.json,
+    written by tools/make_profiles.py from the same workload), or None."""
+    p = os.path.join(ROOT, "profiles", "traffic.json")
+    try:
+        with open(p) as fh:
+            t = json.load(fh)["kernels"]
+        key = {"integrate": "integrate_kernel", "collide": "collide_kernel", "render": "render_tile_kernel"}[kernel]
+        return float(t[key]["dram_bytes"])
+    except Exception:
+        return None
+
+
 def load_peaks():
     p = os.path.join(ROOT, "MEASURED_PEAKS.json")
     if os.path.exists(p):
@@ -105,9 +118,11 @@ class ClockSampler:
         return out
 
 
-def make_worlds(n_worlds, n_balls, seed):
-    from pyphy_engine_b200 import sampler
-    return sampler.sample_rect_worlds(n_worlds, n_balls, seed=seed, **sampler.scaled64_params(n_balls))
+def make_worlds(first, count, n_balls, seed0=None):
+    """Worlds first..first+count-1 of the synthetic job: world w is the same whatever the rank count."""
+    from pyphy_engine_b200 import sampler, sharding
+    return sharding.sample_world_range(first, count, n_balls, seed0=SEED0 if seed0 is None else seed0,
+                                       **sampler.scaled64_params(n_balls))
 
 
 STYLE_BALL = (1, (0.5, 0.5, 0.5, 1.0), (0.0, 0.0, 0.0, 1.0))   # sThick 1, gray fill, black ring
@@ -124,7 +139,7 @@ class CpuPort:
         sys.path.insert(0, os.path.join(ROOT, "oracle"))
         import oracle
         self.oracle = oracle
-        self.W = make_worlds(n_worlds, n_balls, seed)
+        self.W = make_worlds(0, n_worlds, n_balls, seed)
         self.ob = oracle.OracleBatch(self.W["wall"], self.W["pos"], self.W["vel"], self.W["rad"], self.W["mass"],
                                      trig_mode=0, max_substeps=MAX_SUBSTEPS)
         self.threads = threads
@@ -205,8 +220,9 @@ def run_ours(args, rank, local_rank, world_size):
             dist.barrier(device_ids=[local_rank])
         torch.cuda.synchronize(dev)
 
-    n_worlds = WORLDS_PER_GPU
-    W = make_worlds(n_worlds, N_BALLS, SEED0 + 7919 * rank)   # shard `rank` of the global world list
+    from pyphy_engine_b200 import sharding
+    first, n_worlds = sharding.shard_range(WORLDS_PER_GPU * world_size, rank, world_size)
+    W = make_worlds(first, n_worlds, N_BALLS)                  # shard `rank` of the global world list
     wb = WorldBatch(n_worlds, N_BALLS, 4, dtype="f32", canvas=(CANVAS, CANVAS), device=local_rank,
                     max_substeps=MAX_SUBSTEPS)
     wb.set_walls(W["wall"])
@@ -299,7 +315,7 @@ def run_ours(args, rank, local_rank, world_size):
                        "max_substeps": MAX_SUBSTEPS, "halted_worlds": int(total_worlds - live_total),
                        "events_per_world_step": events_total / (total_worlds * max(args.steps, 1))},
             "roofline": {"bound": "hbm", "kernel": names[dom], "achieved": achieved[dom], "peak": peak,
-                         "unit": "GB/s", "frac": achieved[dom] / peak, "traffic": None, "peak_source": peak_src,
+                         "unit": "GB/s", "frac": achieved[dom] / peak, "traffic": load_traffic(names[dom]), "peak_source": peak_src,
                          "avg_launch_us": float(avg_us[dom]),
                          "all_kernels": {names[i]: {"avg_launch_us": float(avg_us[i]), "achieved_gbs": achieved[i],
                                                     "frac": achieved[i] / peak, "algorithmic_bytes_per_launch": alg_bytes[i]}

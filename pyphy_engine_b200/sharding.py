@@ -1,0 +1,102 @@
+"""Partitioning of independent worlds over the GPUs of one node.
+
+Worlds never interact (the reference's only parallelism is one ``DataSaver`` per process,
+parallel_fetch.py:12-25), so the step loop needs no collective: every rank owns a contiguous
+block of world indices and runs the same three kernels on it.  ``torch.distributed`` (NCCL on
+the GPUs, gloo in the CPU tests) only carries the end-of-run statistics and, on request, the
+recorded trajectories.
+
+World ``w`` of a synthetic job is defined by its index alone (block ``w // BLOCK`` of the sampler
+stream ``seed0 + block``), so the same world is produced whatever the number of ranks -- which
+is what makes "1 GPU vs N GPUs give identical per-world results" checkable.
+"""
+from __future__ import annotations
+
+from typing import Dict, Optional, Sequence, Tuple
+
+import numpy as np
+
+BLOCK = 4096   # worlds per sampler block
+
+
+def shard_range(n_worlds: int, rank: int, world_size: int) -> Tuple[int, int]:
+    """(first, count) of the worlds of ``rank``: contiguous blocks of ceil(n / world_size)."""
+    if world_size < 1 or not (0 <= rank < world_size):
+        raise ValueError("bad rank %d / world_size %d" % (rank, world_size))
+    per = -(-int(n_worlds) // world_size)
+    first = min(int(n_worlds), rank * per)
+    return first, max(0, min(int(n_worlds), first + per) - first)
+
+
+def sample_world_range(first: int, count: int, n_balls: int, seed0: int = 0, **sampler_kw) -> Dict[str, np.ndarray]:
+    """Worlds ``first .. first+count-1`` of the synthetic job ``seed0`` (see module docstring)."""
+    from . import sampler
+    parts = []
+    b0, b1 = first // BLOCK, (first + count - 1) // BLOCK if count > 0 else first // BLOCK - 1
+    for blk in range(b0, b1 + 1):
+        W = sampler.sample_rect_worlds(BLOCK, n_balls, seed=seed0 + blk, **sampler_kw)
+        lo = max(first, blk * BLOCK) - blk * BLOCK
+        hi = min(first + count, (blk + 1) * BLOCK) - blk * BLOCK
+        parts.append({k: v[lo:hi] for k, v in W.items()})
+    if not parts:
+        W = sampler.sample_rect_worlds(1, n_balls, seed=seed0, **sampler_kw)
+        return {k: v[:0] for k, v in W.items()}
+    return {k: np.concatenate([p[k] for p in parts], 0) for k in parts[0]}
+
+
+def _dist():
+    import torch.distributed as dist
+    return dist
+
+
+def is_distributed() -> bool:
+    dist = _dist()
+    return dist.is_available() and dist.is_initialized() and dist.get_world_size() > 1
+
+
+def all_gather_stats(stats: Dict[str, float], device=None) -> Dict[str, np.ndarray]:
+    """Every rank contributes a dict of scalars; every rank receives ``{key: array[world_size]}``.
+    One small all_gather (a few hundred bytes) -- the only collective of a run."""
+    import torch
+    keys = sorted(stats)
+    local = torch.tensor([float(stats[k]) for k in keys], dtype=torch.float64, device=device)
+    if not is_distributed():
+        return {k: np.array([float(stats[k])]) for k in keys}
+    dist = _dist()
+    out = [torch.empty_like(local) for _ in range(dist.get_world_size())]
+    dist.all_gather(out, local)
+    mat = torch.stack(out).cpu().numpy()
+    return {k: mat[:, i] for i, k in enumerate(keys)}
+
+
+def gather_trajectories(local, n_worlds_total: int, dst: int = 0):
+    """Gather the per-rank ``position`` shards (steps, local_worlds, balls, 2) on rank ``dst`` in
+    world order (the reference collects ``Pool`` results the same way, parallel_fetch.py:22-25).
+    Returns the full tensor on ``dst`` and None elsewhere."""
+    import torch
+    if not is_distributed():
+        return local
+    dist = _dist()
+    rank, ws = dist.get_rank(), dist.get_world_size()
+    per = -(-int(n_worlds_total) // ws)
+    pad = torch.zeros((local.shape[0], per) + tuple(local.shape[2:]), dtype=local.dtype, device=local.device)
+    pad[:, :local.shape[1]] = local
+    bufs = [torch.empty_like(pad) for _ in range(ws)] if rank == dst else None
+    dist.gather(pad, bufs, dst=dst)
+    if rank != dst:
+        return None
+    parts = []
+    for r in range(ws):
+        _, cnt = shard_range(n_worlds_total, r, ws)
+        parts.append(bufs[r][:, :cnt])
+    return torch.cat(parts, 1)
+
+
+def world_checksum(pos: np.ndarray) -> np.ndarray:
+    """Order-independent per-world fingerprint of a position array (..., balls, 2) -> (...,) uint64,
+    used to compare shards across different rank counts."""
+    b = np.ascontiguousarray(pos, np.float64).view(np.uint64)
+    b = b.reshape(b.shape[:-2] + (-1,))
+    mult = (np.arange(b.shape[-1], dtype=np.uint64) * np.uint64(0x9E3779B97F4A7C15) + np.uint64(1))
+    with np.errstate(over="ignore"):
+        return (b * mult).sum(axis=-1, dtype=np.uint64)
