@@ -182,6 +182,10 @@ PPB_API int ppb_set_gravity(ppb_batch *b, double gx, double gy);
  *                (primitives.py:991-1008, dataio.py:119-120)                       */
 PPB_API int ppb_step_async(ppb_batch *b, int32_t n_steps, void *traj_dev, uint8_t *frames_dev,
                    int32_t render_every, void *stream);
+/* Scheduling note: when frames are requested, the render of step k runs on a stream owned by the
+ * batch, concurrently with the integrate / collide kernels of step k+1 (it reads a snapshot of
+ * the positions); `stream` waits for the last render before the call's work counts as complete,
+ * so stream-ordered consumers of `frames_dev` need no extra synchronisation. */
 
 /* Drains the collision queue without stepping: Dynamics.time_to_collide_all (primitives.py:720-733)
  * for every ball of every world whose queue is non-empty (after ppb_set_balls / ppb_requeue), i.e.
@@ -194,6 +198,12 @@ PPB_API int ppb_scan_async(ppb_batch *b, void *stream);
  * Ball.futureVel_ (dynamics.py:129): [count][n_balls][2] each, may be NULL */
 PPB_API int ppb_get_collision_response(ppb_batch *b, int32_t world0, int32_t count, double *nrml, double *future_vel,
                                void *stream);
+
+/* As ppb_step_async, with the frames written round-robin into `ring_slots` frame slots
+ * ([ring_slots][n_worlds][H][W][4] uint8): the frame of the j-th rendered step goes to slot
+ * j % ring_slots.  Lets a long run keep its frames in a bounded buffer (a consumer drains it). */
+PPB_API int ppb_step_ring_async(ppb_batch *b, int32_t n_steps, void *traj_dev, uint8_t *frames_dev, int32_t ring_slots,
+                        int32_t render_every, void *stream);
 
 /* World.generate_image() of the current state: [n_worlds][H][W][4] uint8, asynchronous */
 PPB_API int ppb_render_async(ppb_batch *b, uint8_t *frames_dev, void *stream);

@@ -79,6 +79,7 @@ SIGNATURES = {
     "ppb_step_async": (ctypes.c_int, [_vp, _i32, _vp, _vp, _i32, _vp]),
     "ppb_scan_async": (ctypes.c_int, [_vp, _vp]),
     "ppb_get_collision_response": (ctypes.c_int, [_vp, _i32, _i32, _dp, _dp, _vp]),
+    "ppb_step_ring_async": (ctypes.c_int, [_vp, _i32, _vp, _vp, _i32, _i32, _vp]),
     "ppb_render_async": (ctypes.c_int, [_vp, _vp, _vp]),
     "ppb_simulate_host": (ctypes.c_int, [_vp, _i32, _vp, _vp, _i32, _vp]),
     "ppb_read_events": (ctypes.c_int, [_vp, ctypes.POINTER(Event), _i64, ctypes.POINTER(_i64), _vp]),

@@ -9,6 +9,7 @@
 #include <cstring>
 #include <new>
 #include <string>
+#include <thread>
 #include <vector>
 
 #include "ppb_launch.h"
@@ -69,6 +70,13 @@ struct ppb_batch {
   std::vector<cudaEvent_t> ev_pool;
   std::vector<int> ev_kind;  // kernel kind per (start, stop) pair
   size_t ev_used = 0;
+  // software pipeline of ppb_step_async: render of step k on its own stream, overlapped with the physics of step k+1
+  cudaStream_t render_stream = nullptr;
+  void *snap[2] = {nullptr, nullptr};
+  cudaEvent_t ev_phys[2] = {nullptr, nullptr}, ev_rend[2] = {nullptr, nullptr};
+  // page-locked staging for host <-> device state transfers (grown on demand)
+  void *stage = nullptr;
+  size_t stage_bytes = 0;
   // scratch of ppb_simulate_host
   void *scr_traj[2] = {nullptr, nullptr};
   float *scr_traj32[2] = {nullptr, nullptr};
@@ -90,31 +98,62 @@ int check_range(const ppb_batch *b, int32_t world0, int32_t count) {
   return PPB_OK;
 }
 
-// host fp64 -> device array of the batch dtype
+// page-locked staging buffer of at least `bytes`
+int stage_reserve(ppb_batch *b, size_t bytes) {
+  if (bytes <= b->stage_bytes) return PPB_OK;
+  if (b->stage) cudaFreeHost(b->stage);
+  b->stage = nullptr;
+  b->stage_bytes = 0;
+  size_t want = bytes + bytes / 4 + 4096;
+  if (cudaHostAlloc(&b->stage, want, cudaHostAllocDefault) != cudaSuccess) {
+    cudaGetLastError();
+    return fail(PPB_E_NOMEM, "cudaHostAlloc(%zu bytes) failed", want);
+  }
+  b->stage_bytes = want;
+  return PPB_OK;
+}
+
+// element-wise conversion spread over a few host threads (large batches only)
+template <typename D, typename S>
+void convert_array(D *dst, const S *src, size_t n) {
+  const size_t kMin = 1u << 18;
+  unsigned nt = std::thread::hardware_concurrency();
+  if (nt > 8) nt = 8;
+  if (n < 2 * kMin || nt < 2) {
+    for (size_t i = 0; i < n; ++i) dst[i] = (D)src[i];
+    return;
+  }
+  std::vector<std::thread> th;
+  const size_t per = (n + nt - 1) / nt;
+  for (unsigned t = 0; t < nt; ++t) {
+    const size_t lo = t * per, hi = (lo + per < n) ? lo + per : n;
+    if (lo >= hi) break;
+    th.emplace_back([=]() {
+      for (size_t i = lo; i < hi; ++i) dst[i] = (D)src[i];
+    });
+  }
+  for (auto &t : th) t.join();
+}
+
+// host fp64 -> device array of the batch dtype, through the page-locked staging buffer
 int upload(ppb_batch *b, void *dst_base, size_t elem_off, const double *src, size_t n, cudaStream_t st) {
   if (n == 0) return PPB_OK;
-  if (is64(b)) {
-    CU(cudaMemcpyAsync((char *)dst_base + elem_off * 8, src, n * 8, cudaMemcpyHostToDevice, st));
-    CU(cudaStreamSynchronize(st));
-  } else {
-    std::vector<float> tmp(n);
-    for (size_t i = 0; i < n; ++i) tmp[i] = (float)src[i];
-    CU(cudaMemcpyAsync((char *)dst_base + elem_off * 4, tmp.data(), n * 4, cudaMemcpyHostToDevice, st));
-    CU(cudaStreamSynchronize(st));
-  }
+  int rc = stage_reserve(b, n * b->esz);
+  if (rc) return rc;
+  if (is64(b)) memcpy(b->stage, src, n * 8);
+  else convert_array((float *)b->stage, src, n);
+  CU(cudaMemcpyAsync((char *)dst_base + elem_off * b->esz, b->stage, n * b->esz, cudaMemcpyHostToDevice, st));
+  CU(cudaStreamSynchronize(st));   // the staging buffer is reused by the next call
   return PPB_OK;
 }
 int download(ppb_batch *b, const void *src_base, size_t elem_off, double *dst, size_t n, cudaStream_t st) {
   if (n == 0) return PPB_OK;
-  if (is64(b)) {
-    CU(cudaMemcpyAsync(dst, (const char *)src_base + elem_off * 8, n * 8, cudaMemcpyDeviceToHost, st));
-    CU(cudaStreamSynchronize(st));
-  } else {
-    std::vector<float> tmp(n);
-    CU(cudaMemcpyAsync(tmp.data(), (const char *)src_base + elem_off * 4, n * 4, cudaMemcpyDeviceToHost, st));
-    CU(cudaStreamSynchronize(st));
-    for (size_t i = 0; i < n; ++i) dst[i] = (double)tmp[i];
-  }
+  int rc = stage_reserve(b, n * b->esz);
+  if (rc) return rc;
+  CU(cudaMemcpyAsync(b->stage, (const char *)src_base + elem_off * b->esz, n * b->esz, cudaMemcpyDeviceToHost, st));
+  CU(cudaStreamSynchronize(st));
+  if (is64(b)) memcpy(dst, b->stage, n * 8);
+  else convert_array(dst, (const float *)b->stage, n);
   return PPB_OK;
 }
 
@@ -153,27 +192,53 @@ struct Prof {
   }
 };
 
-int step_once(ppb_batch *b, int step_off, void *traj, uint8_t *frame, cudaStream_t st) {
+int step_physics(ppb_batch *b, int step_off, void *traj, void *snap, cudaStream_t st) {
   StepParams P = b->P;
   P.step_off = step_off;
+  StatePtrs S = b->S;
+  S.snap = snap;
   {
     Prof p(b, st, 0);
-    CU(is64(b) ? Launch<double>::integrate(b->S, b->cfg.n_balls, P, traj, st)
-               : Launch<float>::integrate(b->S, b->cfg.n_balls, P, traj, st));
+    CU(is64(b) ? Launch<double>::integrate(S, b->cfg.n_balls, P, traj, st)
+               : Launch<float>::integrate(S, b->cfg.n_balls, P, traj, st));
     ++b->launches;
   }
   {
     Prof p(b, st, 1);
-    CU(is64(b) ? Launch<double>::collide(b->S, b->L, P, traj, b->collide_grid, st)
-               : Launch<float>::collide(b->S, b->L, P, traj, b->collide_grid, st));
+    CU(is64(b) ? Launch<double>::collide(S, b->L, P, traj, b->collide_grid, st)
+               : Launch<float>::collide(S, b->L, P, traj, b->collide_grid, st));
     ++b->launches;
   }
-  if (frame) {
-    Prof p(b, st, 2);
-    CU(is64(b) ? Launch<double>::render(b->S, b->L, b->RL, b->atlas, frame, st)
-               : Launch<float>::render(b->S, b->L, b->RL, b->atlas, frame, st));
-    ++b->launches;
+  return PPB_OK;
+}
+
+// World.generate_image() from the positions in `pos_src` (the live array or a snapshot)
+int step_render(ppb_batch *b, void *pos_src, uint8_t *frame, cudaStream_t st) {
+  StatePtrs S = b->S;
+  S.pos = pos_src;
+  Prof p(b, st, 2);
+  CU(is64(b) ? Launch<double>::render(S, b->L, b->RL, b->atlas, frame, st)
+             : Launch<float>::render(S, b->L, b->RL, b->atlas, frame, st));
+  ++b->launches;
+  return PPB_OK;
+}
+
+int step_once(ppb_batch *b, int step_off, void *traj, uint8_t *frame, cudaStream_t st) {
+  int rc = step_physics(b, step_off, traj, nullptr, st);
+  if (rc) return rc;
+  if (frame) return step_render(b, b->S.pos, frame, st);
+  return PPB_OK;
+}
+
+int pipeline_reserve(ppb_batch *b) {
+  if (b->render_stream) return PPB_OK;
+  const size_t bytes = (size_t)b->cfg.n_worlds * b->cfg.n_balls * 2 * b->esz;
+  for (int i = 0; i < 2; ++i) {
+    CU(cudaMalloc(&b->snap[i], bytes ? bytes : 16));
+    CU(cudaEventCreateWithFlags(&b->ev_phys[i], cudaEventDisableTiming));
+    CU(cudaEventCreateWithFlags(&b->ev_rend[i], cudaEventDisableTiming));
   }
+  CU(cudaStreamCreateWithFlags(&b->render_stream, cudaStreamNonBlocking));
   return PPB_OK;
 }
 
@@ -277,6 +342,7 @@ int ppb_create(const ppb_config *cfg, ppb_batch **out) {
       {&b->S.pos, nb * 2 * b->esz},   {&b->S.vel, nb * 2 * b->esz},
       {&b->S.aux, nb * 4 * b->esz},   {&b->S.tcol, nb * b->esz},
       {&b->S.rm, nb * 2 * b->esz},    {&b->S.wall, nw * (size_t)(nW > 0 ? nW : 1) * 8 * b->esz},
+      {&b->S.wall_rc, nw * (size_t)(nW > 0 ? nW : 1) * sizeof(WallRC)},
       {&b->S.hdr, nw * 16},           {(void **)&b->S.partner, nb * 4},
       {(void **)&b->S.nev, nw * 4},   {(void **)&b->S.events, (size_t)(cfg->event_capacity > 0 ? cfg->event_capacity : 1) * sizeof(ppb_event)},
       {(void **)&b->S.counters, 8 * sizeof(unsigned long long)},
@@ -326,7 +392,15 @@ int ppb_destroy(ppb_batch *b) {
   cudaSetDevice(b->cfg.device);
   cudaDeviceSynchronize();
   free_scratch(b);
-  void *ptrs[] = {b->S.pos, b->S.vel, b->S.aux, b->S.tcol, b->S.rm, b->S.wall, b->S.hdr, b->S.partner,
+  if (b->stage) cudaFreeHost(b->stage);
+  b->stage = nullptr;
+  for (int i = 0; i < 2; ++i) {
+    if (b->snap[i]) cudaFree(b->snap[i]);
+    if (b->ev_phys[i]) cudaEventDestroy(b->ev_phys[i]);
+    if (b->ev_rend[i]) cudaEventDestroy(b->ev_rend[i]);
+  }
+  if (b->render_stream) cudaStreamDestroy(b->render_stream);
+  void *ptrs[] = {b->S.pos, b->S.vel, b->S.aux, b->S.tcol, b->S.rm, b->S.wall, b->S.wall_rc, b->S.hdr, b->S.partner,
                   b->S.nev, b->S.events, b->S.counters, b->S.step_base, b->S.list, b->S.list_count, b->atlas, b->d_fill8,
                   b->d_stroke8};
   for (void *p : ptrs)
@@ -342,7 +416,13 @@ int ppb_set_walls(ppb_batch *b, int32_t world0, int32_t count, const double *wal
   if (!wall && b->cfg.n_walls > 0) return fail(PPB_E_INVALID, "wall is null");
   CU(cudaSetDevice(b->cfg.device));
   const size_t per = (size_t)b->cfg.n_walls * 8;
-  return upload(b, b->S.wall, (size_t)world0 * per, wall, (size_t)count * per, (cudaStream_t)stream);
+  rc = upload(b, b->S.wall, (size_t)world0 * per, wall, (size_t)count * per, (cudaStream_t)stream);
+  if (rc) return rc;
+  CU(is64(b) ? Launch<double>::wall_cache(b->S, b->L, b->RL, world0, count, (cudaStream_t)stream)
+             : Launch<float>::wall_cache(b->S, b->L, b->RL, world0, count, (cudaStream_t)stream));
+  ++b->launches;
+  CU(cudaStreamSynchronize((cudaStream_t)stream));
+  return PPB_OK;
 }
 
 int ppb_set_balls(ppb_batch *b, int32_t world0, int32_t count, const double *pos, const double *vel,
@@ -354,15 +434,26 @@ int ppb_set_balls(ppb_batch *b, int32_t world0, int32_t count, const double *pos
   cudaStream_t st = (cudaStream_t)stream;
   const size_t nB = (size_t)b->cfg.n_balls, n = (size_t)count * nB, off = (size_t)world0 * nB;
   // empty slots carry zero velocity and position so that the integrate kernel may stream over them
-  std::vector<double> p(pos, pos + n * 2), v(vel, vel + n * 2), rm(n * 2);
+  bool any_empty = false;
+  for (size_t i = 0; i < n; ++i) {
+    if (rad[i] < 0) any_empty = true;
+    else if (!(mass[i] > 0)) return fail(PPB_E_INVALID, "mass has to be a positive number");  // primitives.py:588
+  }
+  std::vector<double> rm(n * 2);
   for (size_t i = 0; i < n; ++i) {
     rm[2 * i] = rad[i];
     rm[2 * i + 1] = mass[i];
-    if (rad[i] < 0) p[2 * i] = p[2 * i + 1] = v[2 * i] = v[2 * i + 1] = 0.0;
-    else if (!(mass[i] > 0)) return fail(PPB_E_INVALID, "mass has to be a positive number");  // primitives.py:588
   }
-  if ((rc = upload(b, b->S.pos, off * 2, p.data(), n * 2, st))) return rc;
-  if ((rc = upload(b, b->S.vel, off * 2, v.data(), n * 2, st))) return rc;
+  if (any_empty) {
+    std::vector<double> p(pos, pos + n * 2), v(vel, vel + n * 2);
+    for (size_t i = 0; i < n; ++i)
+      if (rad[i] < 0) p[2 * i] = p[2 * i + 1] = v[2 * i] = v[2 * i + 1] = 0.0;
+    if ((rc = upload(b, b->S.pos, off * 2, p.data(), n * 2, st))) return rc;
+    if ((rc = upload(b, b->S.vel, off * 2, v.data(), n * 2, st))) return rc;
+  } else {
+    if ((rc = upload(b, b->S.pos, off * 2, pos, n * 2, st))) return rc;
+    if ((rc = upload(b, b->S.vel, off * 2, vel, n * 2, st))) return rc;
+  }
   if ((rc = upload(b, b->S.rm, off * 2, rm.data(), n * 2, st))) return rc;
   CU(do_reset(b, world0, count, 0, st));
   CU(cudaStreamSynchronize(st));
@@ -476,6 +567,10 @@ int ppb_set_styles(ppb_batch *b, const ppb_ball_style *balls, const ppb_wall_sty
   CU(cudaMemcpyAsync(b->d_stroke8, stroke8.data(), nB * 4, cudaMemcpyHostToDevice, st));
   CU(launch_build_sprites(b->atlas, b->RL, nB, b->d_fill8, b->d_stroke8, st));
   ++b->launches;
+  // the wall kind decides the paste rectangle (primitives.py:242-245 vs 310-312)
+  CU(is64(b) ? Launch<double>::wall_cache(b->S, b->L, b->RL, 0, b->cfg.n_worlds, st)
+             : Launch<float>::wall_cache(b->S, b->L, b->RL, 0, b->cfg.n_worlds, st));
+  ++b->launches;
   CU(cudaStreamSynchronize(st));
   b->styles_set = true;
   return PPB_OK;
@@ -510,23 +605,52 @@ int ppb_set_gravity(ppb_batch *b, double gx, double gy) {
   return PPB_OK;
 }
 
-int ppb_step_async(ppb_batch *b, int32_t n_steps, void *traj_dev, uint8_t *frames_dev, int32_t render_every,
-                   void *stream) {
+int ppb_step_ring_async(ppb_batch *b, int32_t n_steps, void *traj_dev, uint8_t *frames_dev, int32_t ring_slots,
+                        int32_t render_every, void *stream) {
   if (!b) return fail(PPB_E_INVALID, "null batch");
   if (n_steps < 0) return fail(PPB_E_INVALID, "n_steps must be >= 0");
   if (frames_dev) {
     if (!b->styles_set) return fail(PPB_E_STATE, "ppb_set_styles must be called before rendering");
     if (render_every < 1) return fail(PPB_E_INVALID, "render_every must be >= 1");
+    if (ring_slots < 1) return fail(PPB_E_INVALID, "ring_slots must be >= 1");
     if (b->RL.W < 1 || b->RL.H < 1) return fail(PPB_E_STATE, "batch was created without a canvas");
   }
   CU(cudaSetDevice(b->cfg.device));
   cudaStream_t st = (cudaStream_t)stream;
   const size_t frame_bytes = (size_t)b->cfg.n_worlds * b->RL.W * b->RL.H * 4;
-  for (int s = 0; s < n_steps; ++s) {
-    uint8_t *frame = nullptr;
-    if (frames_dev && ((s + 1) % render_every) == 0) frame = frames_dev + (size_t)((s + 1) / render_every - 1) * frame_bytes;
-    int rc = step_once(b, s, traj_dev, frame, st);
+  if (!frames_dev) {
+    for (int s = 0; s < n_steps; ++s) {
+      int rc = step_physics(b, s, traj_dev, nullptr, st);
+      if (rc) return rc;
+    }
+  } else {
+    // physics of step s+1 (K1, K2 on `st`) overlaps the render of step s (K3 on the render stream,
+    // reading the position snapshot K1 / K2 left for it); snapshot slots alternate
+    int rc = pipeline_reserve(b);
     if (rc) return rc;
+    int n_rendered = 0, last_slot = -1;
+    for (int s = 0; s < n_steps; ++s) {
+      const bool draw = ((s + 1) % render_every) == 0;
+      const int slot = n_rendered & 1;
+      if (draw && n_rendered >= 2) CU(cudaStreamWaitEvent(st, b->ev_rend[slot], 0));   // snapshot slot free again
+      rc = step_physics(b, s, traj_dev, draw ? b->snap[slot] : nullptr, st);
+      if (rc) return rc;
+      if (draw) {
+        uint8_t *frame = frames_dev + (size_t)(n_rendered % ring_slots) * frame_bytes;
+        CU(cudaEventRecord(b->ev_phys[slot], st));
+        CU(cudaStreamWaitEvent(b->render_stream, b->ev_phys[slot], 0));
+        rc = step_render(b, b->snap[slot], frame, b->render_stream);
+        if (rc) return rc;
+        CU(cudaEventRecord(b->ev_rend[slot], b->render_stream));
+        last_slot = slot;
+        ++n_rendered;
+      }
+    }
+    // the caller's stream sees every frame complete
+    if (last_slot >= 0) {
+      CU(cudaStreamWaitEvent(st, b->ev_rend[last_slot], 0));
+      if (n_rendered >= 2) CU(cudaStreamWaitEvent(st, b->ev_rend[last_slot ^ 1], 0));
+    }
   }
   if (n_steps > 0) {
     CU(launch_advance_step_base(b->S.step_base, n_steps, st));
@@ -534,6 +658,12 @@ int ppb_step_async(ppb_batch *b, int32_t n_steps, void *traj_dev, uint8_t *frame
     b->host_step += n_steps;
   }
   return PPB_OK;
+}
+
+int ppb_step_async(ppb_batch *b, int32_t n_steps, void *traj_dev, uint8_t *frames_dev, int32_t render_every,
+                   void *stream) {
+  const int32_t slots = (frames_dev && render_every >= 1 && n_steps / render_every > 0) ? n_steps / render_every : 1;
+  return ppb_step_ring_async(b, n_steps, traj_dev, frames_dev, slots, render_every, stream);
 }
 
 int ppb_scan_async(ppb_batch *b, void *stream) {

@@ -120,11 +120,15 @@ struct Layout {
 // device state of a batch (raw pointers; T-typed views are made in the kernels)
 struct StatePtrs {
   void *pos;       // [n_worlds][n_balls] {x, y}
+  void *snap;      // NULL or [n_worlds][n_balls] {x, y}: copy of the positions after this step, written by K1 / K2
+                   // (the render kernel of step k reads it while the physics of step k+1 already runs)
   void *vel;       // [n_worlds][n_balls] {vx, vy}
   void *aux;       // [n_worlds][n_balls] {nrmlCol.x, nrmlCol.y, futureVel.x, futureVel.y}
   void *tcol;      // [n_worlds][n_balls]
   void *rm;        // [n_worlds][n_balls] {radius, mass}
   void *wall;      // [n_worlds][n_walls][4][2]
+  void *wall_rc;   // [n_worlds][n_walls] WallRC: what the render kernel needs of a wall, derived once per
+                   // ppb_set_walls / ppb_set_styles (walls never move)
   void *hdr;       // [n_worlds] Hdr<T>
   int32_t *partner;   // [n_worlds][n_balls]
   uint32_t *nev;      // [n_worlds] events emitted so far (sequence numbers)
@@ -145,6 +149,13 @@ struct StepParams {
 };
 
 // ---- render ----
+struct __align__(16) WallRC {
+  float x0, x1, y0, y1;       // bounding box of the quad
+  int bx0, bx1, by0, by1;     // integer rectangle the reference pastes the wall sprite into
+  int lo, hi;                 // rows [lo, hi) the wall can touch
+  int flags;                  // bit 0: axis-aligned, bit 1: axis-aligned with integral y edges
+  uint32_t col;               // premultiplied RGBA8 of the wall slot
+};
 struct RenderWall {  // per wall slot, shared by the batch
   int32_t kind;
   uint32_t rgba8;    // colour as premultiplied 8-bit r | g<<8 | b<<16 | a<<24 (array channel order)

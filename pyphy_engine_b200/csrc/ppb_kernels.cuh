@@ -61,6 +61,10 @@ __global__ void __launch_bounds__(256) integrate_kernel(StatePtrs S, int n_balls
 #pragma unroll
         for (int j = 0; j < BPT; ++j) reinterpret_cast<T2 *>(traj)[(long long)P.step_off * total + i + j] = pos[i + j];
       }
+      if (S.snap) {
+#pragma unroll
+        for (int j = 0; j < BPT; ++j) reinterpret_cast<T2 *>(S.snap)[i + j] = pos[i + j];
+      }
     } else if (h.step == k) {
       if (h.flags == 0u && h.tmin > dt) {
         // event-free step: Dynamics.move_object for every ball (primitives.py:600-611)
@@ -88,6 +92,7 @@ __global__ void __launch_bounds__(256) integrate_kernel(StatePtrs S, int n_balls
           }
           *reinterpret_cast<T2 *>(tcol + i) = tc;
           if (traj) st4(reinterpret_cast<T4 *>(traj + ((long long)P.step_off * total + i) * 2), po);
+          if (S.snap) st4(reinterpret_cast<T4 *>(reinterpret_cast<T2 *>(S.snap) + i), po);
         } else {
           T2 p = pos[i], v = vel[i];
           T tc = tcol[i];
@@ -102,6 +107,7 @@ __global__ void __launch_bounds__(256) integrate_kernel(StatePtrs S, int n_balls
           }
           tcol[i] = tc;
           if (traj) reinterpret_cast<T2 *>(traj)[(long long)P.step_off * total + i] = p;
+          if (S.snap) reinterpret_cast<T2 *>(S.snap)[i] = p;
         }
         if (duty) {
           Hdr<T> o = h;
@@ -429,6 +435,7 @@ collide_kernel(StatePtrs S, Layout L, StepParams P, T *traj) {
         S.partner[base + bi] = partner;
       }
       if (traj) reinterpret_cast<T2 *>(traj)[((long long)P.step_off * S.n_worlds + w) * nB + bi] = p;
+      if (S.snap) reinterpret_cast<T2 *>(S.snap)[base + bi] = p;
     }
     if (lane == 0) {
       Hdr<T> o;

@@ -14,6 +14,9 @@ struct Launch {
                              cudaStream_t st);
   static int collide_grid(int n_worlds, int sm_count);
   static cudaError_t list_pending(const StatePtrs &S, cudaStream_t st);
+  // WallRC of worlds [world0, world0 + count)
+  static cudaError_t wall_cache(const StatePtrs &S, const Layout &L, const RenderLayout &RL, int world0, int count,
+                                cudaStream_t st);
   static cudaError_t render(const StatePtrs &S, const Layout &L, const RenderLayout &RL, const uint32_t *atlas,
                             uint8_t *frames, cudaStream_t st);
   static cudaError_t reset_cache(const StatePtrs &S, int n_balls, int world0, int count, int keep_cache,

@@ -54,6 +54,15 @@ cudaError_t Launch<T>::list_pending(const StatePtrs &S, cudaStream_t st) {
 }
 
 template <typename T>
+cudaError_t Launch<T>::wall_cache(const StatePtrs &S, const Layout &L, const RenderLayout &RL, int world0, int count,
+                                  cudaStream_t st) {
+  const long long n = (long long)count * L.n_walls;
+  if (n <= 0) return cudaSuccess;
+  wall_cache_kernel<T><<<(unsigned)((n + 127) / 128), 128, 0, st>>>(S, L.n_walls, RL, world0, count);
+  return cudaGetLastError();
+}
+
+template <typename T>
 cudaError_t Launch<T>::render(const StatePtrs &S, const Layout &L, const RenderLayout &RL, const uint32_t *atlas,
                               uint8_t *frames, cudaStream_t st) {
   const int tiles = ((RL.W + PPB_TILE - 1) / PPB_TILE) * ((RL.H + PPB_TILE - 1) / PPB_TILE);
@@ -64,21 +73,22 @@ cudaError_t Launch<T>::render(const StatePtrs &S, const Layout &L, const RenderL
   for (int k = 0; k < L.n_obj; ++k)
     if (L.order[k] < L.n_walls && k >= L.n_walls) walls_first = false;
   if (walls_first && (RL.W & 3) == 0 && (reinterpret_cast<uintptr_t>(frames) & 15u) == 0) {
-    static int sm_count = 0;
     static_assert(PPB_RENDER_WARPS * sizeof(RenderWarpSmem) <= 227 * 1024, "render tiles exceed the 227 KB of shared memory per CTA");
     static_assert(sizeof(RenderWarpSmem) % 16 == 0, "tile buffers must stay 16-byte aligned for cp.async.bulk");
     const int smem = (int)(PPB_RENDER_WARPS * sizeof(RenderWarpSmem));
-    if (!sm_count) {
-      int dev = 0;
-      cudaGetDevice(&dev);
-      cudaDeviceGetAttribute(&sm_count, cudaDevAttrMultiProcessorCount, dev);
-    }
-    static bool attr_set = false;   // per instantiation (T)
-    if (!attr_set) {
+    // per device (and per instantiation T): SM count, opt-in to the large dynamic shared memory
+    static int sm_counts[64] = {0};
+    int dev = 0;
+    cudaGetDevice(&dev);
+    if (dev < 0 || dev >= 64) return cudaErrorInvalidDevice;
+    if (!sm_counts[dev]) {
+      int n = 0;
+      cudaDeviceGetAttribute(&n, cudaDevAttrMultiProcessorCount, dev);
       cudaError_t e = cudaFuncSetAttribute(render_tile_kernel<T>, cudaFuncAttributeMaxDynamicSharedMemorySize, smem);
       if (e != cudaSuccess) return e;
-      attr_set = true;
+      sm_counts[dev] = n > 0 ? n : 1;
     }
+    const int sm_count = sm_counts[dev];
     // persistent: one CTA of PPB_RENDER_WARPS warps per SM, every warp walks the tile list
     long long blocks = (jobs + PPB_RENDER_WARPS - 1) / PPB_RENDER_WARPS;
     if (blocks > sm_count) blocks = sm_count;

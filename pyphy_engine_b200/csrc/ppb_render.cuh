@@ -374,7 +374,7 @@ __global__ void __launch_bounds__(256) render_general_kernel(StatePtrs S, Layout
 //           the buffer, and only waits (cp.async.bulk.wait_group.read) before overwriting it.
 // HBM sees exactly one full-line write per frame byte and a few hundred bytes of state reads.
 // ------------------------------------------------------------------------------------
-#define PPB_RENDER_WARPS 12
+#define PPB_RENDER_WARPS 11   // 11 x 18.6 KB leaves room for one collide CTA per SM next to the render CTA
 struct RTBall {      // one ball inside the current tile, already clipped to it (32 bytes)
   uint32_t tex;      // atlas element index of the first visible sprite pixel
   uint32_t dst_sz;   // tile element offset of that pixel | sprite side << 16
@@ -413,6 +413,25 @@ __device__ __forceinline__ int round_half_away_to_int(double v) { return (int)ro
 // src OVER dst without the white-canvas shortcut (branch-free; a transparent src leaves dst unchanged)
 __device__ __forceinline__ uint32_t over_nb(uint32_t src, uint32_t dst) { return src + mul_un8x4(dst, 255u - (src >> 24)); }
 
+// WallRC of every wall of worlds [world0, world0 + count): walls never move, so the bounding boxes,
+// paste rectangles and row ranges the render kernel needs are derived once per ppb_set_walls / ppb_set_styles
+template <typename T>
+__global__ void wall_cache_kernel(StatePtrs S, int n_walls, RenderLayout RL, int world0, int count) {
+  const long long i = (long long)blockIdx.x * blockDim.x + threadIdx.x;
+  if (i >= (long long)count * n_walls) return;
+  const int q = (int)(i % n_walls);
+  const long long idx = (long long)world0 * n_walls + i;
+  SWall s;
+  setup_wall<T>(s, reinterpret_cast<const T *>(S.wall) + idx * 8, RL.wall[q]);
+  WallRC rc;
+  rc.x0 = s.x0; rc.x1 = s.x1; rc.y0 = s.y0; rc.y1 = s.y1;
+  rc.bx0 = s.bx0; rc.bx1 = s.bx1; rc.by0 = s.by0; rc.by1 = s.by1;
+  rc.lo = s.lo; rc.hi = s.hi;
+  rc.flags = (s.axis ? 1 : 0) | (s.fast ? 2 : 0);
+  rc.col = s.col;
+  reinterpret_cast<WallRC *>(S.wall_rc)[idx] = rc;
+}
+
 template <typename T>
 __global__ void __launch_bounds__(PPB_RENDER_WARPS * 32, 1) render_tile_kernel(StatePtrs S, Layout L, RenderLayout RL,
                                                                            const uint32_t *atlas, uint8_t *frames) {
@@ -427,28 +446,27 @@ __global__ void __launch_bounds__(PPB_RENDER_WARPS * 32, 1) render_tile_kernel(S
   const int nB = L.n_balls, nWl = L.n_walls;
   const bool whole_rows = (RL.W == PPB_TILE);   // tile rows are contiguous in the frame
   // raw state of the world of the current / next tile, held in registers: lane q < nWl keeps wall q's
-  // vertices, lane b keeps ball b's position and radius.  The next tile's loads are issued before the
-  // current tile is drawn, so their latency hides behind the drawing.
-  T wv[8];
+  // WallRC, lane b keeps ball b's position and radius.  The next tile's loads are
+  // issued before the current tile is drawn, so their latency hides behind the drawing.
+  uint4 rc0 = make_uint4(0, 0, 0, 0), rc1 = rc0;
+  uint4 rc2 = rc0;   // every loaded word is consumed below: a dead destination register would be
+                     // recycled by ptxas and stall its next writer on the load (128-bit scoreboard)
   T2 bp;
   T brad = T(-1);
-#pragma unroll
-  for (int i = 0; i < 8; ++i) wv[i] = T(0);
   bp.x = bp.y = T(0);
   const long long job0 = (long long)blockIdx.x * PPB_RENDER_WARPS + warp;
   const long long jstride = (long long)gridDim.x * PPB_RENDER_WARPS;
-  if (job0 < total) {
-    const int w0 = (tiles == 1) ? (int)job0 : (int)(job0 / tiles);
+  auto load_world = [&](int wn) {
     if (lane < nWl) {
-      const T2 *src = reinterpret_cast<const T2 *>(S.wall) + ((long long)w0 * nWl + lane) * 4;
-#pragma unroll
-      for (int i = 0; i < 4; ++i) { const T2 u = src[i]; wv[2 * i] = u.x; wv[2 * i + 1] = u.y; }
+      const uint4 *src = reinterpret_cast<const uint4 *>(reinterpret_cast<const WallRC *>(S.wall_rc) + ((long long)wn * nWl + lane));
+      rc0 = src[0]; rc1 = src[1]; rc2 = src[2];
     }
     if (lane < nB) {
-      bp = reinterpret_cast<const T2 *>(S.pos)[(long long)w0 * nB + lane];
-      brad = reinterpret_cast<const T2 *>(S.rm)[(long long)w0 * nB + lane].x;
+      bp = reinterpret_cast<const T2 *>(S.pos)[(long long)wn * nB + lane];
+      brad = reinterpret_cast<const T2 *>(S.rm)[(long long)wn * nB + lane].x;
     }
-  }
+  };
+  if (job0 < total) load_world((tiles == 1) ? (int)job0 : (int)(job0 / tiles));
   for (long long job = job0; job < total; job += jstride) {
     int w = (int)job, tx0 = 0, ty0 = 0;
     if (tiles != 1) {
@@ -460,43 +478,46 @@ __global__ void __launch_bounds__(PPB_RENDER_WARPS * 32, 1) render_tile_kernel(S
     }
     const int y_end = min(ty0 + PPB_TILE, RL.H);
     const int x_end = min(tx0 + PPB_TILE, RL.W);
+    const int th = y_end - ty0, tw = x_end - tx0;
     // ---- geometry of this tile from the registers, then the loads of the next tile's world ----
-    T cwv[8];
-#pragma unroll
-    for (int i = 0; i < 8; ++i) cwv[i] = wv[i];
+    const uint4 c0 = rc0, c1 = rc1, c2 = rc2;
     const T2 cbp = bp;
     const T cbrad = brad;
     {
       const long long nj = job + jstride;
       if (nj < total) {
         const int wn = (tiles == 1) ? (int)nj : (int)(nj / tiles);
-        if (wn != w) {
-          if (lane < nWl) {
-            const T2 *src = reinterpret_cast<const T2 *>(S.wall) + ((long long)wn * nWl + lane) * 4;
-#pragma unroll
-            for (int i = 0; i < 4; ++i) { const T2 u = src[i]; wv[2 * i] = u.x; wv[2 * i + 1] = u.y; }
-          }
-          if (lane < nB) {
-            bp = reinterpret_cast<const T2 *>(S.pos)[(long long)wn * nB + lane];
-            brad = reinterpret_cast<const T2 *>(S.rm)[(long long)wn * nB + lane].x;
-          }
-        }
+        if (wn != w) load_world(wn);
       }
     }
     if (lane < nWl) {
-      SWall s;
-      setup_wall<T>(s, cwv, RL.wall[lane]);
+      const float wx0 = __uint_as_float(c0.x), wx1 = __uint_as_float(c0.y);
+      const int bx0 = (int)c1.x, bx1 = (int)c1.y, lo = (int)c2.x, hi = (int)c2.y, flags = (int)c2.z;
+      const uint32_t col = c2.w;
       // pixels of this tile the wall can touch
-      const int px0 = max(max(s.bx0, (int)floorf(s.x0)), tx0), px1 = min(min(s.bx1, (int)ceilf(s.x1)), x_end);
-      const int r0 = max(s.lo, ty0), r1 = min(s.hi, y_end);
+      const int px0 = max(max(bx0, (int)floorf(wx0)), tx0), px1 = min(min(bx1, (int)ceilf(wx1)), x_end);
+      const int r0 = max(lo, ty0), r1 = min(hi, y_end);
       int mode = PPB_WM_SLOW;
       if (px0 >= px1 || r0 >= r1) mode = PPB_WM_SKIP;
-      else if (s.fast)
-        mode = ((s.col >> 24) == 255u && floorf(s.x0) == s.x0 && floorf(s.x1) == s.x1) ? PPB_WM_SOLID : PPB_WM_FAST;
-      const int c0 = (px0 - tx0) >> 2, c1 = (px1 - tx0 + 3) >> 2;
-      sm.w[lane] = static_cast<const SWallGeom &>(s);
-      sm.wpaint[lane] = make_int4(mode, (int)s.col, (r0 - ty0) | ((r1 - r0) << 16), c0 | ((c1 - c0) << 16));
+      else if (flags & 2)
+        mode = ((col >> 24) == 255u && floorf(wx0) == wx0 && floorf(wx1) == wx1) ? PPB_WM_SOLID : PPB_WM_FAST;
+      const int g0 = (px0 - tx0) >> 2, g1 = (px1 - tx0 + 3) >> 2;
+      sm.wpaint[lane] = make_int4(mode, (int)col, (r0 - ty0) | ((r1 - r0) << 16), g0 | ((g1 - g0) << 16));
       sm.wspan[lane] = make_int2(px0 - tx0, px1 - tx0);
+      if (mode >= PPB_WM_FAST) {
+        SWallGeom g;
+        g.x0 = wx0; g.x1 = wx1; g.y0 = __uint_as_float(c0.z); g.y1 = __uint_as_float(c0.w);
+        g.bx0 = bx0; g.bx1 = bx1; g.by0 = (int)c1.z; g.by1 = (int)c1.w;
+        g.axis = flags & 1;
+#pragma unroll
+        for (int i = 0; i < 8; ++i) g.v[i] = 0.f;
+        if (mode == PPB_WM_SLOW) {
+          const T *wv = reinterpret_cast<const T *>(S.wall) + ((long long)w * nWl + lane) * 8;
+#pragma unroll
+          for (int i = 0; i < 8; ++i) g.v[i] = (float)wv[i];
+        }
+        sm.w[lane] = g;
+      }
     }
     if (lane < nB) {
       const int b = lane;
@@ -542,10 +563,10 @@ __global__ void __launch_bounds__(PPB_RENDER_WARPS * 32, 1) render_tile_kernel(S
       const int4 h = sm.wpaint[q];
       if (h.x == PPB_WM_SKIP) continue;
       const uint32_t col = (uint32_t)h.y;
-      const int r0 = h.z & 0xffff, nrows = h.z >> 16, c0 = h.w & 0xffff, ncg = h.w >> 16;
+      const int r0 = h.z & 0xffff, nrows = h.z >> 16, g0 = h.w & 0xffff, ncg = h.w >> 16;
       const int items = nrows * ncg;
       const float inv_ncg = __frcp_rn((float)ncg);
-      uint4 *base = reinterpret_cast<uint4 *>(sm.tile) + r0 * 16 + c0;
+      uint4 *base = reinterpret_cast<uint4 *>(sm.tile) + r0 * 16 + g0;
       if (h.x == PPB_WM_SOLID) {
         const int2 span = sm.wspan[q];
         const uint32_t width = (uint32_t)(span.y - span.x);
@@ -553,7 +574,7 @@ __global__ void __launch_bounds__(PPB_RENDER_WARPS * 32, 1) render_tile_kernel(S
           const int r = (int)(((float)i + 0.5f) * inv_ncg);
           const int c = i - r * ncg;
           uint4 *p = base + r * 16 + c;
-          const uint32_t d = (uint32_t)(((c0 + c) << 2) - span.x);   // pixel k of the group is inside iff d + k < width
+          const uint32_t d = (uint32_t)(((g0 + c) << 2) - span.x);   // pixel k of the group is inside iff d + k < width
           uint4 v = *p;
           v.x = (d < width) ? col : v.x;
           v.y = (d + 1u < width) ? col : v.y;
@@ -567,7 +588,7 @@ __global__ void __launch_bounds__(PPB_RENDER_WARPS * 32, 1) render_tile_kernel(S
           const int r = (int)(((float)i + 0.5f) * inv_ncg);
           const int c = i - r * ncg;
           uint4 *p = base + r * 16 + c;
-          const int x = tx0 + ((c0 + c) << 2), y = ty0 + r0 + r;
+          const int x = tx0 + ((g0 + c) << 2), y = ty0 + r0 + r;
           uint4 v = *p;
           if (h.x == PPB_WM_FAST) {
             // full row coverage: the mask of a pixel is its x-overlap with the wall
@@ -604,10 +625,20 @@ __global__ void __launch_bounds__(PPB_RENDER_WARPS * 32, 1) render_tile_kernel(S
       uint32_t ti = ra.x + (uint32_t)(sy * sz + sx);                      // atlas element index
       uint32_t di = (ra.y & 0xffffu) + (uint32_t)(sy * PPB_TILE + sx);    // tile element index
       const uint32_t wti = rb.z & 0xffffu, wdi = rb.z >> 16;
+      // two pixels per trip (this lane's pixel and the one 32 further on): two independent
+      // load -> blend -> store chains in flight
       while (sy < ah) {
+        int sx2 = sx + dr, sy2 = sy + dq;
+        uint32_t ti2 = ti + rb.x, di2 = di + rb.y;
+        if (sx2 >= aw) { sx2 -= aw; ++sy2; ti2 += wti; di2 += wdi; }
+        const bool has2 = sy2 < ah;
         const uint32_t t = __ldg(atlas + ti);
-        sm.tile[di] = over_nb(t, sm.tile[di]);
-        sx += dr; sy += dq; ti += rb.x; di += rb.y;
+        const uint32_t t2 = has2 ? __ldg(atlas + ti2) : 0u;
+        const uint32_t d = sm.tile[di];
+        const uint32_t d2 = has2 ? sm.tile[di2] : 0u;
+        sm.tile[di] = over_nb(t, d);
+        if (has2) sm.tile[di2] = over_nb(t2, d2);
+        sx = sx2 + dr; sy = sy2 + dq; ti = ti2 + rb.x; di = di2 + rb.y;
         if (sx >= aw) { sx -= aw; ++sy; ti += wti; di += wdi; }
       }
       __syncwarp();
@@ -617,10 +648,10 @@ __global__ void __launch_bounds__(PPB_RENDER_WARPS * 32, 1) render_tile_kernel(S
     __syncwarp();
     uint32_t *out = reinterpret_cast<uint32_t *>(frames) + (size_t)w * RL.W * RL.H;
     if (whole_rows) {
-      if (lane == 0) bulk_store_s2g(out + (size_t)ty0 * RL.W, sm.tile, (uint32_t)(y_end - ty0) * PPB_TILE * 4u);
+      if (lane == 0) bulk_store_s2g(out + (size_t)ty0 * RL.W, sm.tile, (uint32_t)th * PPB_TILE * 4u);
     } else {
-      const uint32_t row_bytes = (uint32_t)(x_end - tx0) * 4u;
-      for (int r = lane; r < y_end - ty0; r += 32)
+      const uint32_t row_bytes = (uint32_t)tw * 4u;
+      for (int r = lane; r < th; r += 32)
         bulk_store_s2g(out + (size_t)(ty0 + r) * RL.W + tx0, sm.tile + r * PPB_TILE, row_bytes);
     }
     bulk_commit();

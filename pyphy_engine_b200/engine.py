@@ -238,6 +238,16 @@ class WorldBatch:
         check(self._lib.ppb_step_async(self._h, int(n_steps), tp, fp, int(render_every), _stream_handle(stream)))
         self.steps_done += int(n_steps)
 
+    def step_ring_async(self, n_steps: int, frames, render_every: int = 1, traj=None, stream=None):
+        """n_steps x (step + render) with the frames written round-robin into the slots of
+        ``frames`` (ring_slots, n_worlds, H, W, 4): bounded frame memory for long runs."""
+        assert frames.is_cuda and frames.is_contiguous() and frames.dtype.itemsize == 1
+        assert tuple(frames.shape[1:]) == (self.n_worlds, self.canvas_h, self.canvas_w, 4)
+        tp = ctypes.c_void_p(traj.data_ptr()) if traj is not None else None
+        check(self._lib.ppb_step_ring_async(self._h, int(n_steps), tp, ctypes.c_void_p(frames.data_ptr()),
+                                            int(frames.shape[0]), int(render_every), _stream_handle(stream)))
+        self.steps_done += int(n_steps)
+
     def step(self, n_steps: int = 1, record_traj: bool = False, render_every: int = 0, stream=None):
         """Synchronous convenience: returns (traj, frames) as CUDA tensors (or None)."""
         import torch
