@@ -137,6 +137,29 @@ PPB_API int ppb_set_walls(ppb_batch *b, int32_t world0, int32_t count, const dou
 PPB_API int ppb_set_balls(ppb_batch *b, int32_t world0, int32_t count, const double *pos, const double *vel,
                   const double *rad, const double *mass, void *stream);
 
+/* parameters of the random rectangular tables of DataSaver(isRect=True) (dataio.py:21-27) */
+typedef struct ppb_sampler_params {
+  double arena;            /* arenaSz */
+  double w_thick;          /* wThick */
+  double mn_wlen, mx_wlen; /* mnWLen, mxWLen */
+  double mn_ball, mx_ball; /* mnBallSz, mxBallSz */
+  double mn_force, mx_force;
+  double force_t;          /* forceT of the initial kick (1.0 in dataio.py:414) */
+  uint64_t seed;
+  int64_t world_index0;    /* global index of world 0 of this batch (sharded jobs) */
+  int32_t max_tries;       /* give up on a world after this many rejections (dataio.py:359-362: 500) */
+} ppb_sampler_params;
+
+/* DataSaver._generate_model + apply_force (dataio.py:198-416) for worlds [world0, world0+count),
+ * drawn ON THE DEVICE: cage of 4 walls (the batch needs n_walls >= 4), n_balls balls placed by
+ * rejection sampling, initial velocities from random kicks; collision caches reset as by
+ * ppb_set_balls.  Distribution-equivalent to the reference (same loop structure and fp64
+ * arithmetic) on a Philox stream keyed by (seed, world_index0 + world); the stream-exact sampler is
+ * the host-side DataSaver.  *n_failed receives the number of worlds that could not be filled
+ * (left empty: every ball slot has radius -1). */
+PPB_API int ppb_sample_rect_worlds(ppb_batch *b, int32_t world0, int32_t count, const ppb_sampler_params *params,
+                           int32_t *n_failed, void *stream);
+
 /* ball.set_position / ball.set_velocity without touching the caches
  * (primitives.py:462-466); NULL leaves that quantity unchanged. */
 PPB_API int ppb_update_balls(ppb_batch *b, int32_t world0, int32_t count, const double *pos, const double *vel,
@@ -148,6 +171,12 @@ PPB_API int ppb_requeue(ppb_batch *b, int32_t world0, int32_t count, void *strea
 
 /* ball.get_position / get_velocity (primitives.py:450-457): [count][n_balls][2] each, may be NULL */
 PPB_API int ppb_get_balls(ppb_batch *b, int32_t world0, int32_t count, double *pos, double *vel, void *stream);
+
+/* ball.get_radius / get_mass (primitives.py:468-475): [count][n_balls] each, may be NULL; radius < 0 = empty slot */
+PPB_API int ppb_get_radius_mass(ppb_batch *b, int32_t world0, int32_t count, double *rad, double *mass, void *stream);
+
+/* wall vertices back: [count][n_walls][4][2] (wall.bbox_.vert_, geometry.py:471-505) */
+PPB_API int ppb_get_walls(ppb_batch *b, int32_t world0, int32_t count, double *wall, void *stream);
 
 /* Dynamics.tCol_ / objCol_ (primitives.py:548-549): [count][n_balls]; partner -1 = (None, None) */
 PPB_API int ppb_get_collision_cache(ppb_batch *b, int32_t world0, int32_t count, double *tcol, int32_t *partner,

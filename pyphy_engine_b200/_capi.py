@@ -43,6 +43,13 @@ class Config(ctypes.Structure):
     ]
 
 
+class SamplerParams(ctypes.Structure):
+    _fields_ = [("arena", ctypes.c_double), ("w_thick", ctypes.c_double), ("mn_wlen", ctypes.c_double),
+                ("mx_wlen", ctypes.c_double), ("mn_ball", ctypes.c_double), ("mx_ball", ctypes.c_double),
+                ("mn_force", ctypes.c_double), ("mx_force", ctypes.c_double), ("force_t", ctypes.c_double),
+                ("seed", ctypes.c_uint64), ("world_index0", ctypes.c_int64), ("max_tries", ctypes.c_int32)]
+
+
 class Event(ctypes.Structure):
     _fields_ = [("world", ctypes.c_int32), ("seq", ctypes.c_int32), ("step", ctypes.c_int32),
                 ("ball", ctypes.c_int16), ("partner", ctypes.c_int16)]
@@ -68,9 +75,12 @@ SIGNATURES = {
     "ppb_destroy": (ctypes.c_int, [_vp]),
     "ppb_set_walls": (ctypes.c_int, [_vp, _i32, _i32, _dp, _vp]),
     "ppb_set_balls": (ctypes.c_int, [_vp, _i32, _i32, _dp, _dp, _dp, _dp, _vp]),
+    "ppb_sample_rect_worlds": (ctypes.c_int, [_vp, _i32, _i32, ctypes.POINTER(SamplerParams), _ip, _vp]),
     "ppb_update_balls": (ctypes.c_int, [_vp, _i32, _i32, _dp, _dp, _vp]),
     "ppb_requeue": (ctypes.c_int, [_vp, _i32, _i32, _vp]),
     "ppb_get_balls": (ctypes.c_int, [_vp, _i32, _i32, _dp, _dp, _vp]),
+    "ppb_get_radius_mass": (ctypes.c_int, [_vp, _i32, _i32, _dp, _dp, _vp]),
+    "ppb_get_walls": (ctypes.c_int, [_vp, _i32, _i32, _dp, _vp]),
     "ppb_get_collision_cache": (ctypes.c_int, [_vp, _i32, _i32, _dp, _ip, _vp]),
     "ppb_get_status": (ctypes.c_int, [_vp, _i32, _i32, _ip, _ip, _vp]),
     "ppb_set_styles": (ctypes.c_int, [_vp, ctypes.POINTER(BallStyle), ctypes.POINTER(WallStyle), _i32, _i32, _vp]),

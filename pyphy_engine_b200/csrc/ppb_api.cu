@@ -460,6 +460,35 @@ int ppb_set_balls(ppb_batch *b, int32_t world0, int32_t count, const double *pos
   return PPB_OK;
 }
 
+int ppb_sample_rect_worlds(ppb_batch *b, int32_t world0, int32_t count, const ppb_sampler_params *sp, int32_t *n_failed,
+                           void *stream) {
+  int rc = check_range(b, world0, count);
+  if (rc) return rc;
+  if (!sp) return fail(PPB_E_INVALID, "null params");
+  if (b->cfg.n_walls < 4) return fail(PPB_E_INVALID, "the rectangular cage needs 4 wall slots");
+  if (!(sp->mx_wlen >= sp->mn_wlen) || !(sp->mx_ball >= sp->mn_ball) || !(sp->mn_ball >= 1) ||
+      !(sp->arena > sp->mx_wlen + sp->w_thick) || sp->max_tries < 1)
+    return fail(PPB_E_INVALID, "inconsistent sampler parameters");
+  CU(cudaSetDevice(b->cfg.device));
+  cudaStream_t st = (cudaStream_t)stream;
+  SamplerParams P;
+  P.arena = sp->arena; P.w_thick = sp->w_thick; P.mn_wlen = sp->mn_wlen; P.mx_wlen = sp->mx_wlen;
+  P.mn_ball = sp->mn_ball; P.mx_ball = sp->mx_ball; P.mn_force = sp->mn_force; P.mx_force = sp->mx_force;
+  P.force_t = sp->force_t; P.seed = sp->seed; P.world_index0 = sp->world_index0; P.max_tries = sp->max_tries;
+  int32_t *d_fail = reinterpret_cast<int32_t *>(b->S.counters + 6);   // spare counter slot
+  CU(cudaMemsetAsync(d_fail, 0, sizeof(int32_t), st));
+  CU(is64(b) ? Launch<double>::sample_rect(b->S, b->cfg.n_balls, b->cfg.n_walls, world0, count, P, b->host_step, d_fail, st)
+             : Launch<float>::sample_rect(b->S, b->cfg.n_balls, b->cfg.n_walls, world0, count, P, b->host_step, d_fail, st));
+  CU(is64(b) ? Launch<double>::wall_cache(b->S, b->L, b->RL, world0, count, st)
+             : Launch<float>::wall_cache(b->S, b->L, b->RL, world0, count, st));
+  b->launches += 2;
+  int32_t nf = 0;
+  CU(cudaMemcpyAsync(&nf, d_fail, sizeof nf, cudaMemcpyDeviceToHost, st));
+  CU(cudaStreamSynchronize(st));
+  if (n_failed) *n_failed = nf;
+  return PPB_OK;
+}
+
 int ppb_update_balls(ppb_batch *b, int32_t world0, int32_t count, const double *pos, const double *vel,
                      void *stream) {
   int rc = check_range(b, world0, count);
@@ -490,6 +519,29 @@ int ppb_get_balls(ppb_batch *b, int32_t world0, int32_t count, double *pos, doub
   if (pos && (rc = download(b, b->S.pos, off * 2, pos, n * 2, st))) return rc;
   if (vel && (rc = download(b, b->S.vel, off * 2, vel, n * 2, st))) return rc;
   return PPB_OK;
+}
+
+int ppb_get_radius_mass(ppb_batch *b, int32_t world0, int32_t count, double *rad, double *mass, void *stream) {
+  int rc = check_range(b, world0, count);
+  if (rc) return rc;
+  CU(cudaSetDevice(b->cfg.device));
+  const size_t nB = (size_t)b->cfg.n_balls, n = (size_t)count * nB, off = (size_t)world0 * nB;
+  std::vector<double> rm(n * 2);
+  if ((rc = download(b, b->S.rm, off * 2, rm.data(), n * 2, (cudaStream_t)stream))) return rc;
+  for (size_t i = 0; i < n; ++i) {
+    if (rad) rad[i] = rm[2 * i];
+    if (mass) mass[i] = rm[2 * i + 1];
+  }
+  return PPB_OK;
+}
+
+int ppb_get_walls(ppb_batch *b, int32_t world0, int32_t count, double *wall, void *stream) {
+  int rc = check_range(b, world0, count);
+  if (rc) return rc;
+  if (!wall) return fail(PPB_E_INVALID, "wall is null");
+  CU(cudaSetDevice(b->cfg.device));
+  const size_t per = (size_t)b->cfg.n_walls * 8;
+  return download(b, b->S.wall, (size_t)world0 * per, wall, (size_t)count * per, (cudaStream_t)stream);
 }
 
 int ppb_get_collision_cache(ppb_batch *b, int32_t world0, int32_t count, double *tcol, int32_t *partner,
@@ -618,9 +670,16 @@ int ppb_step_ring_async(ppb_batch *b, int32_t n_steps, void *traj_dev, uint8_t *
   CU(cudaSetDevice(b->cfg.device));
   cudaStream_t st = (cudaStream_t)stream;
   const size_t frame_bytes = (size_t)b->cfg.n_worlds * b->RL.W * b->RL.H * 4;
+  const int n_draws = frames_dev ? n_steps / render_every : 0;
   if (!frames_dev) {
     for (int s = 0; s < n_steps; ++s) {
       int rc = step_physics(b, s, traj_dev, nullptr, st);
+      if (rc) return rc;
+    }
+  } else if (n_draws <= 1) {
+    // a single frame in this call: nothing to overlap with, everything on the caller's stream
+    for (int s = 0; s < n_steps; ++s) {
+      int rc = step_once(b, s, traj_dev, ((s + 1) % render_every) == 0 ? frames_dev : nullptr, st);
       if (rc) return rc;
     }
   } else {

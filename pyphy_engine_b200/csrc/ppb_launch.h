@@ -2,6 +2,7 @@
 // (ppb_f32.cu is compiled with FMA contraction, ppb_f64.cu with -fmad=false).
 #pragma once
 #include "ppb_common.cuh"
+#include "ppb_sampler.cuh"
 
 namespace ppb {
 
@@ -21,6 +22,8 @@ struct Launch {
                             uint8_t *frames, cudaStream_t st);
   static cudaError_t reset_cache(const StatePtrs &S, int n_balls, int world0, int count, int keep_cache,
                                  int32_t step_value, cudaStream_t st);
+  static cudaError_t sample_rect(const StatePtrs &S, int n_balls, int n_walls, int world0, int count,
+                                 const SamplerParams &P, int32_t step_value, int32_t *fail_count, cudaStream_t st);
   // traj (batch dtype) -> float32
   static cudaError_t traj_to_f32(const void *src, float *dst, long long n, cudaStream_t st);
 };

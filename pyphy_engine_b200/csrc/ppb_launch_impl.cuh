@@ -54,6 +54,14 @@ cudaError_t Launch<T>::list_pending(const StatePtrs &S, cudaStream_t st) {
 }
 
 template <typename T>
+cudaError_t Launch<T>::sample_rect(const StatePtrs &S, int n_balls, int n_walls, int world0, int count,
+                                   const SamplerParams &P, int32_t step_value, int32_t *fail_count, cudaStream_t st) {
+  if (count <= 0) return cudaSuccess;
+  sample_rect_worlds_kernel<T><<<(count + 127) / 128, 128, 0, st>>>(S, n_balls, n_walls, world0, count, P, step_value, fail_count);
+  return cudaGetLastError();
+}
+
+template <typename T>
 cudaError_t Launch<T>::wall_cache(const StatePtrs &S, const Layout &L, const RenderLayout &RL, int world0, int count,
                                   cudaStream_t st) {
   const long long n = (long long)count * L.n_walls;

@@ -118,6 +118,35 @@ class WorldBatch:
         mass = np.ascontiguousarray(np.broadcast_to(np.asarray(mass, np.float64), shp))
         check(self._lib.ppb_set_balls(self._h, world0, count, _dp(pos), _dp(vel), _dp(rad), _dp(mass), stream))
 
+    def sample_rect_worlds(self, seed: int = 0, world0: int = 0, count: Optional[int] = None, world_index0: int = 0,
+                           arena=700, w_thick=30, mn_wlen=300, mx_wlen=550, mn_ball=25, mx_ball=25, mn_force=3e4,
+                           mx_force=8e4, force_t=1.0, max_tries=500, stream=0) -> int:
+        """Fill worlds [world0, world0+count) with random rectangular tables drawn ON THE DEVICE from
+        the DataSaver(isRect=True) distribution (dataio.py:198-416); returns the number of worlds that
+        could not be filled.  World w depends on (seed, world_index0 + w) only."""
+        count = self.n_worlds - world0 if count is None else count
+        sp = _capi.SamplerParams(float(arena), float(w_thick), float(mn_wlen), float(mx_wlen), float(mn_ball),
+                                 float(mx_ball), float(mn_force), float(mx_force), float(force_t), int(seed),
+                                 int(world_index0), int(max_tries))
+        nf = ctypes.c_int32(0)
+        check(self._lib.ppb_sample_rect_worlds(self._h, world0, count, ctypes.byref(sp), ctypes.byref(nf), stream))
+        return nf.value
+
+    def get_walls(self, world0: int = 0, count: Optional[int] = None, stream=0):
+        """(count, n_walls, 4, 2) wall vertices read back from the device."""
+        count = self.n_worlds - world0 if count is None else count
+        wall = np.empty((count, self.n_walls, 4, 2), np.float64)
+        check(self._lib.ppb_get_walls(self._h, world0, count, _dp(wall), stream))
+        return wall
+
+    def get_radius_mass(self, world0: int = 0, count: Optional[int] = None, stream=0):
+        """(radius, mass) per ball slot, (count, n_balls) each; radius < 0 marks an empty slot."""
+        count = self.n_worlds - world0 if count is None else count
+        rad = np.empty((count, self.n_balls), np.float64)
+        mass = np.empty((count, self.n_balls), np.float64)
+        check(self._lib.ppb_get_radius_mass(self._h, world0, count, _dp(rad), _dp(mass), stream))
+        return rad, mass
+
     def update_balls(self, pos=None, vel=None, world0: int = 0, stream=0):
         """ball.set_position / set_velocity: caches are left alone (primitives.py:462-466)."""
         ref = pos if pos is not None else vel
