@@ -310,9 +310,14 @@ int ppb_create(const ppb_config *cfg, ppb_batch **out) {
   for (int k = 0; k < nO; ++k) {
     const int q = b->L.order[k];
     if (q < nW)
-      for (int e = 0; e < 4; ++e) b->L.item[b->L.n_items++] = (int16_t)((q << 2) | e);
-    else
+      for (int e = 0; e < 4; ++e) {
+        b->L.edge_k[(q << 2) | e] = (int16_t)b->L.n_items;
+        b->L.item[b->L.n_items++] = (int16_t)((q << 2) | e);
+      }
+    else {
+      b->L.ball_k[q - nW] = (int16_t)b->L.n_items;
       b->L.item[b->L.n_items++] = (int16_t)(0x8000 | (q - nW));
+    }
   }
   // Dynamics.step walks the dynamic objects in ball insertion order (primitives.py:642, 653);
   // slot numbers are that order, so ball ranks must be increasing

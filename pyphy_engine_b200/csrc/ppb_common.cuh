@@ -115,6 +115,9 @@ struct Layout {
   // dynamics.py:20): a wall contributes its four edges (wall << 2 | edge), a ball 0x8000 | slot
   int32_t n_items;
   int16_t item[PPB_MAX_WALLS * 4 + PPB_MAX_BALLS];
+  // the inverse: position in that visiting order of edge (wall << 2 | edge) and of ball slot b
+  int16_t edge_k[PPB_MAX_WALLS * 4];
+  int16_t ball_k[PPB_MAX_BALLS];
 };
 
 // device state of a batch (raw pointers; T-typed views are made in the kernels)

@@ -202,7 +202,7 @@ collide_kernel(StatePtrs S, Layout L, StepParams P, T *traj) {
   const unsigned FULL = 0xffffffffu;
   constexpr int G = 32 / LB;                   // lanes per ball
   const int bi = lane & (LB - 1), grp = lane / LB;
-  const int nB = L.n_balls, nWl = L.n_walls, nItems = L.n_items;
+  const int nB = L.n_balls, nWl = L.n_walls;
   const uint32_t k = (uint32_t)(*S.step_base + P.step_off);
   const T dt = (T)P.dt;
   const V2<T> g = mk<T>((T)P.gx, (T)P.gy);
@@ -295,32 +295,38 @@ collide_kernel(StatePtrs S, Layout L, StepParams P, T *traj) {
         int kbest = PPB_K_NONE, kfv = -1, kerr = PPB_K_NONE;
         V2<T> nb = nrm, fb = fv;
         if (active) {
-          for (int it = grp; it < nItems; it += G) {
-            const int item = L.item[it];
-            if (item >= 0) {
-              // one edge of dynamics.get_toc_ball_wall (dynamics.py:20-59)
-              T te;
-              V2<T> ne;
-              const int ee = M::edge_toc(pos, vel, rad, sm.edge[item], te, ne);
-              if (ee) {
-                if (kerr == PPB_K_NONE) { kerr = it; err = ee; }
-              } else if (te < tc) {
-                tc = te; kbest = it; partner = item >> 2; nb = ne;
-              }
-            } else {
-              const int b2 = item & 0xff;
-              const T2 q2 = sm.rm[b2];
-              if (b2 == bi || q2.x < T(0)) continue;
-              const T2 p2 = sm.pos[b2], v2 = sm.vel[b2];
-              const Toc<T> r = M::ball(pos, vel, rad, mass, mk<T>(p2.x, p2.y), mk<T>(v2.x, v2.y), q2.x, q2.y);
-              if (r.err) {
-                if (kerr == PPB_K_NONE) { kerr = it; err = r.err; }
-                continue;
-              }
-              if (r.has_fv) { fb = r.fv; kfv = it; }   // futureVel_ (dynamics.py:129)
-              if (r.t < tc) {
-                tc = r.t; kbest = it; partner = nWl + b2; nb = r.n;
-              }
+          // The lane's share of the scan items, edges first, then balls.  The order of evaluation is
+          // free: every candidate carries its position k in the reference's visiting order and ties
+          // are broken on k, so the result equals the sequential strict-'<' scan.  Type-pure loops
+          // with independent trips let the tests of several items overlap in the pipeline.
+          const int nE = nWl << 2;
+#pragma unroll 4
+          for (int e = grp; e < nE; e += G) {
+            // one edge of dynamics.get_toc_ball_wall (dynamics.py:20-59)
+            const int kk = L.edge_k[e];
+            T te;
+            V2<T> ne;
+            const int ee = M::edge_toc(pos, vel, rad, sm.edge[e], te, ne);
+            if (ee) {
+              if (kk < kerr) { kerr = kk; err = ee; }
+            } else if (te < tc || (te == tc && kk < kbest && kbest != PPB_K_NONE)) {
+              tc = te; kbest = kk; partner = e >> 2; nb = ne;
+            }
+          }
+#pragma unroll 2
+          for (int b2 = grp; b2 < nB; b2 += G) {
+            const T2 q2 = sm.rm[b2];
+            if (b2 == bi || q2.x < T(0)) continue;
+            const int kk = L.ball_k[b2];
+            const T2 p2 = sm.pos[b2], v2 = sm.vel[b2];
+            const Toc<T> r = M::ball(pos, vel, rad, mass, mk<T>(p2.x, p2.y), mk<T>(v2.x, v2.y), q2.x, q2.y);
+            if (r.err) {
+              if (kk < kerr) { kerr = kk; err = r.err; }
+              continue;
+            }
+            if (r.has_fv && kk > kfv) { fb = r.fv; kfv = kk; }   // futureVel_: last partner in order (dynamics.py:129)
+            if (r.t < tc || (r.t == tc && kk < kbest && kbest != PPB_K_NONE)) {
+              tc = r.t; kbest = kk; partner = nWl + b2; nb = r.n;
             }
           }
         }
