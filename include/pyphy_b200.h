@@ -245,6 +245,22 @@ PPB_API int ppb_render_async(ppb_batch *b, uint8_t *frames_dev, void *stream);
 PPB_API int ppb_simulate_host(ppb_batch *b, int32_t n_steps, float *traj_host, uint8_t *frames_host,
                       int32_t render_every, void *stream);
 
+/* The ball-centred crops of DataSaver.fetch(cropSz) (dataio.py:160-182) for every frame, world and ball:
+ *   frames_dev : [n_frames][n_worlds][H][W][4] uint8 (what ppb_step_async rendered)
+ *   traj_dev   : [n_frames][n_worlds][n_balls][2] in the batch dtype -- the ball centres in those frames
+ *   crops_dev  : [n_frames][n_worlds][n_balls][crop_sz][crop_sz][3] uint8, white where the crop leaves the canvas
+ *   pos_dev    : NULL or [n_frames][n_worlds][n_balls][2] float32 -- the centres in crop coordinates (dataio.py:178-179)
+ * Asynchronous. */
+PPB_API int ppb_crop_async(ppb_batch *b, const uint8_t *frames_dev, const void *traj_dev, int32_t n_frames, int32_t crop_sz,
+                   uint8_t *crops_dev, float *pos_dev, void *stream);
+
+/* utils.detect_collision's per-frame test (utils.py:38-49) on a recorded trajectory:
+ *   traj_dev  : [n_steps][n_items][2] float32 positions (n_items = worlds x balls)
+ *   flags_dev : [n_items][n_steps - 2] uint8, 1 where |diff(diff(pos))|^2 >= thresh * |diff(pos)|^2
+ * No batch is needed; runs on the current device.  Asynchronous. */
+PPB_API int ppb_collision_flags_async(const float *traj_dev, int64_t n_items, int32_t n_steps, float thresh,
+                              uint8_t *flags_dev, void *stream);
+
 /* events recorded since the last ppb_set_balls on world 0 / ppb_clear_events:
  * copies up to `cap` records (unordered across worlds; sort by (world, seq)) and
  * returns the total number produced in *n_total (may exceed event_capacity). */

@@ -7,6 +7,13 @@ cudaError_t launch_advance_step_base(int32_t *step_base, int32_t n, cudaStream_t
   advance_step_base_kernel<<<1, 1, 0, st>>>(step_base, n);
   return cudaGetLastError();
 }
+cudaError_t launch_collision_flags(const float *traj, long long n_items, int n_steps, float thresh, uint8_t *flags,
+                                   cudaStream_t st) {
+  const long long total = n_items * (long long)(n_steps - 2);
+  if (total <= 0) return cudaSuccess;
+  collision_flag_kernel<<<(unsigned)((total + 255) / 256), 256, 0, st>>>(traj, n_items, n_steps, thresh, flags);
+  return cudaGetLastError();
+}
 cudaError_t launch_build_sprites(uint32_t *atlas, const RenderLayout &RL, int n_balls, const uint32_t *fill8,
                                  const uint32_t *stroke8, cudaStream_t st) {
   const int nr = RL.r_max - RL.r_min + 1;

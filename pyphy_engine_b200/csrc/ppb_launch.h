@@ -24,10 +24,14 @@ struct Launch {
                                  int32_t step_value, cudaStream_t st);
   static cudaError_t sample_rect(const StatePtrs &S, int n_balls, int n_walls, int world0, int count,
                                  const SamplerParams &P, int32_t step_value, int32_t *fail_count, cudaStream_t st);
+  static cudaError_t crop(const uint8_t *frames, const void *traj, long long n_frames, int n_worlds, int n_balls, int W,
+                          int H, int c, uint8_t *crops, float *pos_out, cudaStream_t st);
   // traj (batch dtype) -> float32
   static cudaError_t traj_to_f32(const void *src, float *dst, long long n, cudaStream_t st);
 };
 
+cudaError_t launch_collision_flags(const float *traj, long long n_items, int n_steps, float thresh, uint8_t *flags,
+                                   cudaStream_t st);
 cudaError_t launch_advance_step_base(int32_t *step_base, int32_t n, cudaStream_t st);
 cudaError_t launch_build_sprites(uint32_t *atlas, const RenderLayout &RL, int n_balls, const uint32_t *fill8,
                                  const uint32_t *stroke8, cudaStream_t st);

@@ -2,6 +2,7 @@
 #pragma once
 #include "ppb_kernels.cuh"
 #include "ppb_launch.h"
+#include "ppb_post.cuh"
 #include "ppb_render.cuh"
 
 namespace ppb {
@@ -58,6 +59,17 @@ cudaError_t Launch<T>::sample_rect(const StatePtrs &S, int n_balls, int n_walls,
                                    const SamplerParams &P, int32_t step_value, int32_t *fail_count, cudaStream_t st) {
   if (count <= 0) return cudaSuccess;
   sample_rect_worlds_kernel<T><<<(count + 127) / 128, 128, 0, st>>>(S, n_balls, n_walls, world0, count, P, step_value, fail_count);
+  return cudaGetLastError();
+}
+
+template <typename T>
+cudaError_t Launch<T>::crop(const uint8_t *frames, const void *traj, long long n_frames, int n_worlds, int n_balls, int W,
+                            int H, int c, uint8_t *crops, float *pos_out, cudaStream_t st) {
+  const long long items = n_frames * n_worlds * n_balls;
+  if (items <= 0) return cudaSuccess;
+  if (items > 2147483647LL) return cudaErrorInvalidValue;
+  const int threads = c * c >= 256 ? 256 : (c * c >= 128 ? 128 : 64);
+  crop_kernel<T><<<(unsigned)items, threads, 0, st>>>(frames, (const T *)traj, n_worlds, n_balls, W, H, c, crops, pos_out);
   return cudaGetLastError();
 }
 

@@ -17,7 +17,6 @@ There is no CPU simulation or drawing in this module.
 """
 from __future__ import annotations
 
-import math
 import os
 import pickle
 from concurrent.futures import ThreadPoolExecutor
@@ -29,10 +28,6 @@ from . import primitives as pm
 
 __all__ = ["DataSaver", "save_rect_arena", "save_nonrect_arena_train", "save_nonrect_arena_val",
            "save_multishape_rect_arena"]
-
-
-def _py2_round(v):
-    return math.floor(abs(v) + 0.5) * (-1.0 if v < 0 else 1.0)
 
 
 class SequenceSpec(object):
@@ -347,61 +342,53 @@ class DataSaver(object):
 
     def fetch(self, cropSz=None, procSz=None):
         """One sequence in memory (dataio.py:131-196): the list of frames, or with ``cropSz`` the
-        ball-centred crops ``(imBalls, force, velocity, position)``."""
+        ball-centred crops ``(imBalls, force, velocity, position)``.  Stepping, drawing and cropping
+        run on the device (``ppb_step_async`` + ``ppb_crop_async``); only the optional ``procSz``
+        resize (scipy.misc.imresize in the reference, i.e. PIL bilinear) is done on the host."""
         self.seqLen_ = self._draw_seq_len()
         model, f, ballPos, _ = self.generate_model()
         sp = SequenceSpec(model, f, ballPos, self.pts, self.seqLen_)
-        position, frames = self.run_sequences([sp], want_frames=True)
-        imList = [frames[0][i] for i in range(sp.seq_len)]
         if cropSz is None:
-            return imList
-        return self._crops(sp, imList, position[0], cropSz, procSz)
+            _, frames = self.run_sequences([sp], want_frames=True)
+            return [frames[0][i] for i in range(sp.seq_len)]
+        return self._fetch_crops(sp, int(cropSz), procSz)
+
+    def _fetch_crops(self, sp, cropSz, procSz):
+        from PIL import Image
+        nB, L = self.numBalls_, sp.seq_len
+        wb = self._batch_from_specs([sp], True)
+        try:
+            traj, frames = wb.step(L, record_traj=True, render_every=1)
+            status, at = wb.get_status()
+            if status[0] != 0 and at[0] < L:
+                from ._capi import STATUS_NAMES
+                raise AssertionError("the reference raises in step %d (%s)" % (int(at[0]), STATUS_NAMES.get(int(status[0]))))
+            crops, cpos = wb.crop(frames, traj, cropSz)
+            crops = crops[:, 0].cpu().numpy()                       # (L, nB, c, c, 3)
+            cpos = cpos[:, 0].cpu().numpy()                         # (L, nB, 2) in crop coordinates
+            pos = traj[:, 0].cpu().numpy().astype(np.float64)       # (L, nB, 2) in canvas coordinates
+        finally:
+            wb.close()
+        force = np.zeros((2 * nB, L), np.float32)
+        for b, fb in enumerate(sp.forces):
+            force[2 * b, 0], force[2 * b + 1, 0] = fb.x(), fb.y()
+        position = cpos.reshape(L, 2 * nB).T.copy()
+        velocity = np.zeros((2 * nB, L), np.float32)
+        imBalls = [[crops[i, j] for i in range(L)] for j in range(nB)]
+        if procSz is not None:
+            scale = float(procSz) / float(cropSz)
+            imBalls = [[np.asarray(Image.fromarray(im).resize((procSz, procSz), Image.BILINEAR)) for im in seq]
+                       for seq in imBalls]
+            position = (position * np.float32(scale)).astype(np.float32)
+            d = np.diff(pos, axis=0)                                # displacement between consecutive frames
+            velocity[:, :L - 1] = (d * scale).reshape(L - 1, 2 * nB).T
+        return imBalls, force, velocity, position
 
     def fetch_batch(self, numSeq, want_frames=True):
         """``numSeq`` fetches as one GPU batch: (specs, position list, frames list)."""
         specs = self.sample_sequences(numSeq)
         position, frames = self.run_sequences(specs, want_frames=want_frames)
         return specs, position, frames
-
-    def _crops(self, sp, imList, pos_full, cropSz, procSz):
-        """Ball-centred white-padded crops and the re-based positions (dataio.py:160-189)."""
-        from PIL import Image
-        nB, L = self.numBalls_, sp.seq_len
-        force = np.zeros((2 * nB, L), np.float32)
-        for b, fb in enumerate(sp.forces):
-            force[2 * b, 0], force[2 * b + 1, 0] = fb.x(), fb.y()
-        position = pos_full.copy()
-        velocity = np.zeros((2 * nB, L), np.float32)
-        imBalls = [[] for _ in range(nB)]
-        prev = np.full((nB, 2), np.nan)
-        half = cropSz / 2.0
-        for i, im in enumerate(imList):
-            for j in range(nB):
-                px, py = float(pos_full[2 * j, i]), float(pos_full[2 * j + 1, i])
-                vx = vy = None
-                if not np.isnan(prev[j, 0]):
-                    vx, vy = px - prev[j, 0], py - prev[j, 1]
-                prev[j] = (px, py)
-                xMid, yMid = _py2_round(px), _py2_round(py)
-                crop = 255 * np.ones((cropSz, cropSz, 3), np.uint8)
-                x1, x2 = max(0, xMid - half), min(self.xSz_, xMid + half)
-                y1, y2 = max(0, yMid - half), min(self.ySz_, yMid + half)
-                imX1, imX2 = int(_py2_round(half - (xMid - x1))), int(_py2_round(half + (x2 - xMid)))
-                imY1, imY2 = int(_py2_round(half - (yMid - y1))), int(_py2_round(half + (y2 - yMid)))
-                x1, x2, y1, y2 = int(_py2_round(x1)), int(_py2_round(x2)), int(_py2_round(y1)), int(_py2_round(y2))
-                crop[imY1:imY2, imX1:imX2, :] = im[y1:y2, x1:x2, 0:3]
-                position[2 * j, i] = position[2 * j, i] - x1 + imX1
-                position[2 * j + 1, i] = position[2 * j + 1, i] - y1 + imY1
-                if procSz is not None:
-                    scale = float(procSz) / float(cropSz)
-                    crop = np.asarray(Image.fromarray(crop).resize((procSz, procSz), Image.BILINEAR))
-                    position[2 * j, i] *= scale
-                    position[2 * j + 1, i] *= scale
-                    if vx is not None:
-                        velocity[2 * j, i - 1] = vx * scale
-                        velocity[2 * j + 1, i - 1] = vy * scale
-                imBalls[j].append(crop)
-        return imBalls, force, velocity, position
 
 
 # ----------------------------------------------------------------------------------------------

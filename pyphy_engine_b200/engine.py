@@ -47,6 +47,20 @@ def _stream_handle(stream) -> int:
     return int(stream)
 
 
+def collision_flags(traj, thresh: float = 0.03, stream=None):
+    """utils.detect_collision's test on a float32 CUDA trajectory (n_steps, n_items, 2):
+    (n_items, n_steps - 2) uint8, 1 where |diff(diff(pos))|^2 >= thresh * |diff(pos)|^2 (utils.py:38-49)."""
+    import torch
+    assert traj.is_cuda and traj.is_contiguous() and traj.dtype == torch.float32 and traj.shape[-1] == 2
+    n_steps = int(traj.shape[0])
+    n_items = int(traj.numel() // (2 * n_steps))
+    flags = torch.empty((n_items, n_steps - 2), dtype=torch.uint8, device=traj.device)
+    with torch.cuda.device(traj.device):
+        check(_capi.load().ppb_collision_flags_async(ctypes.c_void_p(traj.data_ptr()), n_items, n_steps, float(thresh),
+                                                     ctypes.c_void_p(flags.data_ptr()), _stream_handle(stream)))
+    return flags
+
+
 class WorldBatch:
     """``n_worlds`` worlds, each with ``n_walls`` wall slots and ``n_balls`` ball slots.
 
@@ -300,6 +314,22 @@ class WorldBatch:
                               dtype=torch.uint8)
         check(self._lib.ppb_render_async(self._h, ctypes.c_void_p(out.data_ptr()), _stream_handle(stream)))
         return out
+
+    def crop(self, frames, traj, crop_sz: int, stream=None):
+        """Ball-centred white-padded crops (dataio.py:160-182) of frames (F, n_worlds, H, W, 4) around the centres
+        traj (F, n_worlds, n_balls, 2): returns (crops (F, n_worlds, n_balls, c, c, 3) uint8, positions in crop
+        coordinates (F, n_worlds, n_balls, 2) float32), both CUDA tensors."""
+        import torch
+        F = int(frames.shape[0])
+        assert frames.is_cuda and frames.is_contiguous() and tuple(frames.shape[1:]) == (self.n_worlds, self.canvas_h, self.canvas_w, 4)
+        assert traj.is_cuda and traj.is_contiguous() and tuple(traj.shape) == (F, self.n_worlds, self.n_balls, 2)
+        dev = frames.device
+        crops = torch.empty((F, self.n_worlds, self.n_balls, crop_sz, crop_sz, 3), dtype=torch.uint8, device=dev)
+        pos = torch.empty((F, self.n_worlds, self.n_balls, 2), dtype=torch.float32, device=dev)
+        check(self._lib.ppb_crop_async(self._h, ctypes.c_void_p(frames.data_ptr()), ctypes.c_void_p(traj.data_ptr()), F,
+                                       int(crop_sz), ctypes.c_void_p(crops.data_ptr()), ctypes.c_void_p(pos.data_ptr()),
+                                       _stream_handle(stream)))
+        return crops, pos
 
     def simulate_host(self, n_steps: int, traj_host=None, frames_host=None, render_every: int = 1, stream=0):
         """Host-buffer path (DataSaver.fetch analogue): copies are inside the call.
