@@ -5,6 +5,7 @@ TAG=${1:-r1}
 OUT=gpurun_out
 mkdir -p $OUT
 python -m pytest tests -m gpu -x -q 2>&1 | tail -6 > $OUT/${TAG}_pytest_gpu.log
+python __graft_entry__.py --smoke > $OUT/${TAG}_smoke.log 2>&1
 python bench.py --impl reference --steps 10 --warmup 3 > $OUT/${TAG}_bench_reference.json 2> $OUT/${TAG}_bench_reference.err
 python bench.py --steps 50 --warmup 5 > $OUT/${TAG}_bench.json 2> $OUT/${TAG}_bench.err
 # launch list of the same command (cold-cache, serialised times: only the SHARES are comparable)
@@ -15,6 +16,8 @@ for K in integrate_kernel collide_kernel render_tile_kernel; do
   ncu --set full --import-source on --clock-control none -k regex:$K -s 8 -c 1 -f -o $OUT/${TAG}_full_$K \
       python tools/perf_probe.py --worlds 131072 --balls 8 --steps 12 --render --warm 8 --max-substeps 64 > $OUT/${TAG}_ncu_$K.log 2>&1
 done
+python tools/sweep.py --out $OUT/${TAG}_sweep.json > $OUT/${TAG}_sweep.log 2>&1
 tail -3 $OUT/${TAG}_pytest_gpu.log
+tail -2 $OUT/${TAG}_smoke.log
 head -c 600 $OUT/${TAG}_bench.json; echo
 head -c 400 $OUT/${TAG}_bench_reference.json; echo

@@ -63,7 +63,7 @@ def main():
                                  "source": "profiles/%s_ncu_%s.txt" % (rnd, kern)}
             fh.write("\n# heaviest SASS runs (instructions executed per launch)\n")
             fh.write(sass_blocks(rep))
-    for name in ("launches.csv", "bench.json", "bench_reference.json", "pytest_gpu.log"):
+    for name in ("launches.csv", "bench.json", "bench_reference.json", "pytest_gpu.log", "smoke.log", "sweep.json"):
         p = os.path.join(src, "%s_%s" % (tag, name))
         if os.path.exists(p):
             shutil.copy(p, os.path.join(dst, "%s_%s" % (rnd, name)))
