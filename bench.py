@@ -213,7 +213,18 @@ def run_ours(args, rank, local_rank, world_size):
     dev = torch.device("cuda", local_rank)
     distributed = world_size > 1
     if distributed and not dist.is_initialized():
-        dist.init_process_group("nccl", device_id=dev)
+        # NCCL prints its version banner on stdout at the first communicator; keep stdout for the JSON line
+        sys.stdout.flush()
+        saved = os.dup(1)
+        os.dup2(2, 1)
+        try:
+            dist.init_process_group("nccl", device_id=dev)
+            dist.barrier(device_ids=[local_rank])
+            torch.cuda.synchronize(dev)
+        finally:
+            sys.stdout.flush()
+            os.dup2(saved, 1)
+            os.close(saved)
 
     def barrier():
         if distributed:
