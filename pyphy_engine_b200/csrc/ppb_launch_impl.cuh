@@ -93,9 +93,10 @@ cudaError_t Launch<T>::render(const StatePtrs &S, const Layout &L, const RenderL
   for (int k = 0; k < L.n_obj; ++k)
     if (L.order[k] < L.n_walls && k >= L.n_walls) walls_first = false;
   if (walls_first && (RL.W & 3) == 0 && (reinterpret_cast<uintptr_t>(frames) & 15u) == 0) {
-    static_assert(PPB_RENDER_WARPS * sizeof(RenderWarpSmem) <= 227 * 1024, "render tiles exceed the 227 KB of shared memory per CTA");
-    static_assert(sizeof(RenderWarpSmem) % 16 == 0, "tile buffers must stay 16-byte aligned for cp.async.bulk");
-    const int smem = (int)(PPB_RENDER_WARPS * sizeof(RenderWarpSmem));
+    const int warps = render_warps(L.n_walls, L.n_balls);
+    const int smem = (int)(warps * render_warp_smem_bytes(L.n_walls, L.n_balls));
+    const int smem_max = (int)(PPB_RENDER_MAX_WARPS * render_warp_smem_bytes(0, 0) < 227 * 1024
+                                   ? 227 * 1024 : 227 * 1024);
     // per device (and per instantiation T): SM count, opt-in to the large dynamic shared memory
     static int sm_counts[64] = {0};
     int dev = 0;
@@ -104,15 +105,15 @@ cudaError_t Launch<T>::render(const StatePtrs &S, const Layout &L, const RenderL
     if (!sm_counts[dev]) {
       int n = 0;
       cudaDeviceGetAttribute(&n, cudaDevAttrMultiProcessorCount, dev);
-      cudaError_t e = cudaFuncSetAttribute(render_tile_kernel<T>, cudaFuncAttributeMaxDynamicSharedMemorySize, smem);
+      cudaError_t e = cudaFuncSetAttribute(render_tile_kernel<T>, cudaFuncAttributeMaxDynamicSharedMemorySize, smem_max);
       if (e != cudaSuccess) return e;
       sm_counts[dev] = n > 0 ? n : 1;
     }
     const int sm_count = sm_counts[dev];
-    // persistent: one CTA of PPB_RENDER_WARPS warps per SM, every warp walks the tile list
-    long long blocks = (jobs + PPB_RENDER_WARPS - 1) / PPB_RENDER_WARPS;
+    // persistent: one CTA of `warps` warps per SM, every warp walks the tile list
+    long long blocks = (jobs + warps - 1) / warps;
     if (blocks > sm_count) blocks = sm_count;
-    render_tile_kernel<T><<<(unsigned)blocks, PPB_RENDER_WARPS * 32, smem, st>>>(S, L, RL, atlas, frames);
+    render_tile_kernel<T><<<(unsigned)blocks, warps * 32, smem, st>>>(S, L, RL, atlas, frames);
   } else {
     if (jobs > 2147483647LL) return cudaErrorInvalidValue;
     render_general_kernel<T><<<(unsigned)jobs, 256, 0, st>>>(S, L, RL, atlas, frames);

@@ -374,7 +374,11 @@ __global__ void __launch_bounds__(256) render_general_kernel(StatePtrs S, Layout
 //           the buffer, and only waits (cp.async.bulk.wait_group.read) before overwriting it.
 // HBM sees exactly one full-line write per frame byte and a few hundred bytes of state reads.
 // ------------------------------------------------------------------------------------
-#define PPB_RENDER_WARPS 11   // 11 x 18.6 KB leaves room for one collide CTA per SM next to the render CTA
+// Warps per render CTA: as many as fit next to PPB_RENDER_SMEM_SPARE bytes left for the collide CTAs that
+// share the SM in the pipelined step (see render_warps()); the per-warp metadata is sized by the batch's
+// actual wall / ball counts.
+#define PPB_RENDER_MAX_WARPS 12
+#define PPB_RENDER_SMEM_SPARE (2 * (11264 + 1024) + 1024)
 struct RTBall {      // one ball inside the current tile, already clipped to it (32 bytes)
   uint32_t tex;      // atlas element index of the first visible sprite pixel
   uint32_t dst_sz;   // tile element offset of that pixel | sprite side << 16
@@ -389,13 +393,26 @@ struct RTBall {      // one ball inside the current tile, already clipped to it 
 #define PPB_WM_SOLID 1   // axis-aligned, integral edges, opaque colour: every pixel is either the colour or untouched
 #define PPB_WM_FAST 2    // axis-aligned with integral y edges: coverage depends on the column only
 #define PPB_WM_SLOW 3    // anything else: coverage evaluated per pixel
+// per-warp shared memory: the tile, then metadata arrays sized by (n_walls, n_balls)
 struct RenderWarpSmem {
-  uint32_t tile[PPB_TILE * PPB_TILE];   // 16 KB, source of the bulk store
-  int4 wpaint[PPB_MAX_WALLS];           // {PPB_WM_*, colour, first tile row | rows << 16, first column group | groups << 16}
-  int2 wspan[PPB_MAX_WALLS];            // SOLID: tile-local pixel columns [x0, x1)
-  SWallGeom w[PPB_MAX_WALLS];
-  RTBall b[PPB_MAX_BALLS];
+  uint32_t *tile;      // [PPB_TILE * PPB_TILE]  16 KB, source of the bulk store
+  int4 *wpaint;        // [n_walls] {PPB_WM_*, colour, first tile row | rows << 16, first column group | groups << 16}
+  int2 *wspan;         // [n_walls] SOLID: tile-local pixel columns [x0, x1)
+  SWallGeom *w;        // [n_walls]
+  RTBall *b;           // [n_balls]
 };
+__host__ __device__ inline size_t render_warp_smem_bytes(int n_walls, int n_balls) {
+  size_t meta = (size_t)n_walls * (sizeof(int4) + sizeof(int2) + sizeof(SWallGeom)) + (size_t)n_balls * sizeof(RTBall);
+  meta = (meta + 15) & ~(size_t)15;
+  return (size_t)PPB_TILE * PPB_TILE * 4 + meta;
+}
+// warps per CTA for a batch layout: fill the 227 KB, minus the spare for co-resident collide CTAs
+inline int render_warps(int n_walls, int n_balls) {
+  const size_t per = render_warp_smem_bytes(n_walls, n_balls);
+  int w = (int)((227 * 1024 - PPB_RENDER_SMEM_SPARE) / per);
+  if (w > PPB_RENDER_MAX_WARPS) w = PPB_RENDER_MAX_WARPS;
+  return w < 1 ? 1 : w;
+}
 
 __device__ __forceinline__ void bulk_store_s2g(void *gdst, const void *ssrc, uint32_t bytes) {
   asm volatile("cp.async.bulk.global.shared::cta.bulk_group [%0], [%1], %2;" ::"l"(gdst),
@@ -433,12 +450,21 @@ __global__ void wall_cache_kernel(StatePtrs S, int n_walls, RenderLayout RL, int
 }
 
 template <typename T>
-__global__ void __launch_bounds__(PPB_RENDER_WARPS * 32, 1) render_tile_kernel(StatePtrs S, Layout L, RenderLayout RL,
+__global__ void __maxnreg__(120) render_tile_kernel(StatePtrs S, Layout L, RenderLayout RL,
                                                                            const uint32_t *atlas, uint8_t *frames) {
   typedef typename Vec2<T>::type T2;
   extern __shared__ __align__(128) unsigned char render_smem_raw[];
   const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
-  RenderWarpSmem &sm = reinterpret_cast<RenderWarpSmem *>(render_smem_raw)[warp];
+  const int n_warps = blockDim.x >> 5;
+  RenderWarpSmem sm;
+  {
+    unsigned char *base = render_smem_raw + (size_t)warp * render_warp_smem_bytes(L.n_walls, L.n_balls);
+    sm.tile = reinterpret_cast<uint32_t *>(base);
+    sm.wpaint = reinterpret_cast<int4 *>(base + (size_t)PPB_TILE * PPB_TILE * 4);
+    sm.b = reinterpret_cast<RTBall *>(sm.wpaint + L.n_walls);              // 16-byte records first
+    sm.wspan = reinterpret_cast<int2 *>(sm.b + L.n_balls);
+    sm.w = reinterpret_cast<SWallGeom *>(sm.wspan + L.n_walls);            // 4-byte aligned members only
+  }
   const int tiles_x = (RL.W + PPB_TILE - 1) / PPB_TILE;
   const int tiles_y = (RL.H + PPB_TILE - 1) / PPB_TILE;
   const int tiles = tiles_x * tiles_y;
@@ -454,8 +480,8 @@ __global__ void __launch_bounds__(PPB_RENDER_WARPS * 32, 1) render_tile_kernel(S
   T2 bp;
   T brad = T(-1);
   bp.x = bp.y = T(0);
-  const long long job0 = (long long)blockIdx.x * PPB_RENDER_WARPS + warp;
-  const long long jstride = (long long)gridDim.x * PPB_RENDER_WARPS;
+  const long long job0 = (long long)blockIdx.x * n_warps + warp;
+  const long long jstride = (long long)gridDim.x * n_warps;
   auto load_world = [&](int wn) {
     if (lane < nWl) {
       const uint4 *src = reinterpret_cast<const uint4 *>(reinterpret_cast<const WallRC *>(S.wall_rc) + ((long long)wn * nWl + lane));
