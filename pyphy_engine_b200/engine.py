@@ -87,6 +87,7 @@ class WorldBatch:
         cfg.device = self.device
         cfg.dt, cfg.gx, cfg.gy, cfg.friction = float(dt), float(g[0]), float(g[1]), float(friction)
         cfg.event_capacity = int(event_capacity)
+        self.event_capacity = int(event_capacity)
         cfg.max_substeps = int(max_substeps)
         self._order = None
         if order is not None:
@@ -245,9 +246,9 @@ class WorldBatch:
         n = ctypes.c_int64(0)
         check(self._lib.ppb_read_events(self._h, None, 0, ctypes.byref(n), stream))
         total = n.value
-        buf = (Event * max(1, total))()
-        check(self._lib.ppb_read_events(self._h, buf, total, ctypes.byref(n), stream))
-        m = min(total, len(buf))
+        m = min(total, self.event_capacity)          # the ring keeps the first event_capacity records
+        buf = (Event * max(1, m))()
+        check(self._lib.ppb_read_events(self._h, buf, m, ctypes.byref(n), stream))
         raw = np.frombuffer(buf, dtype=np.dtype([("world", "<i4"), ("seq", "<i4"), ("step", "<i4"),
                                                   ("ball", "<i2"), ("partner", "<i2")]), count=m)
         idx = np.lexsort((raw["seq"], raw["world"]))

@@ -1,0 +1,132 @@
+"""C-ABI edge cases and error behaviour on a real device: argument validation, maximum slot counts,
+empty slots, tiny and ragged batches, state-machine errors."""
+import ctypes
+
+import numpy as np
+import pytest
+
+import oracle
+from pyphy_engine_b200 import _capi, sampler
+from pyphy_engine_b200.engine import WorldBatch
+
+pytestmark = pytest.mark.gpu
+
+
+def test_argument_validation():
+    with pytest.raises(_capi.PpbError, match="n_balls"):
+        WorldBatch(4, 0, 4)
+    with pytest.raises(_capi.PpbError, match="n_balls"):
+        WorldBatch(4, 33, 4)
+    with pytest.raises(_capi.PpbError, match="n_walls"):
+        WorldBatch(4, 2, 17)
+    with pytest.raises(_capi.PpbError, match="dt"):
+        WorldBatch(4, 2, 4, dt=0.0)
+    with pytest.raises(_capi.PpbError, match="permutation"):
+        WorldBatch(4, 2, 2, order=[0, 0, 2, 3])
+    with pytest.raises(_capi.PpbError, match="increasing"):
+        WorldBatch(4, 2, 1, order=[0, 2, 1])
+    with pytest.raises(_capi.PpbError, match="device"):
+        WorldBatch(4, 2, 4, device=99)
+    wb = WorldBatch(4, 2, 4)
+    with pytest.raises(_capi.PpbError, match="range"):
+        wb.get_balls(world0=3, count=5)
+    with pytest.raises(_capi.PpbError, match="mass"):
+        wb.set_balls(np.zeros((4, 2, 2)), np.zeros((4, 2, 2)), np.ones((4, 2)), np.zeros((4, 2)))
+    wc = WorldBatch(4, 2, 4, canvas=(32, 32))
+    with pytest.raises(_capi.PpbError, match="ppb_set_styles"):
+        wc.render()
+    with pytest.raises(_capi.PpbError, match="ppb_set_styles"):
+        wc.step(2, render_every=1)
+    wc.close()
+    import torch
+    wb.set_styles([(1, (0, 0, 0, 1), (0, 0, 0, 1))] * 2, [(0, (1, 0, 0, 1))] * 4, 3, 3)
+    with pytest.raises(_capi.PpbError, match="canvas"):
+        wb.render(out=torch.empty((4, 8, 8, 4), dtype=torch.uint8, device="cuda"))
+    lib = _capi.load()
+    assert lib.ppb_step_async(None, 1, None, None, 1, None) == -1 and b"null batch" in lib.ppb_last_error()
+    assert lib.ppb_version() >= 1
+    wb.close()
+    wb.close()      # idempotent
+
+
+def test_max_walls_and_empty_slots_bit_exact():
+    """16 wall slots (64 collision edges: a 16-gon cage) and ball slots left empty (radius < 0)."""
+    rng = np.random.RandomState(3)
+    n, nb, nw = 300, 6, 16
+    ang = 2 * np.pi * np.arange(nw) / nw
+    R = 300.0
+    pts = np.stack([400 + R * np.cos(ang), 400 + R * np.sin(ang)], -1)            # clockwise on screen (y down)
+    wall = sampler.cage_vertices(np.broadcast_to(pts, (n, nw, 2)).copy(), 20.0)
+    pos = np.zeros((n, nb, 2)); vel = rng.uniform(-900, 900, (n, nb, 2))
+    rad = np.full((n, nb), 18.0)
+    for w in range(n):                                                              # non-overlapping starts on a small ring
+        a0 = rng.uniform(0, 2 * np.pi)
+        for b in range(nb):
+            pos[w, b] = (400 + 120 * np.cos(a0 + b * 2 * np.pi / nb), 400 + 120 * np.sin(a0 + b * 2 * np.pi / nb))
+    rad[::3, 4:] = -1.0                                                             # every third world has 2 empty slots
+    mass = sampler.ball_mass(np.abs(rad))
+    wb = WorldBatch(n, nb, nw, dtype="f64", event_capacity=1 << 20, max_substeps=4096)
+    wb.set_walls(wall)
+    wb.set_balls(pos, vel, rad, mass)
+    ob = oracle.OracleBatch(wall, pos, vel, rad, mass, trig_mode=1, max_substeps=4096)
+    traj, _ = wb.step(120, record_traj=True)
+    otraj, oev = ob.step(120, record_traj=True, max_events=1 << 20)
+    status, _ = wb.get_status()
+    assert np.array_equal(status, ob.status)
+    alive = ob.status == 0
+    live_slots = (rad >= 0)[alive]
+    assert np.array_equal(traj.cpu().numpy()[:, alive][:, live_slots], otraj[:, alive][:, live_slots])
+    ev, total = wb.read_events()
+    assert total == len(oev) > 0 and np.array_equal(ev, oev)
+    assert alive.mean() > 0.9
+    wb.close()
+
+
+def test_single_world_single_ball_and_ragged_sizes():
+    for n, nb in ((1, 1), (33, 5), (257, 7)):
+        W = sampler.sample_rect_worlds(n, nb, seed=n, arena=1200, mn_wlen=700, mx_wlen=1000)
+        wb = WorldBatch(n, nb, 4, dtype="f64", event_capacity=1 << 18)
+        wb.set_walls(W["wall"]); wb.set_balls(W["pos"], W["vel"], W["rad"], W["mass"])
+        ob = oracle.OracleBatch(W["wall"], W["pos"], W["vel"], W["rad"], W["mass"], trig_mode=1)
+        traj, _ = wb.step(80, record_traj=True)
+        otraj, oev = ob.step(80, record_traj=True, max_events=1 << 18)
+        ok = ob.status == 0
+        assert np.array_equal(wb.get_status()[0], ob.status)
+        assert np.array_equal(traj.cpu().numpy()[:, ok], otraj[:, ok])
+        assert np.array_equal(wb.read_events()[0], oev)
+        wb.close()
+
+
+def test_event_buffer_overflow_is_counted_not_fatal():
+    W = sampler.sample_rect_worlds(2048, 4, seed=9)
+    wb = WorldBatch(2048, 4, 4, dtype="f32", event_capacity=64, max_substeps=256)
+    wb.set_walls(W["wall"]); wb.set_balls(W["pos"], W["vel"], W["rad"], W["mass"])
+    wb.step(200)
+    ev, total = wb.read_events()
+    assert len(ev) == 64 and total > 1000
+    assert wb.counters()["events"] == total
+    wb.clear_events()
+    assert wb.read_events()[1] == 0
+    wb.close()
+
+
+def test_partial_world_range_updates():
+    """set_walls / set_balls / requeue on a sub-range leave the other worlds untouched."""
+    W = sampler.sample_rect_worlds(64, 3, seed=2)
+    a = WorldBatch(64, 3, 4, dtype="f64"); b = WorldBatch(64, 3, 4, dtype="f64")
+    for wb in (a, b):
+        wb.set_walls(W["wall"]); wb.set_balls(W["pos"], W["vel"], W["rad"], W["mass"])
+        wb.step(30)
+    # rewrite worlds 16..31 of `a` with their initial state, step both, compare outside / inside the range
+    a.set_walls(W["wall"][16:32], world0=16)
+    a.set_balls(W["pos"][16:32], W["vel"][16:32], W["rad"][16:32], W["mass"][16:32], world0=16)
+    a.step(30); b.step(30)
+    pa, _ = a.get_balls(); pb, _ = b.get_balls()
+    keep = np.r_[0:16, 32:64]
+    assert np.array_equal(pa[keep], pb[keep])
+    c = WorldBatch(16, 3, 4, dtype="f64")
+    c.set_walls(W["wall"][16:32]); c.set_balls(W["pos"][16:32], W["vel"][16:32], W["rad"][16:32], W["mass"][16:32])
+    c.step(30)
+    assert np.array_equal(pa[16:32], c.get_balls()[0])
+    for wb in (a, b, c):
+        wb.close()
