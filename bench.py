@@ -211,6 +211,9 @@ def run_ours(args, rank, local_rank, world_size):
         raise SystemExit("bench.py: no CUDA device -- the engine has no CPU fallback")
     torch.cuda.set_device(local_rank)
     dev = torch.device("cuda", local_rank)
+    from pyphy_engine_b200 import sharding as _sh
+    full_affinity = os.sched_getaffinity(0)
+    numa_node = _sh.bind_to_gpu_numa_node(local_rank) if world_size > 1 else None
     distributed = world_size > 1
     if distributed and not dist.is_initialized():
         # NCCL prints its version banner on stdout at the first communicator; keep stdout for the JSON line
@@ -225,6 +228,9 @@ def run_ours(args, rank, local_rank, world_size):
             sys.stdout.flush()
             os.dup2(saved, 1)
             os.close(saved)
+
+    # the last rendezvous waits for rank 0's CPU-baseline run: on gloo the other ranks sleep instead of spinning
+    cpu_group = dist.new_group(backend="gloo") if distributed else None
 
     def barrier():
         if distributed:
@@ -324,7 +330,8 @@ def run_ours(args, rank, local_rank, world_size):
         alg_bytes = [BYTES_K1_PER_BALL_STEP * n_worlds * N_BALLS, _bytes_k2_per_world_step(N_BALLS) * n_worlds,
                      BYTES_K3_PER_FRAME * n_worlds]
         achieved = [alg_bytes[i] / (avg_us[i] * 1e-6) / 1e9 if avg_us[i] > 0 else 0.0 for i in range(3)]
-        cpu = cpu_baseline(os.cpu_count() or 1)
+        os.sched_setaffinity(0, full_affinity)     # the CPU baseline may use every host core again
+        cpu = cpu_baseline(len(full_affinity))
         line = {
             "metric": "ball_steps_per_sec", "value": value, "unit": "ball-steps/s", "n_gpus": world_size,
             "steps": args.steps, "warmup": args.warmup, "ms_per_step": ms / max(args.steps, 1),
@@ -350,13 +357,15 @@ def run_ours(args, rank, local_rank, world_size):
             "e2e": {"value": live_total * N_BALLS * e2e_steps / e2e_s, "unit": "ball-steps/s",
                     "frames_per_sec": live_total * e2e_steps / e2e_s,
                     "h2d_bytes_per_step": int(h2d), "d2h_bytes_per_step": int(d2h), "steps": e2e_steps,
-                    "api": "WorldBatch.set_walls/set_balls + simulate_host (ppb_simulate_host), pinned host buffers"},
+                    "api": "WorldBatch.set_walls/set_balls + simulate_host (ppb_simulate_host), pinned host buffers",
+                    "numa_node_rank0": numa_node},
             "gpu_launches": int(launches_total),
             "clocks": {"sm_mhz": clk["sm_mhz"], "sm_max_mhz": clk["sm_max_mhz"], "reasons": clk["reasons"]},
         }
         print(json.dumps(line), flush=True)
     if distributed:
-        dist.barrier(device_ids=[local_rank])
+        torch.cuda.synchronize(dev)
+        dist.barrier(group=cpu_group)
         dist.destroy_process_group()
 
 

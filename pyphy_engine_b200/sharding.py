@@ -44,6 +44,37 @@ def sample_world_range(first: int, count: int, n_balls: int, seed0: int = 0, **s
     return {k: np.concatenate([p[k] for p in parts], 0) for k in parts[0]}
 
 
+def bind_to_gpu_numa_node(device: int) -> Optional[int]:
+    """Pin this process (and therefore its page-locked staging buffers, allocated first-touch) to the
+    CPU cores of the NUMA node the GPU hangs off, so that the frame D2H stream of each rank stays on
+    its own socket's memory controllers.  Returns the node, or None when the topology is not exposed."""
+    import os
+    try:
+        import torch
+        props = torch.cuda.get_device_properties(device)
+        bdf = "%04x:%02x:%02x.0" % (props.pci_domain_id, props.pci_bus_id, props.pci_device_id)
+        with open("/sys/bus/pci/devices/%s/numa_node" % bdf) as fh:
+            node = int(fh.read().strip())
+        if node < 0:
+            return None
+        with open("/sys/devices/system/node/node%d/cpulist" % node) as fh:
+            spec = fh.read().strip()
+        cpus = set()
+        for part in spec.split(","):
+            if "-" in part:
+                a, b = part.split("-")
+                cpus.update(range(int(a), int(b) + 1))
+            elif part:
+                cpus.add(int(part))
+        allowed = cpus & set(os.sched_getaffinity(0))
+        if not allowed:
+            return None
+        os.sched_setaffinity(0, allowed)
+        return node
+    except Exception:
+        return None
+
+
 def _dist():
     import torch.distributed as dist
     return dist
