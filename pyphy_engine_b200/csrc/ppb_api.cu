@@ -438,28 +438,46 @@ int ppb_set_balls(ppb_batch *b, int32_t world0, int32_t count, const double *pos
   CU(cudaSetDevice(b->cfg.device));
   cudaStream_t st = (cudaStream_t)stream;
   const size_t nB = (size_t)b->cfg.n_balls, n = (size_t)count * nB, off = (size_t)world0 * nB;
-  // empty slots carry zero velocity and position so that the integrate kernel may stream over them
-  bool any_empty = false;
-  for (size_t i = 0; i < n; ++i) {
-    if (rad[i] < 0) any_empty = true;
-    else if (!(mass[i] > 0)) return fail(PPB_E_INVALID, "mass has to be a positive number");  // primitives.py:588
+  // One pass over the slots, spread over host threads, straight into the page-locked staging buffer
+  // (batch dtype): [pos | vel | radius,mass].  Empty slots carry zero position and velocity so that the
+  // integrate kernel may stream over them.
+  const size_t esz = b->esz;
+  if ((rc = stage_reserve(b, n * 6 * esz))) return rc;
+  char *sp = (char *)b->stage, *sv = sp + n * 2 * esz, *sr = sv + n * 2 * esz;
+  const bool f64 = is64(b);
+  unsigned nt = std::thread::hardware_concurrency();
+  if (nt > 8) nt = 8;
+  if (nt < 1 || n < (1u << 16)) nt = 1;
+  std::vector<int> bad(nt, 0);
+  auto work = [&](unsigned t) {
+    const size_t per = (n + nt - 1) / nt, lo = t * per, hi = lo + per < n ? lo + per : n;
+    for (size_t i = lo; i < hi; ++i) {
+      const bool empty = rad[i] < 0;
+      if (!empty && !(mass[i] > 0)) bad[t] = 1;   // primitives.py:588
+      const double px = empty ? 0.0 : pos[2 * i], py = empty ? 0.0 : pos[2 * i + 1];
+      const double vx = empty ? 0.0 : vel[2 * i], vy = empty ? 0.0 : vel[2 * i + 1];
+      if (f64) {
+        ((double *)sp)[2 * i] = px; ((double *)sp)[2 * i + 1] = py;
+        ((double *)sv)[2 * i] = vx; ((double *)sv)[2 * i + 1] = vy;
+        ((double *)sr)[2 * i] = rad[i]; ((double *)sr)[2 * i + 1] = mass[i];
+      } else {
+        ((float *)sp)[2 * i] = (float)px; ((float *)sp)[2 * i + 1] = (float)py;
+        ((float *)sv)[2 * i] = (float)vx; ((float *)sv)[2 * i + 1] = (float)vy;
+        ((float *)sr)[2 * i] = (float)rad[i]; ((float *)sr)[2 * i + 1] = (float)mass[i];
+      }
+    }
+  };
+  if (nt == 1) work(0);
+  else {
+    std::vector<std::thread> th;
+    for (unsigned t = 0; t < nt; ++t) th.emplace_back(work, t);
+    for (auto &t : th) t.join();
   }
-  std::vector<double> rm(n * 2);
-  for (size_t i = 0; i < n; ++i) {
-    rm[2 * i] = rad[i];
-    rm[2 * i + 1] = mass[i];
-  }
-  if (any_empty) {
-    std::vector<double> p(pos, pos + n * 2), v(vel, vel + n * 2);
-    for (size_t i = 0; i < n; ++i)
-      if (rad[i] < 0) p[2 * i] = p[2 * i + 1] = v[2 * i] = v[2 * i + 1] = 0.0;
-    if ((rc = upload(b, b->S.pos, off * 2, p.data(), n * 2, st))) return rc;
-    if ((rc = upload(b, b->S.vel, off * 2, v.data(), n * 2, st))) return rc;
-  } else {
-    if ((rc = upload(b, b->S.pos, off * 2, pos, n * 2, st))) return rc;
-    if ((rc = upload(b, b->S.vel, off * 2, vel, n * 2, st))) return rc;
-  }
-  if ((rc = upload(b, b->S.rm, off * 2, rm.data(), n * 2, st))) return rc;
+  for (int f : bad)
+    if (f) return fail(PPB_E_INVALID, "mass has to be a positive number");
+  CU(cudaMemcpyAsync((char *)b->S.pos + off * 2 * esz, sp, n * 2 * esz, cudaMemcpyHostToDevice, st));
+  CU(cudaMemcpyAsync((char *)b->S.vel + off * 2 * esz, sv, n * 2 * esz, cudaMemcpyHostToDevice, st));
+  CU(cudaMemcpyAsync((char *)b->S.rm + off * 2 * esz, sr, n * 2 * esz, cudaMemcpyHostToDevice, st));
   CU(do_reset(b, world0, count, 0, st));
   CU(cudaStreamSynchronize(st));
   return PPB_OK;
