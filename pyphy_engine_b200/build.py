@@ -20,7 +20,7 @@ ARCH = ["-gencode", "arch=compute_100a,code=sm_100a"]
 COMMON = ["-O3", "-lineinfo", "-std=c++17", "-Xcompiler", "-fPIC", "-Xcompiler", "-fvisibility=hidden"]
 # (source, extra flags).  The fp64 "compat" kernels must not contract a*b+c into FMAs.
 UNITS = [
-    ("ppb_f32.cu", []),
+    ("ppb_f32.cu", ["-prec-div=false", "-prec-sqrt=false"]),
     ("ppb_f64.cu", ["-fmad=false"]),
     ("ppb_api.cu", []),
 ]
