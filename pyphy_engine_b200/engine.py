@@ -37,11 +37,12 @@ def _ip(a: Optional[np.ndarray]):
     return None if a is None else a.ctypes.data_as(ctypes.POINTER(ctypes.c_int32))
 
 
-def _stream_handle(stream) -> int:
-    """cudaStream_t of a torch stream / raw handle; None = torch's current stream."""
+def _stream_handle(stream, device=None) -> int:
+    """cudaStream_t of a torch stream / raw handle; None = torch's current stream (every WorldBatch
+    method defaults to it, so state transfers, steps and read-backs of one thread are stream-ordered)."""
     if stream is None:
         import torch
-        return int(torch.cuda.current_stream().cuda_stream)
+        return int(torch.cuda.current_stream(device).cuda_stream)
     if hasattr(stream, "cuda_stream"):
         return int(stream.cuda_stream)
     return int(stream)
@@ -57,7 +58,7 @@ def collision_flags(traj, thresh: float = 0.03, stream=None):
     flags = torch.empty((n_items, n_steps - 2), dtype=torch.uint8, device=traj.device)
     with torch.cuda.device(traj.device):
         check(_capi.load().ppb_collision_flags_async(ctypes.c_void_p(traj.data_ptr()), n_items, n_steps, float(thresh),
-                                                     ctypes.c_void_p(flags.data_ptr()), _stream_handle(stream)))
+                                                     ctypes.c_void_p(flags.data_ptr()), _stream_handle(stream, traj.device)))
     return flags
 
 
@@ -112,15 +113,15 @@ class WorldBatch:
             pass
 
     # ------------------------------------------------------------------ state in
-    def set_walls(self, wall, world0: int = 0, stream=0):
+    def set_walls(self, wall, world0: int = 0, stream=None):
         """wall: (count, n_walls, 4, 2) vertices (Bbox order, geometry.py:471-505)."""
         wall = np.ascontiguousarray(wall, np.float64)
         count = wall.shape[0] if self.n_walls else self.n_worlds - world0
         if self.n_walls and wall.shape[1:] != (self.n_walls, 4, 2):
             raise ValueError("wall must be (count, %d, 4, 2)" % self.n_walls)
-        check(self._lib.ppb_set_walls(self._h, world0, count, _dp(wall), stream))
+        check(self._lib.ppb_set_walls(self._h, world0, count, _dp(wall), _stream_handle(stream, self.device)))
 
-    def set_balls(self, pos, vel, rad, mass, world0: int = 0, stream=0):
+    def set_balls(self, pos, vel, rad, mass, world0: int = 0, stream=None):
         """pos, vel: (count, n_balls, 2); rad, mass: (count, n_balls) or broadcastable.
         Resets the collision caches of these worlds (Dynamics._include_object)."""
         pos = np.ascontiguousarray(pos, np.float64)
@@ -131,11 +132,11 @@ class WorldBatch:
         vel = np.ascontiguousarray(np.broadcast_to(np.asarray(vel, np.float64), shp + (2,)))
         rad = np.ascontiguousarray(np.broadcast_to(np.asarray(rad, np.float64), shp))
         mass = np.ascontiguousarray(np.broadcast_to(np.asarray(mass, np.float64), shp))
-        check(self._lib.ppb_set_balls(self._h, world0, count, _dp(pos), _dp(vel), _dp(rad), _dp(mass), stream))
+        check(self._lib.ppb_set_balls(self._h, world0, count, _dp(pos), _dp(vel), _dp(rad), _dp(mass), _stream_handle(stream, self.device)))
 
     def sample_rect_worlds(self, seed: int = 0, world0: int = 0, count: Optional[int] = None, world_index0: int = 0,
                            arena=700, w_thick=30, mn_wlen=300, mx_wlen=550, mn_ball=25, mx_ball=25, mn_force=3e4,
-                           mx_force=8e4, force_t=1.0, max_tries=500, stream=0) -> int:
+                           mx_force=8e4, force_t=1.0, max_tries=500, stream=None) -> int:
         """Fill worlds [world0, world0+count) with random rectangular tables drawn ON THE DEVICE from
         the DataSaver(isRect=True) distribution (dataio.py:198-416); returns the number of worlds that
         could not be filled.  World w depends on (seed, world_index0 + w) only."""
@@ -144,25 +145,25 @@ class WorldBatch:
                                  float(mx_ball), float(mn_force), float(mx_force), float(force_t), int(seed),
                                  int(world_index0), int(max_tries))
         nf = ctypes.c_int32(0)
-        check(self._lib.ppb_sample_rect_worlds(self._h, world0, count, ctypes.byref(sp), ctypes.byref(nf), stream))
+        check(self._lib.ppb_sample_rect_worlds(self._h, world0, count, ctypes.byref(sp), ctypes.byref(nf), _stream_handle(stream, self.device)))
         return nf.value
 
-    def get_walls(self, world0: int = 0, count: Optional[int] = None, stream=0):
+    def get_walls(self, world0: int = 0, count: Optional[int] = None, stream=None):
         """(count, n_walls, 4, 2) wall vertices read back from the device."""
         count = self.n_worlds - world0 if count is None else count
         wall = np.empty((count, self.n_walls, 4, 2), np.float64)
-        check(self._lib.ppb_get_walls(self._h, world0, count, _dp(wall), stream))
+        check(self._lib.ppb_get_walls(self._h, world0, count, _dp(wall), _stream_handle(stream, self.device)))
         return wall
 
-    def get_radius_mass(self, world0: int = 0, count: Optional[int] = None, stream=0):
+    def get_radius_mass(self, world0: int = 0, count: Optional[int] = None, stream=None):
         """(radius, mass) per ball slot, (count, n_balls) each; radius < 0 marks an empty slot."""
         count = self.n_worlds - world0 if count is None else count
         rad = np.empty((count, self.n_balls), np.float64)
         mass = np.empty((count, self.n_balls), np.float64)
-        check(self._lib.ppb_get_radius_mass(self._h, world0, count, _dp(rad), _dp(mass), stream))
+        check(self._lib.ppb_get_radius_mass(self._h, world0, count, _dp(rad), _dp(mass), _stream_handle(stream, self.device)))
         return rad, mass
 
-    def update_balls(self, pos=None, vel=None, world0: int = 0, stream=0):
+    def update_balls(self, pos=None, vel=None, world0: int = 0, stream=None):
         """ball.set_position / set_velocity: caches are left alone (primitives.py:462-466)."""
         ref = pos if pos is not None else vel
         if ref is None:
@@ -173,14 +174,14 @@ class WorldBatch:
         for a in (p, v):
             if a is not None and a.shape != (count, self.n_balls, 2):
                 raise ValueError("expected (count, n_balls, 2)")
-        check(self._lib.ppb_update_balls(self._h, world0, count, _dp(p), _dp(v), stream))
+        check(self._lib.ppb_update_balls(self._h, world0, count, _dp(p), _dp(v), _stream_handle(stream, self.device)))
 
-    def requeue(self, world0: int = 0, count: Optional[int] = None, stream=0):
+    def requeue(self, world0: int = 0, count: Optional[int] = None, stream=None):
         """Dynamics.add_all_dynamic_collision_queue (primitives.py:697-700)."""
         count = self.n_worlds - world0 if count is None else count
-        check(self._lib.ppb_requeue(self._h, world0, count, stream))
+        check(self._lib.ppb_requeue(self._h, world0, count, _stream_handle(stream, self.device)))
 
-    def set_styles(self, ball_styles, wall_styles, r_min: int, r_max: int, stream=0):
+    def set_styles(self, ball_styles, wall_styles, r_min: int, r_max: int, stream=None):
         """ball_styles: per slot (s_thick, fill rgba, stroke rgba); wall_styles: per slot (kind, fill rgba)."""
         bs = (BallStyle * self.n_balls)()
         for i, (st, fill, stroke) in enumerate(ball_styles):
@@ -191,64 +192,64 @@ class WorldBatch:
         for i, (kind, fill) in enumerate(wall_styles):
             ws[i].kind = int(kind)
             ws[i].fill[:] = [float(c) for c in fill]
-        check(self._lib.ppb_set_styles(self._h, bs, ws, int(r_min), int(r_max), stream))
+        check(self._lib.ppb_set_styles(self._h, bs, ws, int(r_min), int(r_max), _stream_handle(stream, self.device)))
 
     def set_gravity(self, gx: float, gy: float):
         """Dynamics.set_g (primitives.py:566); collision caches are left alone."""
         check(self._lib.ppb_set_gravity(self._h, float(gx), float(gy)))
 
-    def read_sprite(self, slot: int, radius: int, stream=0):
+    def read_sprite(self, slot: int, radius: int, stream=None):
         """get_ball_im (primitives.py:33-61) as built on the device: (sz, sz, 4) uint8, premultiplied."""
         sz = ctypes.c_int32(0)
-        check(self._lib.ppb_read_sprite(self._h, int(slot), int(radius), None, 0, ctypes.byref(sz), stream))
+        check(self._lib.ppb_read_sprite(self._h, int(slot), int(radius), None, 0, ctypes.byref(sz), _stream_handle(stream, self.device)))
         out = np.empty((sz.value, sz.value, 4), np.uint8)
         check(self._lib.ppb_read_sprite(self._h, int(slot), int(radius), ctypes.c_void_p(out.ctypes.data), out.nbytes,
-                                        ctypes.byref(sz), stream))
+                                        ctypes.byref(sz), _stream_handle(stream, self.device)))
         return out
 
     # ------------------------------------------------------------------ state out
-    def get_balls(self, world0: int = 0, count: Optional[int] = None, stream=0):
+    def get_balls(self, world0: int = 0, count: Optional[int] = None, stream=None):
         count = self.n_worlds - world0 if count is None else count
         pos = np.empty((count, self.n_balls, 2), np.float64)
         vel = np.empty((count, self.n_balls, 2), np.float64)
-        check(self._lib.ppb_get_balls(self._h, world0, count, _dp(pos), _dp(vel), stream))
+        check(self._lib.ppb_get_balls(self._h, world0, count, _dp(pos), _dp(vel), _stream_handle(stream, self.device)))
         return pos, vel
 
-    def get_collision_cache(self, world0: int = 0, count: Optional[int] = None, stream=0):
+    def get_collision_cache(self, world0: int = 0, count: Optional[int] = None, stream=None):
         count = self.n_worlds - world0 if count is None else count
         tcol = np.empty((count, self.n_balls), np.float64)
         partner = np.empty((count, self.n_balls), np.int32)
-        check(self._lib.ppb_get_collision_cache(self._h, world0, count, _dp(tcol), _ip(partner), stream))
+        check(self._lib.ppb_get_collision_cache(self._h, world0, count, _dp(tcol), _ip(partner), _stream_handle(stream, self.device)))
         return tcol, partner
 
     def scan(self, stream=None):
         """Drain the collision queue without stepping (time_to_collide_all for every queued ball)."""
-        check(self._lib.ppb_scan_async(self._h, _stream_handle(stream)))
+        check(self._lib.ppb_scan_async(self._h, _stream_handle(stream, self.device)))
 
-    def get_collision_response(self, world0: int = 0, count: Optional[int] = None, stream=0):
+    def get_collision_response(self, world0: int = 0, count: Optional[int] = None, stream=None):
         """(nrmlCol_, futureVel_) per ball: (count, n_balls, 2) each."""
         count = self.n_worlds - world0 if count is None else count
         nrml = np.empty((count, self.n_balls, 2), np.float64)
         fv = np.empty((count, self.n_balls, 2), np.float64)
-        check(self._lib.ppb_get_collision_response(self._h, world0, count, _dp(nrml), _dp(fv), stream))
+        check(self._lib.ppb_get_collision_response(self._h, world0, count, _dp(nrml), _dp(fv), _stream_handle(stream, self.device)))
         return nrml, fv
 
-    def get_status(self, world0: int = 0, count: Optional[int] = None, stream=0):
+    def get_status(self, world0: int = 0, count: Optional[int] = None, stream=None):
         """(status, steps_done) per world; for a halted world steps_done is the failing step."""
         count = self.n_worlds - world0 if count is None else count
         status = np.empty((count,), np.int32)
         steps = np.empty((count,), np.int32)
-        check(self._lib.ppb_get_status(self._h, world0, count, _ip(status), _ip(steps), stream))
+        check(self._lib.ppb_get_status(self._h, world0, count, _ip(status), _ip(steps), _stream_handle(stream, self.device)))
         return status, steps
 
-    def read_events(self, stream=0):
+    def read_events(self, stream=None):
         """(k, 4) int32 rows (world, step, ball, partner) sorted by (world, call order)."""
         n = ctypes.c_int64(0)
-        check(self._lib.ppb_read_events(self._h, None, 0, ctypes.byref(n), stream))
+        check(self._lib.ppb_read_events(self._h, None, 0, ctypes.byref(n), _stream_handle(stream, self.device)))
         total = n.value
         m = min(total, self.event_capacity)          # the ring keeps the first event_capacity records
         buf = (Event * max(1, m))()
-        check(self._lib.ppb_read_events(self._h, buf, m, ctypes.byref(n), stream))
+        check(self._lib.ppb_read_events(self._h, buf, m, ctypes.byref(n), _stream_handle(stream, self.device)))
         raw = np.frombuffer(buf, dtype=np.dtype([("world", "<i4"), ("seq", "<i4"), ("step", "<i4"),
                                                   ("ball", "<i2"), ("partner", "<i2")]), count=m)
         idx = np.lexsort((raw["seq"], raw["world"]))
@@ -256,13 +257,13 @@ class WorldBatch:
         out = np.stack([raw["world"], raw["step"], raw["ball"].astype(np.int32), raw["partner"].astype(np.int32)], 1)
         return out.astype(np.int32), total
 
-    def clear_events(self, stream=0):
-        check(self._lib.ppb_clear_events(self._h, stream))
+    def clear_events(self, stream=None):
+        check(self._lib.ppb_clear_events(self._h, _stream_handle(stream, self.device)))
 
-    def counters(self, stream=0):
+    def counters(self, stream=None):
         """dict(launches, collide_world_steps, collide_iterations, events)."""
         out = (ctypes.c_int64 * 4)()
-        check(self._lib.ppb_get_counters(self._h, out, stream))
+        check(self._lib.ppb_get_counters(self._h, out, _stream_handle(stream, self.device)))
         return dict(launches=out[0], collide_world_steps=out[1], collide_iterations=out[2], events=out[3])
 
     # ------------------------------------------------------------------ stepping
@@ -279,7 +280,7 @@ class WorldBatch:
         if frames is not None:
             assert frames.is_cuda and frames.is_contiguous()
             assert tuple(frames.shape) == (n_steps // render_every, self.n_worlds, self.canvas_h, self.canvas_w, 4)
-        check(self._lib.ppb_step_async(self._h, int(n_steps), tp, fp, int(render_every), _stream_handle(stream)))
+        check(self._lib.ppb_step_async(self._h, int(n_steps), tp, fp, int(render_every), _stream_handle(stream, self.device)))
         self.steps_done += int(n_steps)
 
     def step_ring_async(self, n_steps: int, frames, render_every: int = 1, traj=None, stream=None):
@@ -289,7 +290,7 @@ class WorldBatch:
         assert tuple(frames.shape[1:]) == (self.n_worlds, self.canvas_h, self.canvas_w, 4)
         tp = ctypes.c_void_p(traj.data_ptr()) if traj is not None else None
         check(self._lib.ppb_step_ring_async(self._h, int(n_steps), tp, ctypes.c_void_p(frames.data_ptr()),
-                                            int(frames.shape[0]), int(render_every), _stream_handle(stream)))
+                                            int(frames.shape[0]), int(render_every), _stream_handle(stream, self.device)))
         self.steps_done += int(n_steps)
 
     def step(self, n_steps: int = 1, record_traj: bool = False, render_every: int = 0, stream=None):
@@ -313,7 +314,7 @@ class WorldBatch:
         if out is None:
             out = torch.empty((self.n_worlds, self.canvas_h, self.canvas_w, 4), device=torch.device("cuda", self.device),
                               dtype=torch.uint8)
-        check(self._lib.ppb_render_async(self._h, ctypes.c_void_p(out.data_ptr()), _stream_handle(stream)))
+        check(self._lib.ppb_render_async(self._h, ctypes.c_void_p(out.data_ptr()), _stream_handle(stream, self.device)))
         return out
 
     def crop(self, frames, traj, crop_sz: int, stream=None):
@@ -329,10 +330,10 @@ class WorldBatch:
         pos = torch.empty((F, self.n_worlds, self.n_balls, 2), dtype=torch.float32, device=dev)
         check(self._lib.ppb_crop_async(self._h, ctypes.c_void_p(frames.data_ptr()), ctypes.c_void_p(traj.data_ptr()), F,
                                        int(crop_sz), ctypes.c_void_p(crops.data_ptr()), ctypes.c_void_p(pos.data_ptr()),
-                                       _stream_handle(stream)))
+                                       _stream_handle(stream, self.device)))
         return crops, pos
 
-    def simulate_host(self, n_steps: int, traj_host=None, frames_host=None, render_every: int = 1, stream=0):
+    def simulate_host(self, n_steps: int, traj_host=None, frames_host=None, render_every: int = 1, stream=None):
         """Host-buffer path (DataSaver.fetch analogue): copies are inside the call.
 
         traj_host: None or float32 array (n_steps, n_worlds, n_balls, 2);
@@ -346,7 +347,7 @@ class WorldBatch:
                 return ctypes.c_void_p(a.data_ptr())
             return ctypes.c_void_p(a.ctypes.data)
         check(self._lib.ppb_simulate_host(self._h, int(n_steps), _ptr(traj_host), _ptr(frames_host),
-                                          int(render_every), stream))
+                                          int(render_every), _stream_handle(stream, self.device)))
         self.steps_done += int(n_steps)
 
     # ------------------------------------------------------------------ profiling
