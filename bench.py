@@ -342,7 +342,8 @@ def run_ours(args, rank, local_rank, world_size):
                        "l2": "per-step working set (2 GiB of frames + 70 MB of state per GPU) exceeds the 126 MB L2",
                        "schedule": "render of step k on its own stream overlaps integrate+collide of step k+1; frames into a 2-slot ring",
                        "max_substeps": MAX_SUBSTEPS, "halted_worlds": int(total_worlds - live_total),
-                       "events_per_world_step": events_total / (total_worlds * max(args.steps, 1))},
+                       "events_per_world_step": events_total / (total_worlds * max(args.steps, 1)),
+                       "pair_tests_per_sec_rank0": (c1["pair_tests"] - c0["pair_tests"]) / (ms * 1e-3)},
             "roofline": {"bound": "hbm", "kernel": names[dom], "achieved": achieved[dom], "peak": peak,
                          "unit": "GB/s", "frac": achieved[dom] / peak, "traffic": load_traffic(names[dom]), "peak_source": peak_src,
                          "avg_launch_us": float(avg_us[dom]),

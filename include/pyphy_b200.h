@@ -269,8 +269,10 @@ PPB_API int ppb_clear_events(ppb_batch *b, void *stream);
 
 /* counters since creation: [0] kernels launched by this batch, [1] world-steps taken by the
  * collide kernel (all other world-steps went through the integrate kernel), [2] sub-step loop
- * iterations inside the collide kernel, [3] collision events */
-PPB_API int ppb_get_counters(ppb_batch *b, int64_t out[4], void *stream);
+ * iterations inside the collide kernel, [3] collision events, [4] world rescans (one rescan =
+ * time_to_collide_all for every ball of a world = n_balls x (4 n_walls + n_balls - 1) pair tests),
+ * [5..7] reserved (0) */
+PPB_API int ppb_get_counters(ppb_batch *b, int64_t out[8], void *stream);
 
 /* raw device pointers for zero-copy consumers (e.g. torch via __cuda_array_interface__):
  * which = 0: positions   [n_worlds][n_balls] x {x, y} (batch dtype)

@@ -930,7 +930,7 @@ int ppb_clear_events(ppb_batch *b, void *stream) {
   return PPB_OK;
 }
 
-int ppb_get_counters(ppb_batch *b, int64_t out[4], void *stream) {
+int ppb_get_counters(ppb_batch *b, int64_t out[8], void *stream) {
   if (!b || !out) return fail(PPB_E_INVALID, "null argument");
   CU(cudaSetDevice(b->cfg.device));
   unsigned long long c[4];
@@ -940,6 +940,8 @@ int ppb_get_counters(ppb_batch *b, int64_t out[4], void *stream) {
   out[1] = (int64_t)c[1];
   out[2] = (int64_t)c[2];
   out[3] = (int64_t)c[0];
+  out[4] = (int64_t)c[3];
+  out[5] = out[6] = out[7] = 0;
   return PPB_OK;
 }
 

@@ -92,7 +92,7 @@ cudaError_t Launch<T>::render(const StatePtrs &S, const Layout &L, const RenderL
   bool walls_first = true;
   for (int k = 0; k < L.n_obj; ++k)
     if (L.order[k] < L.n_walls && k >= L.n_walls) walls_first = false;
-  if (walls_first && (RL.W & 3) == 0 && (reinterpret_cast<uintptr_t>(frames) & 15u) == 0) {
+  if (walls_first && (reinterpret_cast<uintptr_t>(frames) & 3u) == 0) {
     const int warps = render_warps(L.n_walls, L.n_balls);
     const int smem = (int)(warps * render_warp_smem_bytes(L.n_walls, L.n_balls));
     const int smem_max = (int)(PPB_RENDER_MAX_WARPS * render_warp_smem_bytes(0, 0) < 227 * 1024

@@ -358,8 +358,7 @@ __global__ void __launch_bounds__(256) render_general_kernel(StatePtrs S, Layout
 }
 
 // ------------------------------------------------------------------------------------
-// K3 fast path: walls inserted before balls (every DataSaver world), W % 4 == 0 and a 16-byte
-// aligned frame buffer.
+// K3 fast path: walls inserted before balls (every DataSaver world).
 //
 // One warp owns one 64x64 tile (a whole frame on the 64x64 canvas) at a time and builds it in
 // its private 16 KB of shared memory:
@@ -471,6 +470,7 @@ __global__ void __maxnreg__(120) render_tile_kernel(StatePtrs S, Layout L, Rende
   const long long total = (long long)S.n_worlds * tiles;
   const int nB = L.n_balls, nWl = L.n_walls;
   const bool whole_rows = (RL.W == PPB_TILE);   // tile rows are contiguous in the frame
+  const bool bulk_ok = ((RL.W & 3) == 0) && ((reinterpret_cast<uintptr_t>(frames) & 15u) == 0);
   // raw state of the world of the current / next tile, held in registers: lane q < nWl keeps wall q's
   // WallRC, lane b keeps ball b's position and radius.  The next tile's loads are
   // issued before the current tile is drawn, so their latency hides behind the drawing.
@@ -673,7 +673,14 @@ __global__ void __maxnreg__(120) render_tile_kernel(StatePtrs S, Layout L, Rende
     fence_async_smem();   // this lane's generic-proxy writes become visible to the async proxy
     __syncwarp();
     uint32_t *out = reinterpret_cast<uint32_t *>(frames) + (size_t)w * RL.W * RL.H;
-    if (whole_rows) {
+    if (!bulk_ok) {
+      // rows of this canvas are not 16-byte aligned (e.g. the reference's default arenaSz = 667):
+      // the copy engine cannot take them, the warp stores the tile row by row (coalesced 128-byte stores)
+      for (int r = 0; r < th; ++r) {
+        uint32_t *orow = out + (size_t)(ty0 + r) * RL.W + tx0;
+        for (int c = lane; c < tw; c += 32) orow[c] = sm.tile[r * PPB_TILE + c];
+      }
+    } else if (whole_rows) {
       if (lane == 0) bulk_store_s2g(out + (size_t)ty0 * RL.W, sm.tile, (uint32_t)th * PPB_TILE * 4u);
     } else {
       const uint32_t row_bytes = (uint32_t)tw * 4u;

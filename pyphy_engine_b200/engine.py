@@ -261,10 +261,12 @@ class WorldBatch:
         check(self._lib.ppb_clear_events(self._h, _stream_handle(stream, self.device)))
 
     def counters(self, stream=None):
-        """dict(launches, collide_world_steps, collide_iterations, events)."""
-        out = (ctypes.c_int64 * 4)()
+        """dict(launches, collide_world_steps, collide_iterations, events, rescans, pair_tests)."""
+        out = (ctypes.c_int64 * 8)()
         check(self._lib.ppb_get_counters(self._h, out, _stream_handle(stream, self.device)))
-        return dict(launches=out[0], collide_world_steps=out[1], collide_iterations=out[2], events=out[3])
+        per_rescan = self.n_balls * (4 * self.n_walls + self.n_balls - 1)
+        return dict(launches=out[0], collide_world_steps=out[1], collide_iterations=out[2], events=out[3],
+                    rescans=out[4], pair_tests=out[4] * per_rescan)
 
     # ------------------------------------------------------------------ stepping
     def step_async(self, n_steps: int = 1, traj=None, frames=None, render_every: int = 1, stream=None):
