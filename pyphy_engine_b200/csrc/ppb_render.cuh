@@ -480,6 +480,8 @@ __global__ void __maxnreg__(120) render_tile_kernel(StatePtrs S, Layout L, Rende
   T2 bp;
   T brad = T(-1);
   bp.x = bp.y = T(0);
+  // small-sprite walk cached per lane: key = (visible width, height, sprite side), offsets of the lane's two pixels
+  uint32_t sp_key = 0u, sp_t1 = 0xffffffffu, sp_t2 = 0xffffffffu, sp_d1 = 0u, sp_d2 = 0u;
   const long long job0 = (long long)blockIdx.x * n_warps + warp;
   const long long jstride = (long long)gridDim.x * n_warps;
   auto load_world = [&](int wn) {
@@ -638,13 +640,39 @@ __global__ void __maxnreg__(120) render_tile_kernel(StatePtrs S, Layout L, Rende
       __syncwarp();
     }
     // ---- pass 2: ball sprites, composited in place in insertion order.  All lanes work on one
-    //      sprite: lane -> pixel (sy, sx) of its visible part, then +32 pixels per iteration ----
+    //      sprite: lane -> pixel (sy, sx) of its visible part, then +32 pixels per iteration.
+    //      Small sprites (<= 64 visible pixels: two per lane) take a short path whose per-lane pixel
+    //      offsets only depend on (visible width, height, sprite side) -- the same for every unclipped
+    //      ball of one radius -- and are kept in registers from ball to ball and tile to tile ----
     for (int b = 0; b < nB; ++b) {
       const uint4 ra = reinterpret_cast<const uint4 *>(&sm.b[b])[0];   // tex, dst_sz, aw_ah, inv_aw
       if (ra.z == 0u) continue;
-      const uint4 rb = reinterpret_cast<const uint4 *>(&sm.b[b])[1];   // dti, ddi, wti_wdi, dq_dr
       const int aw = (int)(ra.z & 0xffffu), ah = (int)(ra.z >> 16);
       const int sz = (int)(ra.y >> 16);
+      if (aw * ah <= 64) {
+        const uint32_t key = ra.z ^ (ra.y & 0xffff0000u) ^ 0x80000000u;   // (aw, ah, sz); never 0
+        if (key != sp_key) {
+          sp_key = key;
+          const float inv = __uint_as_float(ra.w);
+          const int y1 = (int)(((float)lane + 0.5f) * inv), x1 = lane - y1 * aw;
+          const int y2 = (int)(((float)(lane + 32) + 0.5f) * inv), x2 = lane + 32 - y2 * aw;
+          sp_t1 = (y1 < ah) ? (uint32_t)(y1 * sz + x1) : 0xffffffffu;
+          sp_d1 = (uint32_t)(y1 * PPB_TILE + x1);
+          sp_t2 = (y2 < ah) ? (uint32_t)(y2 * sz + x2) : 0xffffffffu;
+          sp_d2 = (uint32_t)(y2 * PPB_TILE + x2);
+        }
+        const uint32_t dst = ra.y & 0xffffu;
+        const bool v1 = sp_t1 != 0xffffffffu, v2 = sp_t2 != 0xffffffffu;
+        const uint32_t t1 = v1 ? __ldg(atlas + ra.x + sp_t1) : 0u;
+        const uint32_t t2 = v2 ? __ldg(atlas + ra.x + sp_t2) : 0u;
+        const uint32_t d1 = v1 ? sm.tile[dst + sp_d1] : 0u;
+        const uint32_t d2 = v2 ? sm.tile[dst + sp_d2] : 0u;
+        if (v1) sm.tile[dst + sp_d1] = over_nb(t1, d1);
+        if (v2) sm.tile[dst + sp_d2] = over_nb(t2, d2);
+        __syncwarp();
+        continue;
+      }
+      const uint4 rb = reinterpret_cast<const uint4 *>(&sm.b[b])[1];   // dti, ddi, wti_wdi, dq_dr
       int sy = (int)(((float)lane + 0.5f) * __uint_as_float(ra.w));
       int sx = lane - sy * aw;
       const int dq = (int)(rb.w & 0xffffu), dr = (int)(rb.w >> 16);
