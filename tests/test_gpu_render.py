@@ -171,3 +171,55 @@ def test_pipelined_ring_equals_serial_stepping():
     pa, va = a.get_balls()
     pb, vb = b.get_balls()
     assert np.array_equal(pa, pb) and np.array_equal(va, vb)
+
+
+def test_full_size_frame_properties():
+    """BASELINE configs[3] shard at full size (131,072 worlds x 8 balls, 64x64 frames): properties that
+    do not need the oracle -- wall pixels per frame equal the analytic area of the cage rectangles, the
+    pixel under every ball centre has the fill colour, rendering is idempotent, balls stay in their cage."""
+    import torch
+    from pyphy_engine_b200 import sampler
+    from pyphy_engine_b200.engine import WorldBatch
+    n, nb = 131072, 8
+    wb = WorldBatch(n, nb, 4, dtype="f32", canvas=(64, 64), max_substeps=64)
+    assert wb.sample_rect_worlds(seed=77, **{k: v for k, v in sampler.scaled64_params(nb).items()}) == 0
+    wb.set_styles([(1, GRAY, BLACK)] * nb, [(0, RED)] * 4, 3, 3)
+    ring = torch.empty((2, n, 64, 64, 4), dtype=torch.uint8, device="cuda")
+    wb.step_ring_async(20, ring, 1)
+    torch.cuda.synchronize()
+    last = ring[(20 - 1) % 2]
+    again = wb.render()
+    assert torch.equal(again, last)                                   # the pipelined frame == a fresh render
+    status, _ = wb.get_status()
+    ok = status == 0
+    assert ok.mean() > 0.999
+    wall = wb.get_walls()
+    pos, _ = wb.get_balls()
+    # analytic wall area: union of the 4 integer rectangles, rasterised on the host in chunks
+    red = ((last[..., 0] == 255) & (last[..., 1] == 0) & (last[..., 2] == 0)).sum(dim=(1, 2)).cpu().numpy()
+    X = np.arange(64)[None, None, :] + 0.5
+    Y = np.arange(64)[None, :, None] + 0.5
+    for c0 in range(0, n, 16384):
+        w = wall[c0:c0 + 16384]
+        x0, x1 = w[..., 0].min(2), w[..., 0].max(2)               # (chunk, 4)
+        y0, y1 = w[..., 1].min(2), w[..., 1].max(2)
+        m = np.zeros((len(w), 64, 64), bool)
+        for q in range(4):
+            m |= (X >= np.round(x0[:, q])[:, None, None]) & (X < np.round(x1[:, q])[:, None, None]) & \
+                 (Y >= np.round(y0[:, q])[:, None, None]) & (Y < np.round(y1[:, q])[:, None, None])
+        area, got = m.sum((1, 2)), red[c0:c0 + 16384]
+        # a ball touching a wall tints a few wall pixels (its stroke ring reaches sThick/2 beyond the
+        # physical radius), so the count of pure wall-colour pixels can only fall short, and only slightly
+        assert np.all(got <= area) and np.all(area - got <= 8 * 8)
+        assert (got == area).mean() > 0.4
+    # the pixel containing every ball's (integer-snapped) centre is the fill colour
+    cx = np.clip(np.floor(np.abs(pos[..., 0]) + 0.5).astype(np.int64) - 1, 0, 63)   # centre lies on a pixel corner;
+    cy = np.clip(np.floor(np.abs(pos[..., 1]) + 0.5).astype(np.int64) - 1, 0, 63)   # the pixel up-left of it is inside
+    idx = torch.from_numpy(np.arange(n)[:, None].repeat(nb, 1)).cuda()
+    px = last[idx, torch.from_numpy(cy).cuda(), torch.from_numpy(cx).cuda()].cpu().numpy()
+    good = (px == np.array([128, 128, 128, 255], np.uint8)).all(-1)
+    assert good[ok].mean() > 0.999, good[ok].mean()                   # (a neighbour's ring may cover it in rare contacts)
+    lo = wall[:, 0, 0, :][:, None, :] + 3 + 3 - 0.01
+    hi = np.stack([wall[:, 1, 0, 0], wall[:, 2, 0, 1]], -1)[:, None, :] - 3 - 3 + 0.01
+    assert ((pos >= lo) & (pos <= hi)).all(axis=(1, 2))[ok].mean() > 0.999
+    wb.close()
