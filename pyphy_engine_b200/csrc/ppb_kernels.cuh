@@ -189,19 +189,48 @@ __device__ __forceinline__ int first_error(int err) {
 __device__ __forceinline__ float shfl_xor_t(float v, int o) { return __shfl_xor_sync(0xffffffffu, v, o); }
 __device__ __forceinline__ double shfl_xor_t(double v, int o) { return __shfl_xor_sync(0xffffffffu, v, o); }
 
-template <typename T, int LB>
+// partial scan result of one ball, exchanged between the warps of a team through shared memory
+template <typename T>
+struct ScanPart {
+  T t, nx, ny, fx, fy;
+  int k, partner, kfv, kerr, err;
+};
+template <typename T, int TW>
+struct TeamSmem {
+  WarpSmem<T> w;                                  // ball / edge staging shared by the team
+  ScanPart<T> part[TW > 1 ? TW : 1][TW > 1 ? 32 : 1];
+  int ticket;
+};
+
+template <int TW>
+__device__ __forceinline__ void team_sync(int team) {
+  if (TW > 1) asm volatile("bar.sync %0, %1;" ::"r"(1 + team), "r"(TW * 32) : "memory");
+  else __syncwarp();
+}
+
+// TW warps work on one world (a "team"): TW = 1 for up to 8 balls, 2 for 16, 4 for 32, so that a lane
+// never has more than a handful of scan items.  Every warp of a team holds the whole (replicated) ball
+// state and takes the same decisions; only the scan is split, and its partial results are exchanged
+// through shared memory.
+template <typename T, int LB, int TW>
 __global__ void __launch_bounds__(PPB_COLLIDE_WARPS * 32)
 collide_kernel(StatePtrs S, Layout L, StepParams P, T *traj) {
   typedef typename MathOf<T>::type M;
   typedef typename Vec2<T>::type T2;
   typedef typename Vec4<T>::type T4;
-  __shared__ WarpSmem<T> smem[PPB_COLLIDE_WARPS];
+  constexpr int TEAMS = PPB_COLLIDE_WARPS / TW;
+  __shared__ TeamSmem<T, TW> smem[TEAMS];
   const int lane = threadIdx.x & 31;
   const int warp = threadIdx.x >> 5;
-  WarpSmem<T> &sm = smem[warp];
+  const int team = warp / TW, wt = warp % TW;  // team in the CTA, warp in the team
+  TeamSmem<T, TW> &ts = smem[team];
+  WarpSmem<T> &sm = ts.w;
   const unsigned FULL = 0xffffffffu;
-  constexpr int G = 32 / LB;                   // lanes per ball
+  constexpr int G = 32 / LB;                   // lanes per ball inside a warp
+  constexpr int GT = G * TW;                   // scan groups per ball in the team
   const int bi = lane & (LB - 1), grp = lane / LB;
+  const int gid = wt * G + grp;                // this lane's scan group
+  const bool writer = (wt == 0) && (grp == 0); // the lane that owns ball bi's global state
   const int nB = L.n_balls, nWl = L.n_walls;
   const uint32_t k = (uint32_t)(*S.step_base + P.step_off);
   const T dt = (T)P.dt;
@@ -225,17 +254,24 @@ collide_kernel(StatePtrs S, Layout L, StepParams P, T *traj) {
 
   unsigned long long cnt_iters = 0, cnt_rescans = 0;
   int idx = 0;
-  if (lane == 0) idx = atomicAdd(ticket, 1);
-  idx = __shfl_sync(FULL, idx, 0);
+  if (TW == 1) {
+    if (lane == 0) idx = atomicAdd(ticket, 1);
+    idx = __shfl_sync(FULL, idx, 0);
+  } else {
+    if (wt == 0 && lane == 0) ts.ticket = atomicAdd(ticket, 1);
+    team_sync<TW>(team);
+    idx = ts.ticket;
+    team_sync<TW>(team);
+  }
 
   while (idx < count) {
     int idx_next = 0;
-    if (lane == 0) idx_next = atomicAdd(ticket, 1);   // its latency hides behind this world's work
+    if (wt == 0 && lane == 0) idx_next = atomicAdd(ticket, 1);   // its latency hides behind this world's work
     const int w = S.list[idx];
     const bool has_ball = bi < nB;
     const long long base = (long long)w * nB;
 
-    // ---- stage the world: ball state replicated over the G lanes of a ball, wall edges in smem ----
+    // ---- stage the world: ball state replicated over the lanes of a ball column, wall edges in smem ----
     V2<T> pos = mk<T>(0, 0), vel = pos, nrm = pos, fv = pos;
     T tc = INF, rad = T(-1), mass = T(1);
     int partner = -1;
@@ -256,15 +292,15 @@ collide_kernel(StatePtrs S, Layout L, StepParams P, T *traj) {
       tc = gtcol[base + bi];
       partner = S.partner[base + bi];
     }
-    __syncwarp();   // the previous world's readers of sm are done
-    for (int e = lane; e < nWl * 4; e += 32) {
+    team_sync<TW>(team);   // the previous world's readers of the staging area are done
+    for (int e = wt * 32 + lane; e < nWl * 4; e += TW * 32) {
       const T2 *wp = gwall + ((long long)w * nWl + (e >> 2)) * 4;
       const T2 a = wp[e & 3], b = wp[(e + 1) & 3];
       sm.edge[e] = M::make_edge(mk<T>(a.x, a.y), mk<T>(b.x, b.y));
     }
     flags = __shfl_sync(FULL, flags, 0);
     nev_base = __shfl_sync(FULL, nev_base, 0);
-    if (grp == 0) {
+    if (writer) {
       T2 q;
       q.x = rad; q.y = mass;
       sm.rm[bi] = q;
@@ -282,14 +318,14 @@ collide_kernel(StatePtrs S, Layout L, StepParams P, T *traj) {
     for (;;) {
       if (pending) {
         // colQueue_ drain: time_to_collide_all for every ball of the world (primitives.py:634-638)
-        __syncwarp();
-        if (grp == 0) {
+        team_sync<TW>(team);
+        if (writer) {
           T2 p, v;
           p.x = pos.x; p.y = pos.y; v.x = vel.x; v.y = vel.y;
           sm.pos[bi] = p;
           sm.vel[bi] = v;
         }
-        __syncwarp();
+        team_sync<TW>(team);
         tc = INF;
         partner = -1;
         int kbest = PPB_K_NONE, kfv = -1, kerr = PPB_K_NONE;
@@ -301,7 +337,7 @@ collide_kernel(StatePtrs S, Layout L, StepParams P, T *traj) {
           // with independent trips let the tests of several items overlap in the pipeline.
           const int nE = nWl << 2;
 #pragma unroll 4
-          for (int e = grp; e < nE; e += G) {
+          for (int e = gid; e < nE; e += GT) {
             // one edge of dynamics.get_toc_ball_wall (dynamics.py:20-59)
             const int kk = L.edge_k[e];
             T te;
@@ -314,7 +350,7 @@ collide_kernel(StatePtrs S, Layout L, StepParams P, T *traj) {
             }
           }
 #pragma unroll 2
-          for (int b2 = grp; b2 < nB; b2 += G) {
+          for (int b2 = gid; b2 < nB; b2 += GT) {
             const T2 q2 = sm.rm[b2];
             if (b2 == bi || q2.x < T(0)) continue;
             const int kk = L.ball_k[b2];
@@ -330,7 +366,7 @@ collide_kernel(StatePtrs S, Layout L, StepParams P, T *traj) {
             }
           }
         }
-        // merge the G partial scans of every ball
+        // merge the partial scans of every ball: inside the warp ...
 #pragma unroll
         for (int o = LB; o < 32; o <<= 1) {
           const T ot = shfl_xor_t(tc, o);
@@ -344,6 +380,26 @@ collide_kernel(StatePtrs S, Layout L, StepParams P, T *traj) {
           if (okf > kfv) { kfv = okf; fb = mk<T>(ofx, ofy); }
           const int oke = __shfl_xor_sync(FULL, kerr, o), oe = __shfl_xor_sync(FULL, err, o);
           if (oke < kerr) { kerr = oke; err = oe; }
+        }
+        // ... and across the warps of the team
+        if (TW > 1) {
+          if (grp == 0) {
+            ScanPart<T> sp;
+            sp.t = tc; sp.nx = nb.x; sp.ny = nb.y; sp.fx = fb.x; sp.fy = fb.y;
+            sp.k = kbest; sp.partner = partner; sp.kfv = kfv; sp.kerr = kerr; sp.err = err;
+            ts.part[wt][bi] = sp;
+          }
+          team_sync<TW>(team);
+#pragma unroll
+          for (int u = 0; u < TW; ++u) {
+            if (u == wt) continue;
+            const ScanPart<T> o = ts.part[u][bi];
+            if (o.t < tc || (o.t == tc && o.k < kbest)) {
+              tc = o.t; kbest = o.k; partner = o.partner; nb = mk<T>(o.nx, o.ny);
+            }
+            if (o.kfv > kfv) { kfv = o.kfv; fb = mk<T>(o.fx, o.fy); }
+            if (o.kerr < kerr) { kerr = o.kerr; err = o.err; }
+          }
         }
         // an item after a raising one is never visited by the reference; the world halts anyway
         if (kbest != PPB_K_NONE) nrm = nb;
@@ -379,9 +435,9 @@ collide_kernel(StatePtrs S, Layout L, StepParams P, T *traj) {
       const bool hit = active && (tc <= t);   // step_object, primitives.py:617
       const unsigned evm = __ballot_sync(FULL, hit && grp == 0);
       if (evm) {
-        // one record per resolve_collision call, in ball order
+        // one record per resolve_collision call, in ball order (written by the first warp of the team)
         const int n_ev = __popc(evm);
-        if (S.event_capacity > 0) {
+        if (S.event_capacity > 0 && wt == 0) {
           unsigned long long slot0 = 0;
           if (lane == 0) slot0 = atomicAdd(S.counters + 0, (unsigned long long)n_ev);
           slot0 = __shfl_sync(FULL, slot0, 0);
@@ -427,8 +483,8 @@ collide_kernel(StatePtrs S, Layout L, StepParams P, T *traj) {
       ++cnt_iters;
     }
 
-    // ---- write back (the group-0 lane of every ball) ----
-    if (has_ball && grp == 0) {
+    // ---- write back (the owning lane of every ball) ----
+    if (has_ball && writer) {
       T2 p, v;
       p.x = pos.x; p.y = pos.y; v.x = vel.x; v.y = vel.y;
       gpos[base + bi] = p;
@@ -443,7 +499,7 @@ collide_kernel(StatePtrs S, Layout L, StepParams P, T *traj) {
       if (traj) reinterpret_cast<T2 *>(traj)[((long long)P.step_off * S.n_worlds + w) * nB + bi] = p;
       if (S.snap) reinterpret_cast<T2 *>(S.snap)[base + bi] = p;
     }
-    if (lane == 0) {
+    if (wt == 0 && lane == 0) {
       Hdr<T> o;
       memset(&o, 0, sizeof o);
       o.tmin = mnt;
@@ -453,10 +509,17 @@ collide_kernel(StatePtrs S, Layout L, StepParams P, T *traj) {
       if (nev_local) S.nev[w] = nev_base + nev_local;
       if (S.event_capacity <= 0 && nev_local) atomicAdd(S.counters + 0, (unsigned long long)nev_local);
     }
-    idx = __shfl_sync(FULL, idx_next, 0);
+    if (TW == 1) {
+      idx = __shfl_sync(FULL, idx_next, 0);
+    } else {
+      if (wt == 0 && lane == 0) ts.ticket = idx_next;
+      team_sync<TW>(team);
+      idx = ts.ticket;
+      team_sync<TW>(team);
+    }
   }
-  // per-warp statistics (every lane counted the same)
-  if (lane == 0 && (cnt_iters | cnt_rescans)) {
+  // per-team statistics (every lane counted the same)
+  if (wt == 0 && lane == 0 && (cnt_iters | cnt_rescans)) {
     atomicAdd(S.counters + 2, cnt_iters);
     atomicAdd(S.counters + 3, cnt_rescans);
   }

@@ -26,7 +26,7 @@ cudaError_t Launch<T>::integrate(const StatePtrs &S, int n_balls, const StepPara
 template <typename T>
 int Launch<T>::collide_grid(int n_worlds, int sm_count) {
   int occ = 0;
-  cudaOccupancyMaxActiveBlocksPerMultiprocessor(&occ, collide_kernel<T, 8>, PPB_COLLIDE_WARPS * 32, 0);
+  cudaOccupancyMaxActiveBlocksPerMultiprocessor(&occ, collide_kernel<T, 8, 1>, PPB_COLLIDE_WARPS * 32, 0);
   if (occ < 1) occ = 1;
   const int need = (n_worlds + PPB_COLLIDE_WARPS - 1) / PPB_COLLIDE_WARPS;   // one world per warp at a time
   int grid = sm_count * occ;
@@ -39,12 +39,13 @@ cudaError_t Launch<T>::collide(const StatePtrs &S, const Layout &L, const StepPa
                                cudaStream_t st) {
   const int nb = L.n_balls;
   const dim3 blk(PPB_COLLIDE_WARPS * 32);
-  if (nb <= 1) collide_kernel<T, 1><<<grid, blk, 0, st>>>(S, L, P, (T *)traj);
-  else if (nb <= 2) collide_kernel<T, 2><<<grid, blk, 0, st>>>(S, L, P, (T *)traj);
-  else if (nb <= 4) collide_kernel<T, 4><<<grid, blk, 0, st>>>(S, L, P, (T *)traj);
-  else if (nb <= 8) collide_kernel<T, 8><<<grid, blk, 0, st>>>(S, L, P, (T *)traj);
-  else if (nb <= 16) collide_kernel<T, 16><<<grid, blk, 0, st>>>(S, L, P, (T *)traj);
-  else collide_kernel<T, 32><<<grid, blk, 0, st>>>(S, L, P, (T *)traj);
+  // lanes per world: one warp up to 8 balls, a team of 2 warps for 16, of 4 warps for 32
+  if (nb <= 1) collide_kernel<T, 1, 1><<<grid, blk, 0, st>>>(S, L, P, (T *)traj);
+  else if (nb <= 2) collide_kernel<T, 2, 1><<<grid, blk, 0, st>>>(S, L, P, (T *)traj);
+  else if (nb <= 4) collide_kernel<T, 4, 1><<<grid, blk, 0, st>>>(S, L, P, (T *)traj);
+  else if (nb <= 8) collide_kernel<T, 8, 1><<<grid, blk, 0, st>>>(S, L, P, (T *)traj);
+  else if (nb <= 16) collide_kernel<T, 16, 2><<<grid, blk, 0, st>>>(S, L, P, (T *)traj);
+  else collide_kernel<T, 32, 4><<<grid, blk, 0, st>>>(S, L, P, (T *)traj);
   return cudaGetLastError();
 }
 
