@@ -2,7 +2,10 @@
 
 Draws worlds from the distribution of the reference's ``DataSaver`` rectangular
 arena (``dataio.py:220-240`` walls, ``:309-379`` balls, ``:382-416`` forces) for
-many worlds at once.  It is *distribution*-equivalent, not RNG-stream-equivalent:
+many worlds at once.  It is *distribution*-equivalent (exactly so for a fixed ball radius; with a radius range it redraws
+the radius together with the position on every rejection, where the reference keeps the radius while
+it searches a position -- the device sampler ``WorldBatch.sample_rect_worlds`` follows the reference's
+loop structure), not RNG-stream-equivalent:
 the stream-exact generator used by the drop-in ``DataSaver`` lives in
 ``pyphy_engine_b200/dataio.py``.  The cage geometry uses the same arithmetic as
 ``primitives.get_box_coords`` (``primitives.py:177-195``).
