@@ -148,10 +148,12 @@ typedef struct ppb_sampler_params {
   uint64_t seed;
   int64_t world_index0;    /* global index of world 0 of this batch (sharded jobs) */
   int32_t max_tries;       /* give up on a world after this many rejections (dataio.py:359-362: 500) */
+  int32_t n_theta;         /* 0 = rectangular table (isRect); 1..4 = rhombus, side angle drawn from theta[] (wTheta) */
+  double theta[4];         /* degrees, dataio.py:243-306 */
 } ppb_sampler_params;
 
 /* DataSaver._generate_model + apply_force (dataio.py:198-416) for worlds [world0, world0+count),
- * drawn ON THE DEVICE: cage of 4 walls (the batch needs n_walls >= 4), n_balls balls placed by
+ * drawn ON THE DEVICE: rectangular or rhombus cage of 4 walls (the batch needs n_walls >= 4), n_balls balls placed by
  * rejection sampling, initial velocities from random kicks; collision caches reset as by
  * ppb_set_balls.  Distribution-equivalent to the reference (same loop structure and fp64
  * arithmetic) on a Philox stream keyed by (seed, world_index0 + world); the stream-exact sampler is

@@ -47,7 +47,8 @@ class SamplerParams(ctypes.Structure):
     _fields_ = [("arena", ctypes.c_double), ("w_thick", ctypes.c_double), ("mn_wlen", ctypes.c_double),
                 ("mx_wlen", ctypes.c_double), ("mn_ball", ctypes.c_double), ("mx_ball", ctypes.c_double),
                 ("mn_force", ctypes.c_double), ("mx_force", ctypes.c_double), ("force_t", ctypes.c_double),
-                ("seed", ctypes.c_uint64), ("world_index0", ctypes.c_int64), ("max_tries", ctypes.c_int32)]
+                ("seed", ctypes.c_uint64), ("world_index0", ctypes.c_int64), ("max_tries", ctypes.c_int32),
+                ("n_theta", ctypes.c_int32), ("theta", ctypes.c_double * 4)]
 
 
 class Event(ctypes.Structure):

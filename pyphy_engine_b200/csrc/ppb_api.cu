@@ -489,15 +489,19 @@ int ppb_sample_rect_worlds(ppb_batch *b, int32_t world0, int32_t count, const pp
   if (rc) return rc;
   if (!sp) return fail(PPB_E_INVALID, "null params");
   if (b->cfg.n_walls < 4) return fail(PPB_E_INVALID, "the rectangular cage needs 4 wall slots");
-  if (!(sp->mx_wlen >= sp->mn_wlen) || !(sp->mx_ball >= sp->mn_ball) || !(sp->mn_ball >= 1) ||
-      !(sp->arena > sp->mx_wlen + sp->w_thick) || sp->max_tries < 1)
+  if (!(sp->mx_wlen >= sp->mn_wlen) || !(sp->mx_ball >= sp->mn_ball) || !(sp->mn_ball >= 1) || sp->max_tries < 1 ||
+      sp->n_theta < 0 || sp->n_theta > 4 || (sp->n_theta == 0 && !(sp->arena > sp->mx_wlen + sp->w_thick)))
     return fail(PPB_E_INVALID, "inconsistent sampler parameters");
+  for (int i = 0; i < sp->n_theta; ++i)
+    if (!(sp->theta[i] > 0 && sp->theta[i] <= 90)) return fail(PPB_E_INVALID, "rhombus angles must be in (0, 90] degrees");
   CU(cudaSetDevice(b->cfg.device));
   cudaStream_t st = (cudaStream_t)stream;
   SamplerParams P;
   P.arena = sp->arena; P.w_thick = sp->w_thick; P.mn_wlen = sp->mn_wlen; P.mx_wlen = sp->mx_wlen;
   P.mn_ball = sp->mn_ball; P.mx_ball = sp->mx_ball; P.mn_force = sp->mn_force; P.mx_force = sp->mx_force;
   P.force_t = sp->force_t; P.seed = sp->seed; P.world_index0 = sp->world_index0; P.max_tries = sp->max_tries;
+  P.n_theta = sp->n_theta;
+  for (int i = 0; i < 4; ++i) P.theta[i] = sp->theta[i];
   int32_t *d_fail = reinterpret_cast<int32_t *>(b->S.counters + 6);   // spare counter slot
   CU(cudaMemsetAsync(d_fail, 0, sizeof(int32_t), st));
   CU(is64(b) ? Launch<double>::sample_rect(b->S, b->cfg.n_balls, b->cfg.n_walls, world0, count, P, b->host_step, d_fail, st)

@@ -16,6 +16,8 @@ struct SamplerParams {
   unsigned long long seed;
   long long world_index0;   // global index of the batch's world 0 (sharded jobs)
   int32_t max_tries;
+  int32_t n_theta;          // 0: rectangular table; > 0: rhombus with the side angle drawn from theta[] (degrees)
+  double theta[4];
 };
 
 struct Philox {
@@ -72,18 +74,51 @@ __global__ void sample_rect_worlds_kernel(StatePtrs S, int n_balls, int n_walls,
   const int w = world0 + i;
   Philox rng(P.seed, (unsigned long long)(P.world_index0 + w));
   const double Tk = P.w_thick;
-  // ---- cage: add_rectangular_walls -> _create_walls(xleft, ytop, (0, 90, 180), (hlen - T, vlen, hlen - T)) ----
-  const double hlen = floor(P.mn_wlen + rng.rand() * (P.mx_wlen - P.mn_wlen));
-  const double vlen = floor(P.mn_wlen + rng.rand() * (P.mx_wlen - P.mn_wlen));
-  const double xleft = floor(rng.rand() * (P.arena - (hlen + Tk)));
-  const double ytop = floor(rng.rand() * (P.arena - (vlen + Tk)));
-  // theta2dir(0 / 90 / 180) as numpy evaluates them (geometry.py:177-188)
-  const double dirx[3] = {1.0, 6.123233995736766e-17, -1.0};
-  const double diry[3] = {0.0, 1.0, 1.2246467991473532e-16};
-  const double wl[3] = {hlen - Tk, vlen, hlen - Tk};
   double px[4], py[4];
-  px[0] = xleft; py[0] = ytop;
-  for (int k = 0; k < 3; ++k) { px[k + 1] = px[k] + wl[k] * dirx[k]; py[k + 1] = py[k] + wl[k] * diry[k]; }
+  bool failed = false;
+  if (P.n_theta <= 0) {
+    // ---- cage: add_rectangular_walls -> _create_walls(xleft, ytop, (0, 90, 180), (hlen - T, vlen, hlen - T)) ----
+    const double hlen = floor(P.mn_wlen + rng.rand() * (P.mx_wlen - P.mn_wlen));
+    const double vlen = floor(P.mn_wlen + rng.rand() * (P.mx_wlen - P.mn_wlen));
+    const double xleft = floor(rng.rand() * (P.arena - (hlen + Tk)));
+    const double ytop = floor(rng.rand() * (P.arena - (vlen + Tk)));
+    // theta2dir(0 / 90 / 180) as numpy evaluates them (geometry.py:177-188)
+    const double dirx[3] = {1.0, 6.123233995736766e-17, -1.0};
+    const double diry[3] = {0.0, 1.0, 1.2246467991473532e-16};
+    const double wl[3] = {hlen - Tk, vlen, hlen - Tk};
+    px[0] = xleft; py[0] = ytop;
+    for (int k = 0; k < 3; ++k) { px[k + 1] = px[k] + wl[k] * dirx[k]; py[k + 1] = py[k] + wl[k] * diry[k]; }
+  } else {
+    // ---- rhombus: sample_walls (dataio.py:243-274) -> _create_walls(xleft, yleft, (-th, th, 180 - th), (h, h, h)) ----
+    const double kPiS = 3.141592653589793;
+    double wtheta = 0, hlen = 0, xleft = 0, yleft = 0;
+    int tries = 0;
+    for (;;) {
+      // rand_.permutation(n)[0] is uniform over the angles
+      int pick = (int)(rng.rand() * P.n_theta);
+      if (pick >= P.n_theta) pick = P.n_theta - 1;
+      wtheta = P.theta[pick];
+      const double rad = (wtheta * kPiS) / 180.0;
+      hlen = P.mn_wlen + rng.rand() * (P.mx_wlen - P.mn_wlen);
+      const double xlen = (wtheta == 90.0) ? hlen : hlen * cos(rad), ylen = (wtheta == 90.0) ? hlen : hlen * sin(rad);
+      const double xleftmin = Tk, xleftmax = P.arena - (2 * xlen + 2 * Tk);
+      const double yleftmin = ylen + Tk, yleftmax = (wtheta == 90.0) ? P.arena - Tk : P.arena - (ylen + Tk);
+      if (!(xleftmin <= 0 || yleftmin <= 0 || xleftmax < xleftmin || yleftmax < yleftmin)) {
+        xleft = xleftmin + floor(rng.rand() * (xleftmax - xleftmin));
+        yleft = yleftmin + floor(rng.rand() * (yleftmax - yleftmin));
+        break;
+      }
+      if (++tries >= P.max_tries) { failed = true; break; }
+    }
+    const double th[3] = {-wtheta, wtheta, 180.0 - wtheta};
+    px[0] = xleft; py[0] = yleft;
+    for (int k = 0; k < 3; ++k) {
+      const double a = kPiS * (th[k] / 180.0);   // theta2dir (geometry.py:177-188)
+      double dx = cos(a), dy = sin(a);
+      s_unit(dx, dy);
+      px[k + 1] = px[k] + hlen * dx; py[k + 1] = py[k] + hlen * dy;
+    }
+  }
   SLine cage[4];
   T *wall = reinterpret_cast<T *>(S.wall) + (long long)w * n_walls * 8;
   for (int k = 0; k < 4; ++k) {
@@ -108,7 +143,6 @@ __global__ void sample_rect_worlds_kernel(StatePtrs S, int n_balls, int n_walls,
     for (int j = 0; j < 8; ++j) wall[k * 8 + j] = T(0);
   // ---- balls: add_balls (dataio.py:328-379) ----
   double bx[PPB_MAX_BALLS], by[PPB_MAX_BALLS], br[PPB_MAX_BALLS];
-  bool failed = false;
   for (int b = 0; b < n_balls && !failed; ++b) {
     int outer = 0;
     for (;;) {

@@ -136,14 +136,19 @@ class WorldBatch:
 
     def sample_rect_worlds(self, seed: int = 0, world0: int = 0, count: Optional[int] = None, world_index0: int = 0,
                            arena=700, w_thick=30, mn_wlen=300, mx_wlen=550, mn_ball=25, mx_ball=25, mn_force=3e4,
-                           mx_force=8e4, force_t=1.0, max_tries=500, stream=None) -> int:
-        """Fill worlds [world0, world0+count) with random rectangular tables drawn ON THE DEVICE from
-        the DataSaver(isRect=True) distribution (dataio.py:198-416); returns the number of worlds that
-        could not be filled.  World w depends on (seed, world_index0 + w) only."""
+                           mx_force=8e4, force_t=1.0, max_tries=500, w_theta=None, stream=None) -> int:
+        """Fill worlds [world0, world0+count) with random tables drawn ON THE DEVICE from the DataSaver
+        distribution (dataio.py:198-416): rectangular (isRect=True) by default, rhombus tables with the
+        side angle drawn from ``w_theta`` (degrees, up to 4 values; isRect=False, wTheta) otherwise.
+        Returns the number of worlds that could not be filled.  World w depends on (seed, world_index0 + w) only."""
         count = self.n_worlds - world0 if count is None else count
+        thetas = [] if w_theta is None else ([float(w_theta)] if np.isscalar(w_theta) else [float(t) for t in w_theta])
+        if len(thetas) > 4:
+            raise ValueError("at most 4 rhombus angles")
         sp = _capi.SamplerParams(float(arena), float(w_thick), float(mn_wlen), float(mx_wlen), float(mn_ball),
                                  float(mx_ball), float(mn_force), float(mx_force), float(force_t), int(seed),
-                                 int(world_index0), int(max_tries))
+                                 int(world_index0), int(max_tries), len(thetas),
+                                 (ctypes.c_double * 4)(*(thetas + [0.0] * (4 - len(thetas)))))
         nf = ctypes.c_int32(0)
         check(self._lib.ppb_sample_rect_worlds(self._h, world0, count, ctypes.byref(sp), ctypes.byref(nf), _stream_handle(stream, self.device)))
         return nf.value

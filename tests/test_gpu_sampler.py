@@ -128,3 +128,48 @@ def test_too_small_cage_is_reported_not_hung():
     rad, _ = wb.get_radius_mass()
     assert np.all(rad < 0)
     wb.close()
+
+
+def test_rhombus_tables_against_the_reference_recipe(tmp_path):
+    """isRect=False (dataio.py:243-306) on the device: constraints + moments vs the stream-exact DataSaver."""
+    import pyphy_engine_b200.dataio as dio
+    nb = 3
+    kw = dict(arena=1600, w_thick=30, mn_wlen=500, mx_wlen=800, mn_ball=25, mx_ball=25, mn_force=3e4, mx_force=8e4,
+              w_theta=[30, 60])
+    wb, nf, wall, pos, vel, rad, mass = _sample(30000, nb, 5, **kw)
+    assert nf == 0
+    pts = wall[:, :, 0, :]
+    side = np.linalg.norm(np.roll(pts, -1, axis=1) - pts, axis=-1)
+    assert np.allclose(side, side[:, :1], rtol=0, atol=1e-9)                  # a rhombus: four equal sides
+    assert np.all((side[:, 0] >= 500) & (side[:, 0] <= 800))
+    ang = np.degrees(np.arctan2(-(pts[:, 1, 1] - pts[:, 0, 1]), pts[:, 1, 0] - pts[:, 0, 0]))
+    assert np.all(np.isclose(ang, 30, atol=1e-9) | np.isclose(ang, 60, atol=1e-9))
+    assert abs(np.isclose(ang, 30, atol=1e-9).mean() - 0.5) < 0.02
+    assert wall.min() >= 0 and wall.max() <= 1600
+    # every ball keeps r + wThick + 2 from every cage line (signed distance, dataio.py:356) and off the others
+    for q in range(4):
+        p0, p1 = pts[:, q], pts[:, (q + 1) % 4]
+        a = -(p1[:, 1] - p0[:, 1]); b = p1[:, 0] - p0[:, 0]; c = p0[:, 0] * p1[:, 1] - p0[:, 1] * p1[:, 0]
+        d = (a[:, None] * pos[..., 0] + b[:, None] * pos[..., 1] + c[:, None]) / np.sqrt(a * a + b * b)[:, None]
+        assert np.all(np.abs(d) > 25 + 30 + 2 - 1e-6)
+    dd = np.linalg.norm(pos[:, :, None, :] - pos[:, None, :, :], axis=-1) + np.eye(nb)[None] * 1e9
+    assert np.all(dd > 50)
+    ds = dio.DataSaver(rootPath=str(tmp_path), makeDirs=False, randSeed=9, numBalls=nb, mnBallSz=25, mxBallSz=25,
+                       mnForce=3e4, mxForce=8e4, wThick=30, isRect=False, wTheta=[30, 60], mnWLen=500, mxWLen=800,
+                       arenaSz=1600, mnSeqLen=10, mxSeqLen=10)
+    R = dict(x0=[], y0=[], side=[], relx=[])
+    for sp in ds.sample_sequences(1500):
+        R["x0"].append(sp.cage_pts[0].x()); R["y0"].append(sp.cage_pts[0].y())
+        R["side"].append((sp.cage_pts[1] - sp.cage_pts[0]).mag())
+        for b in sp.model.world_.dynamic_.values():
+            R["relx"].append(b.pos_.x() - sp.cage_pts[0].x())
+    D = dict(x0=pts[:, 0, 0], y0=pts[:, 0, 1], side=side[:, 0], relx=(pos[:, :, 0] - pts[:, 0, 0][:, None]).ravel())
+    for k in R:
+        r, d = np.asarray(R[k]), np.asarray(D[k])
+        se = r.std() / np.sqrt(len(r)) + d.std() / np.sqrt(len(d))
+        assert abs(r.mean() - d.mean()) < 4.5 * se, (k, r.mean(), d.mean(), se)
+        assert abs(r.std() - d.std()) < 0.08 * r.std(), (k, r.std(), d.std())
+    # and they simulate: 100 fp64 steps without a reference assertion
+    wb.step(100)
+    assert (wb.get_status()[0] == 0).mean() > 0.99
+    wb.close()

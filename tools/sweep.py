@@ -3,40 +3,19 @@ balls per world on rectangular and rhombus (polygonal-wall) tables, fp32, one GP
 
     python tools/sweep.py [--out gpurun_out/sweep.json]
 
-Rectangular tables come from the device sampler; rhombus tables from the stream-exact DataSaver
-(isRect=False, dataio.py:243-306) -- 512 sampled tables tiled to the batch size.
+Both table kinds come from the device sampler (ppb_sample_rect_worlds; rhombus = isRect=False,
+wTheta=[30, 60], dataio.py:243-306).
 """
 import argparse
 import json
 import os
 import sys
-import tempfile
 
 import numpy as np
 import torch
 
 sys.path.insert(0, os.path.dirname(os.path.dirname(os.path.abspath(__file__))))
 from pyphy_engine_b200.engine import WorldBatch  # noqa: E402
-
-
-def rhombus_worlds(n_worlds, n_balls, seed=1, n_src=512):
-    import pyphy_engine_b200.dataio as dio
-    arena = {4: 1600, 8: 2000, 16: 2600, 32: 3600}[n_balls]
-    wl = {4: (500, 800), 8: (800, 1100), 16: (1100, 1500), 32: (1700, 2200)}[n_balls]
-    ds = dio.DataSaver(rootPath=tempfile.mkdtemp(), makeDirs=False, randSeed=seed, numBalls=n_balls, mnBallSz=25,
-                       mxBallSz=25, mnForce=3e4, mxForce=8e4, wThick=30, isRect=False, wTheta=[30, 60],
-                       mnWLen=wl[0], mxWLen=wl[1], arenaSz=arena, mnSeqLen=10, mxSeqLen=10)
-    specs = ds.sample_sequences(n_src)
-    wall = np.zeros((n_src, 4, 4, 2)); pos = np.zeros((n_src, n_balls, 2)); vel = np.zeros_like(pos)
-    for s, sp in enumerate(specs):
-        for i, w in enumerate(sp.model.world_.static_.values()):
-            wall[s, i] = [[v.x(), v.y()] for v in w.bbox_.vert_]
-        for j, b in enumerate(sp.model.world_.dynamic_.values()):
-            pos[s, j] = (b.pos_.x(), b.pos_.y()); vel[s, j] = (b.vel_.x(), b.vel_.y())
-    rep = -(-n_worlds // n_src)
-    t = lambda a: np.tile(a, (rep,) + (1,) * (a.ndim - 1))[:n_worlds]
-    m = (4 / 3.0) * np.pi * 2.5 ** 3
-    return t(wall), t(pos), t(vel), np.full((n_worlds, n_balls), 25.0), np.full((n_worlds, n_balls), m)
 
 
 def run(table, n_worlds, n_balls, steps=200, warm=100, max_substeps=64):
@@ -47,9 +26,10 @@ def run(table, n_worlds, n_balls, steps=200, warm=100, max_substeps=64):
         nf = wb.sample_rect_worlds(seed=3, arena=arena, mn_wlen=wl[0], mx_wlen=wl[1])
         assert nf == 0
     else:
-        wall, pos, vel, rad, mass = rhombus_worlds(n_worlds, n_balls)
-        wb.set_walls(wall)
-        wb.set_balls(pos, vel, rad, mass)
+        arena = {4: 1600, 8: 2000, 16: 2600, 32: 3600}[n_balls]
+        wl = {4: (500, 800), 8: (800, 1100), 16: (1100, 1500), 32: (1700, 2200)}[n_balls]
+        nf = wb.sample_rect_worlds(seed=3, arena=arena, mn_wlen=wl[0], mx_wlen=wl[1], w_theta=[30, 60])
+        assert nf == 0
     wb.step_async(warm)
     torch.cuda.synchronize()
     c0 = wb.counters()
