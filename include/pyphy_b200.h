@@ -252,9 +252,10 @@ PPB_API int ppb_simulate_host(ppb_batch *b, int32_t n_steps, float *traj_host, u
  *   traj_dev   : [n_frames][n_worlds][n_balls][2] in the batch dtype -- the ball centres in those frames
  *   crops_dev  : [n_frames][n_worlds][n_balls][crop_sz][crop_sz][3] uint8, white where the crop leaves the canvas
  *   pos_dev    : NULL or [n_frames][n_worlds][n_balls][2] float32 -- the centres in crop coordinates (dataio.py:178-179)
- * Asynchronous. */
+ * mode 0 = DataSaver.fetch (offsets rounded, positions re-based); mode 1 = CustomWorld.get_glimpse (dataio.py:505-518:
+ * offsets truncated with int(), pos_dev = the centres unchanged).  Asynchronous. */
 PPB_API int ppb_crop_async(ppb_batch *b, const uint8_t *frames_dev, const void *traj_dev, int32_t n_frames, int32_t crop_sz,
-                   uint8_t *crops_dev, float *pos_dev, void *stream);
+                   int32_t mode, uint8_t *crops_dev, float *pos_dev, void *stream);
 
 /* utils.detect_collision's per-frame test (utils.py:38-49) on a recorded trajectory:
  *   traj_dev  : [n_steps][n_items][2] float32 positions (n_items = worlds x balls)

@@ -887,15 +887,15 @@ int ppb_simulate_host(ppb_batch *b, int32_t n_steps, float *traj_host, uint8_t *
 }
 
 int ppb_crop_async(ppb_batch *b, const uint8_t *frames_dev, const void *traj_dev, int32_t n_frames, int32_t crop_sz,
-                   uint8_t *crops_dev, float *pos_dev, void *stream) {
+                   int32_t mode, uint8_t *crops_dev, float *pos_dev, void *stream) {
   if (!b || !frames_dev || !traj_dev || !crops_dev) return fail(PPB_E_INVALID, "null argument");
-  if (n_frames < 0 || crop_sz < 1 || crop_sz > 4096) return fail(PPB_E_INVALID, "bad n_frames / crop_sz");
+  if (n_frames < 0 || crop_sz < 1 || crop_sz > 4096 || mode < 0 || mode > 1) return fail(PPB_E_INVALID, "bad n_frames / crop_sz / mode");
   if (b->RL.W < 1 || b->RL.H < 1) return fail(PPB_E_STATE, "batch was created without a canvas");
   CU(cudaSetDevice(b->cfg.device));
   CU(is64(b) ? Launch<double>::crop(frames_dev, traj_dev, n_frames, b->cfg.n_worlds, b->cfg.n_balls, b->RL.W, b->RL.H,
-                                    crop_sz, crops_dev, pos_dev, (cudaStream_t)stream)
+                                    crop_sz, mode, crops_dev, pos_dev, (cudaStream_t)stream)
              : Launch<float>::crop(frames_dev, traj_dev, n_frames, b->cfg.n_worlds, b->cfg.n_balls, b->RL.W, b->RL.H,
-                                   crop_sz, crops_dev, pos_dev, (cudaStream_t)stream));
+                                   crop_sz, mode, crops_dev, pos_dev, (cudaStream_t)stream));
   ++b->launches;
   return PPB_OK;
 }

@@ -25,7 +25,7 @@ struct Launch {
   static cudaError_t sample_rect(const StatePtrs &S, int n_balls, int n_walls, int world0, int count,
                                  const SamplerParams &P, int32_t step_value, int32_t *fail_count, cudaStream_t st);
   static cudaError_t crop(const uint8_t *frames, const void *traj, long long n_frames, int n_worlds, int n_balls, int W,
-                          int H, int c, uint8_t *crops, float *pos_out, cudaStream_t st);
+                          int H, int c, int mode, uint8_t *crops, float *pos_out, cudaStream_t st);
   // traj (batch dtype) -> float32
   static cudaError_t traj_to_f32(const void *src, float *dst, long long n, cudaStream_t st);
 };

@@ -65,12 +65,12 @@ cudaError_t Launch<T>::sample_rect(const StatePtrs &S, int n_balls, int n_walls,
 
 template <typename T>
 cudaError_t Launch<T>::crop(const uint8_t *frames, const void *traj, long long n_frames, int n_worlds, int n_balls, int W,
-                            int H, int c, uint8_t *crops, float *pos_out, cudaStream_t st) {
+                            int H, int c, int mode, uint8_t *crops, float *pos_out, cudaStream_t st) {
   const long long items = n_frames * n_worlds * n_balls;
   if (items <= 0) return cudaSuccess;
   if (items > 2147483647LL) return cudaErrorInvalidValue;
   const int threads = c * c >= 256 ? 256 : (c * c >= 128 ? 128 : 64);
-  crop_kernel<T><<<(unsigned)items, threads, 0, st>>>(frames, (const T *)traj, n_worlds, n_balls, W, H, c, crops, pos_out);
+  crop_kernel<T><<<(unsigned)items, threads, 0, st>>>(frames, (const T *)traj, n_worlds, n_balls, W, H, c, mode, crops, pos_out);
   return cudaGetLastError();
 }
 

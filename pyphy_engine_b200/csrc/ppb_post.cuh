@@ -13,8 +13,10 @@ __device__ __forceinline__ double round_half_away_d(double v) { return round(v);
 
 // One CTA per (frame, world, ball).  frames: [n_frames][n_worlds][H][W][4] u8; traj: [n_frames][n_worlds][n_balls][2] (T);
 // crops: [n_frames][n_worlds][n_balls][c][c][3] u8; pos_out: [n_frames][n_worlds][n_balls][2] f32.
+// mode 0: DataSaver.fetch (dataio.py:160-179, offsets rounded half away from zero, positions re-based);
+// mode 1: CustomWorld.get_glimpse (dataio.py:505-518, offsets truncated with int(), positions untouched).
 template <typename T>
-__global__ void crop_kernel(const uint8_t *frames, const T *traj, int n_worlds, int n_balls, int W, int H, int c,
+__global__ void crop_kernel(const uint8_t *frames, const T *traj, int n_worlds, int n_balls, int W, int H, int c, int mode,
                             uint8_t *crops, float *pos_out) {
   const long long item = blockIdx.x;   // (frame * n_worlds + world) * n_balls + ball
   const long long fw = item / n_balls;
@@ -23,9 +25,16 @@ __global__ void crop_kernel(const uint8_t *frames, const T *traj, int n_worlds, 
   const double xMid = round_half_away_d(px), yMid = round_half_away_d(py);
   double x1 = fmax(0.0, xMid - half), x2 = fmin((double)W, xMid + half);
   double y1 = fmax(0.0, yMid - half), y2 = fmin((double)H, yMid + half);
-  const int imX1 = (int)round_half_away_d(half - (xMid - x1)), imX2 = (int)round_half_away_d(half + (x2 - xMid));
-  const int imY1 = (int)round_half_away_d(half - (yMid - y1)), imY2 = (int)round_half_away_d(half + (y2 - yMid));
-  const int ix1 = (int)round_half_away_d(x1), iy1 = (int)round_half_away_d(y1);
+  int imX1, imX2, imY1, imY2, ix1, iy1;
+  if (mode == 0) {
+    imX1 = (int)round_half_away_d(half - (xMid - x1)); imX2 = (int)round_half_away_d(half + (x2 - xMid));
+    imY1 = (int)round_half_away_d(half - (yMid - y1)); imY2 = (int)round_half_away_d(half + (y2 - yMid));
+    ix1 = (int)round_half_away_d(x1); iy1 = (int)round_half_away_d(y1);
+  } else {
+    imX1 = (int)(half - (xMid - x1)); imX2 = (int)(half + (x2 - xMid));
+    imY1 = (int)(half - (yMid - y1)); imY2 = (int)(half + (y2 - yMid));
+    ix1 = (int)x1; iy1 = (int)y1;
+  }
   const uint8_t *src = frames + (size_t)fw * H * W * 4;
   uint8_t *dst = crops + (size_t)item * c * c * 3;
   for (int i = threadIdx.x; i < c * c; i += blockDim.x) {
@@ -41,10 +50,15 @@ __global__ void crop_kernel(const uint8_t *frames, const T *traj, int n_worlds, 
     dst[3 * i] = r; dst[3 * i + 1] = g; dst[3 * i + 2] = b;
   }
   if (threadIdx.x == 0 && pos_out) {
-    // position - x1 + imX1, evaluated on float32 values as the reference does on its float32 array
     const float fx = (float)px, fy = (float)py;
-    pos_out[item * 2] = (float)(((double)fx - ix1) + imX1);
-    pos_out[item * 2 + 1] = (float)(((double)fy - iy1) + imY1);
+    if (mode == 0) {
+      // position - x1 + imX1, evaluated on float32 values as the reference does on its float32 array
+      pos_out[item * 2] = (float)(((double)fx - ix1) + imX1);
+      pos_out[item * 2 + 1] = (float)(((double)fy - iy1) + imY1);
+    } else {
+      pos_out[item * 2] = fx;
+      pos_out[item * 2 + 1] = fy;
+    }
   }
 }
 

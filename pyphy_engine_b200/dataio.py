@@ -26,7 +26,7 @@ import numpy as np
 from . import geometry as gm
 from . import primitives as pm
 
-__all__ = ["DataSaver", "save_rect_arena", "save_nonrect_arena_train", "save_nonrect_arena_val",
+__all__ = ["DataSaver", "CustomWorld", "fix_theta_range", "save_rect_arena", "save_nonrect_arena_train", "save_nonrect_arena_val",
            "save_multishape_rect_arena"]
 
 
@@ -389,6 +389,96 @@ class DataSaver(object):
         specs = self.sample_sequences(numSeq)
         position, frames = self.run_sequences(specs, want_frames=want_frames)
         return specs, position, frames
+
+
+class CustomWorld(object):
+    """A world with a fixed layout -- given ball centres and kicks in a cage of side ``wlen`` -- and the
+    per-ball "glimpse" of it (dataio.py:457-570).  ``get_glimpse`` steps the world, draws it and cuts the
+    ball-centred crops on the device (``ppb_crop_async`` mode 1: the offsets are truncated with ``int()``
+    as in dataio.py:510-514, unlike ``DataSaver.fetch`` which rounds them)."""
+
+    def __init__(self, numballs=1, ballsz=25, wthick=30, isrect=True, wtheta=30, wlen=300, arenasz=667, verbose=0,
+                 ballLocs=None, forces=None, dtype="f64", device=0, **kwargs):
+        self.numballs_ = numballs
+        self.bsz_ = ballsz
+        self.bloc_ = [gm.Point.from_self(p) for p in (ballLocs if ballLocs is not None else [gm.Point(120, 120)])]
+        self.forces_ = [gm.Point.from_self(f) for f in (forces if forces is not None else [gm.Point(5e+4, 5e+4)])]
+        self.wthick_ = wthick
+        self.wtheta_ = wtheta
+        self.isrect_ = isrect
+        self.wlen_ = wlen
+        self.asz_ = arenasz
+        self.verbose_ = verbose
+        self.xSz_ = self.ySz_ = arenasz
+        self.dtype_, self.device_ = dtype, device
+
+    def _generate_model(self):
+        self.world_ = pm.World(xSz=self.asz_, ySz=self.asz_, dtype=self.dtype_, device=self.device_)
+        self.walls_ = self.add_walls()
+        self.add_balls()
+        self.model_ = pm.Dynamics(self.world_)
+
+    def generate_model(self):
+        self._generate_model()
+        self.apply_force()
+
+    def apply_force(self):
+        for b in range(self.numballs_):
+            self.model_.apply_force("ball-%d" % b, self.forces_[b], forceT=1.0)
+
+    def add_walls(self, xleft=20, yleft=20, hLen=None, vLen=None, fColor=pm.Color(1.0, 0.0, 0.0)):
+        hLen = self.wlen_ if hLen is None else hLen
+        vLen = self.wlen_ if vLen is None else vLen
+        wt = self.wtheta_
+        th = list(wt) if isinstance(wt, list) else [-wt, wt, 180 - wt]
+        th = [fix_theta_range(t) for t in th]
+        return self._create_walls(xleft, yleft, th, (vLen, hLen, vLen), fColor=fColor)
+
+    def _create_walls(self, xleft, yleft, thetas, wlens, fColor):
+        pts = [gm.Point(xleft, yleft)]
+        for t, wl in zip(thetas, wlens):
+            pts.append(pts[-1] + (wl * gm.theta2dir(t)))
+        walls = pm.create_cage(pts, wThick=self.wthick_, fColor=fColor)
+        self.pts = pts
+        for w in walls:
+            self.world_.add_object(w)
+        self.lines_ = [gm.Line(pts[i], pts[(i + 1) % len(pts)]) for i in range(len(pts))]
+        return walls
+
+    def add_balls(self):
+        for i in range(self.numballs_):
+            self.world_.add_object(pm.BallDef(radius=self.bsz_, fColor=pm.Color(0.5, 0.5, 0.5)), initPos=self.bloc_[i])
+
+    def get_glimpse(self, ballNum=None, cropSz=128):
+        """step() + generate_image() + one white-padded crop per ball: (imBalls, position, velocity)."""
+        import torch
+        self.model_.step()
+        nb = self.numballs_
+        position, velocity = np.zeros((2 * nb,)), np.zeros((2 * nb,))
+        for b in range(nb):
+            ball = self.model_.get_object("ball-%d" % b)
+            p, v = ball.get_position(), ball.get_velocity()
+            position[2 * b], position[2 * b + 1] = p.x(), p.y()
+            velocity[2 * b], velocity[2 * b + 1] = v.x(), v.y()
+        imBalls = []
+        if cropSz is not None:
+            dev = self.model_._dev()
+            dev.ensure_styles(self.world_)
+            frame = dev.batch.render()                                        # (1, H, W, 4) on the device
+            tdt = torch.float64 if self.dtype_ in ("f64", "float64", "fp64") else torch.float32
+            centres = torch.from_numpy(position.reshape(1, 1, nb, 2)).to(frame.device, tdt).contiguous()
+            crops, _ = dev.batch.crop(frame[None], centres, int(cropSz), mode=1)
+            crops = crops[0, 0].cpu().numpy()
+            imBalls = [crops[b] for b in range(nb)]
+        return imBalls, position, velocity
+
+
+def fix_theta_range(theta):
+    """Angle in degrees folded into (-180, 180] (dataio.py:573-577)."""
+    theta = np.mod(theta, 360)
+    if theta > 180:
+        theta = -(360 - theta)
+    return theta
 
 
 # ----------------------------------------------------------------------------------------------

@@ -324,10 +324,11 @@ class WorldBatch:
         check(self._lib.ppb_render_async(self._h, ctypes.c_void_p(out.data_ptr()), _stream_handle(stream, self.device)))
         return out
 
-    def crop(self, frames, traj, crop_sz: int, stream=None):
+    def crop(self, frames, traj, crop_sz: int, mode: int = 0, stream=None):
         """Ball-centred white-padded crops (dataio.py:160-182) of frames (F, n_worlds, H, W, 4) around the centres
         traj (F, n_worlds, n_balls, 2): returns (crops (F, n_worlds, n_balls, c, c, 3) uint8, positions in crop
-        coordinates (F, n_worlds, n_balls, 2) float32), both CUDA tensors."""
+        coordinates (F, n_worlds, n_balls, 2) float32), both CUDA tensors.  mode 1 = CustomWorld.get_glimpse
+        rounding (dataio.py:505-518; positions returned unchanged)."""
         import torch
         F = int(frames.shape[0])
         assert frames.is_cuda and frames.is_contiguous() and tuple(frames.shape[1:]) == (self.n_worlds, self.canvas_h, self.canvas_w, 4)
@@ -336,7 +337,7 @@ class WorldBatch:
         crops = torch.empty((F, self.n_worlds, self.n_balls, crop_sz, crop_sz, 3), dtype=torch.uint8, device=dev)
         pos = torch.empty((F, self.n_worlds, self.n_balls, 2), dtype=torch.float32, device=dev)
         check(self._lib.ppb_crop_async(self._h, ctypes.c_void_p(frames.data_ptr()), ctypes.c_void_p(traj.data_ptr()), F,
-                                       int(crop_sz), ctypes.c_void_p(crops.data_ptr()), ctypes.c_void_p(pos.data_ptr()),
+                                       int(crop_sz), int(mode), ctypes.c_void_p(crops.data_ptr()), ctypes.c_void_p(pos.data_ptr()),
                                        _stream_handle(stream, self.device)))
         return crops, pos
 

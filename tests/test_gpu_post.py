@@ -142,3 +142,29 @@ def test_detect_collision_from_a_saved_tree(tmp_path):
     assert col >= sum(len(a) for a in allfIdx) and 0 <= bcol <= col
     n = ut.save_collisions_seq(ds.dirName_, isSubFolder=False, outFolder=str(tmp_path / "clips"))
     assert n == col
+
+
+def test_custom_world_glimpse(tmp_path):
+    """CustomWorld.get_glimpse (dataio.py:490-519) against a literal restatement of its cropping lines."""
+    import pyphy_engine_b200.geometry as gm
+    cw = dio.CustomWorld(numballs=2, ballsz=20, wthick=20, wtheta=[0, 90, -180], wlen=300, arenasz=400,
+                         ballLocs=[gm.Point(120, 120), gm.Point(250, 200)],
+                         forces=[gm.Point(5e4, 3e4), gm.Point(-4e4, 2e4)])
+    cw.generate_model()
+    assert [n for n in cw.world_.get_object_names()] == ["wall-0", "wall-1", "wall-2", "wall-3", "ball-0", "ball-1"]
+    for it in range(25):
+        imBalls, position, velocity = cw.get_glimpse(cropSz=96)
+        im = cw.model_.generate_image()
+        assert len(imBalls) == 2 and imBalls[0].shape == (96, 96, 3)
+        for b in range(2):
+            px, py = position[2 * b], position[2 * b + 1]
+            xMid, yMid = py2_round(px), py2_round(py)
+            ref = 255 * np.ones((96, 96, 3), np.uint8)
+            x1, x2 = max(0, xMid - 48.0), min(400, xMid + 48.0)
+            y1, y2 = max(0, yMid - 48.0), min(400, yMid + 48.0)
+            imX1, imX2 = int(48.0 - (xMid - x1)), int(48.0 + (x2 - xMid))
+            imY1, imY2 = int(48.0 - (yMid - y1)), int(48.0 + (y2 - yMid))
+            ref[imY1:imY2, imX1:imX2, :] = im[int(y1):int(y2), int(x1):int(x2), 0:3]
+            assert np.array_equal(imBalls[b], ref)
+    assert not np.allclose(position, [120, 120, 250, 200])           # the balls moved
+    assert dio.fix_theta_range(270) == -90 and dio.fix_theta_range(-180) == 180 and dio.fix_theta_range(90) == 90
