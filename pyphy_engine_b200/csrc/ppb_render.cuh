@@ -663,6 +663,29 @@ __global__ void __maxnreg__(120) render_tile_kernel(StatePtrs S, Layout L, Rende
         }
         const uint32_t dst = ra.y & 0xffffu;
         const bool v1 = sp_t1 != 0xffffffffu, v2 = sp_t2 != 0xffffffffu;
+        // the next ball, when it has the same visible geometry and does not touch this one's pixels, is
+        // composited in the same trip: four independent load -> blend -> store chains instead of two
+        // (measured: step 0.459 -> 0.421 ms; grouping up to four sprites was slower again, 0.459 ms)
+        if (b + 1 < nB) {
+          const uint4 rn = reinterpret_cast<const uint4 *>(&sm.b[b + 1])[0];
+          const uint32_t dstn = rn.y & 0xffffu;
+          const int ddx = abs((int)(dst & 63u) - (int)(dstn & 63u)), ddy = abs((int)(dst >> 6) - (int)(dstn >> 6));
+          if (rn.z == ra.z && (rn.y >> 16) == (ra.y >> 16) && (ddx >= aw || ddy >= ah)) {
+            const uint32_t t1 = v1 ? __ldg(atlas + ra.x + sp_t1) : 0u;
+            const uint32_t t2 = v2 ? __ldg(atlas + ra.x + sp_t2) : 0u;
+            const uint32_t u1 = v1 ? __ldg(atlas + rn.x + sp_t1) : 0u;
+            const uint32_t u2 = v2 ? __ldg(atlas + rn.x + sp_t2) : 0u;
+            const uint32_t d1 = v1 ? sm.tile[dst + sp_d1] : 0u;
+            const uint32_t d2 = v2 ? sm.tile[dst + sp_d2] : 0u;
+            const uint32_t e1 = v1 ? sm.tile[dstn + sp_d1] : 0u;
+            const uint32_t e2 = v2 ? sm.tile[dstn + sp_d2] : 0u;
+            if (v1) { sm.tile[dst + sp_d1] = over_nb(t1, d1); sm.tile[dstn + sp_d1] = over_nb(u1, e1); }
+            if (v2) { sm.tile[dst + sp_d2] = over_nb(t2, d2); sm.tile[dstn + sp_d2] = over_nb(u2, e2); }
+            __syncwarp();
+            ++b;
+            continue;
+          }
+        }
         const uint32_t t1 = v1 ? __ldg(atlas + ra.x + sp_t1) : 0u;
         const uint32_t t2 = v2 ? __ldg(atlas + ra.x + sp_t2) : 0u;
         const uint32_t d1 = v1 ? sm.tile[dst + sp_d1] : 0u;
