@@ -353,6 +353,19 @@ def main():
         model, extra, seqLen = build_datasaver(ns, seed, tmpdir, **kw)
         name = "rhomb3_s%d" % seed
         put(name, run_case(ns, model, seqLen), extra); cases.append(name)
+    # oppForce=True: the two balls are kicked towards each other (dataio.py:386-397)
+    for seed in range(600, 604):
+        kw = dict(RECT, numBalls=2, mnForce=8e3, mxForce=5e4, mnSeqLen=120, mxSeqLen=120, oppForce=True)
+        model, extra, seqLen = build_datasaver(ns, seed, tmpdir, **kw)
+        name = "opp2_s%d" % seed
+        put(name, run_case(ns, model, seqLen), extra); cases.append(name)
+    # the validation rhombus set: four angles (dataio.py:419-422 parameters)
+    for seed in range(700, 704):
+        kw = dict(wThick=20, isRect=False, wTheta=[23, 38, 45, 53], mnBallSz=15, mxBallSz=35, arenaSz=667,
+                  mnWLen=200, mxWLen=300, numBalls=1, mnForce=1e3, mxForce=1e5, mnSeqLen=100, mxSeqLen=100)
+        model, extra, seqLen = build_datasaver(ns, seed, tmpdir, **kw)
+        name = "rhombval_s%d" % seed
+        put(name, run_case(ns, model, seqLen), extra); cases.append(name)
     # crowded worlds: search for seeds on which the reference itself raises, to pin
     # the failure outcomes (status code + step)
     n_fail = 0

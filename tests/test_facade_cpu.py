@@ -68,6 +68,11 @@ def datasaver_kwargs(name):
     if name.startswith("rhomb3"):
         return dict(wThick=30, isRect=False, wTheta=[30, 60], mnBallSz=15, mxBallSz=35, arenaSz=1600, mnWLen=500,
                     mxWLen=800, numBalls=3, mnForce=3e4, mxForce=8e4, mnSeqLen=150, mxSeqLen=150), seed
+    if name.startswith("opp2"):
+        return dict(mg.RECT, numBalls=2, mnForce=8e3, mxForce=5e4, mnSeqLen=120, mxSeqLen=120, oppForce=True), seed
+    if name.startswith("rhombval"):
+        return dict(wThick=20, isRect=False, wTheta=[23, 38, 45, 53], mnBallSz=15, mxBallSz=35, arenaSz=667,
+                    mnWLen=200, mxWLen=300, numBalls=1, mnForce=1e3, mxForce=1e5, mnSeqLen=100, mxSeqLen=100), seed
     if name.startswith("crowd12"):
         return dict(wThick=30, isRect=True, mnBallSz=25, mxBallSz=25, arenaSz=900, mnWLen=420, mxWLen=520,
                     numBalls=12, mnForce=3e4, mxForce=8e4, mnSeqLen=200, mxSeqLen=200), seed

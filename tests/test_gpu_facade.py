@@ -60,7 +60,8 @@ def test_hand_built_worlds_step_like_the_reference(name, builder):
     assert np.max(np.abs(vel - ref["vel_final"])) < 1e-6 * max(1.0, np.abs(ref["vel_final"]).max())
 
 
-@pytest.mark.parametrize("name", [n for n in DS_CASES if not n.startswith("crowd12")][:16])
+@pytest.mark.parametrize("name", [n for n in DS_CASES if not n.startswith("crowd12")][:16] +
+                         [n for n in DS_CASES if n.startswith(("opp2", "rhombval"))])
 def test_datasaver_worlds_step_like_the_reference(name, tmp_path):
     kw, seed = datasaver_kwargs(name)
     model, extra, seq_len = mg.build_datasaver(NS, seed, str(tmp_path), **kw)
