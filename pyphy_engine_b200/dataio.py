@@ -247,11 +247,22 @@ class DataSaver(object):
         called for every frame otherwise (possibly from worker threads).
         """
         import torch
+        H, W = int(self.ySz_), int(self.xSz_)
+        # a batch is bounded by one step of frames fitting the staging buffer: larger jobs run as several batches
+        group = max(1, max_stage_bytes // (H * W * 4)) if want_frames else 1 << 20
+        if len(specs) > group:
+            position, frames_out = [], ([] if (want_frames and frame_sink is None) else None)
+            for g0 in range(0, len(specs), group):
+                sink = None if frame_sink is None else (lambda s, i, im, g0=g0: frame_sink(g0 + s, i, im))
+                p, f = self.run_sequences(specs[g0:g0 + group], want_frames, sink, max_stage_bytes)
+                position += p
+                if frames_out is not None:
+                    frames_out += f
+            return position, frames_out
         n, nB = len(specs), self.numBalls_
         lens = np.array([sp.seq_len for sp in specs])
         total = int(lens.max()) if n else 0
         wb = self._batch_from_specs(specs, want_frames)
-        H, W = int(self.ySz_), int(self.xSz_)
         position = [np.zeros((2 * nB, int(l)), np.float32) for l in lens]
         frames_out = [np.zeros((int(l), H, W, 4), np.uint8) for l in lens] if (want_frames and frame_sink is None) else None
         per_step = n * nB * 2 * 4 + (n * H * W * 4 if want_frames else 0)

@@ -220,3 +220,21 @@ def test_dynamics_horizon_delivers_delayed_frames():
     assert im.shape == (64, 64, 4) and mat.shape == (1, 10) and mat.dtype == np.float32
     # constant velocity far from the walls: every displacement equals v * dt
     assert np.allclose(mat[0, 0::2], 60 * 0.01, atol=1e-6) and np.allclose(mat[0, 1::2], 25 * 0.01, atol=1e-6)
+
+
+def test_datasaver_groups_large_jobs(tmp_path):
+    """Jobs whose frames exceed the staging budget run as several batches with identical results."""
+    kw = dict(wThick=3, isRect=True, mnBallSz=3, mxBallSz=3, arenaSz=64, mnWLen=36, mxWLen=50, numBalls=2,
+              mnForce=5.0, mxForce=12.0, mnSeqLen=8, mxSeqLen=14)
+    ds = dio.DataSaver(rootPath=str(tmp_path), randSeed=3, makeDirs=False, **kw)
+    specs = ds.sample_sequences(11)
+    p1, f1 = ds.run_sequences(specs, want_frames=True)
+    p2, f2 = ds.run_sequences(specs, want_frames=True, max_stage_bytes=3 * 64 * 64 * 4)    # groups of 3 sequences
+    seen = []
+    p3, _ = ds.run_sequences(specs, want_frames=True, frame_sink=lambda s, i, im: seen.append((s, i, int(im.sum()))),
+                             max_stage_bytes=4 * 64 * 64 * 4)
+    for a, b, c in zip(p1, p2, p3):
+        assert np.array_equal(a, b) and np.array_equal(a, c)
+    for a, b in zip(f1, f2):
+        assert np.array_equal(a, b)
+    assert sorted(seen) == sorted((s, i, int(f1[s][i].sum())) for s in range(11) for i in range(specs[s].seq_len))
