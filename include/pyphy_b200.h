@@ -89,7 +89,9 @@ typedef struct ppb_config {
                              halted with PPB_ST_ITER_LIMIT */
   double dt;              /* Dynamics(deltaT=0.01), primitives.py:536 */
   double gx, gy;          /* Dynamics.g_ (a Point), primitives.py:541, 566 */
-  double friction;        /* extension, 0 = reference behaviour */
+  double friction;        /* extension, 0 = reference behaviour: at the start of every step all velocities are
+                             scaled by max(0, 1 - friction*dt) (semi-implicit Euler); cached collision times are
+                             rescaled by the inverse, so the event-driven step stays exact */
   int64_t event_capacity; /* records kept for ppb_read_events; 0 = count only */
   const int32_t *order;   /* n_walls + n_balls entries: object insertion order, wall q -> q,
                              ball b -> n_walls + b; NULL = walls first, then balls */

@@ -279,6 +279,7 @@ int ppb_create(const ppb_config *cfg, ppb_batch **out) {
   if (!(cfg->dt > 0)) return fail(PPB_E_INVALID, "dt must be positive");
   if (cfg->canvas_w < 0 || cfg->canvas_h < 0) return fail(PPB_E_INVALID, "canvas size must be >= 0");
   if (cfg->event_capacity < 0) return fail(PPB_E_INVALID, "event_capacity must be >= 0");
+  if (!(cfg->friction >= 0)) return fail(PPB_E_INVALID, "friction must be >= 0");
   int ndev = 0;
   if (cudaGetDeviceCount(&ndev) != cudaSuccess || ndev < 1)
     return fail(PPB_E_CUDA, "no CUDA device available (this library has no CPU fallback)");

@@ -66,18 +66,30 @@ __global__ void __launch_bounds__(256) integrate_kernel(StatePtrs S, int n_balls
         for (int j = 0; j < BPT; ++j) reinterpret_cast<T2 *>(S.snap)[i + j] = pos[i + j];
       }
     } else if (h.step == k) {
-      if (h.flags == 0u && h.tmin > dt) {
+      // friction extension (0 = the reference): every velocity is scaled by s = 1 - friction*dt at the start of
+      // the step (semi-implicit Euler: the step then moves with the new velocity).  A uniform scaling of all
+      // velocities leaves every contact geometry unchanged and stretches every cached time of collision by
+      // 1/s, so the event-driven caches stay exact; worlds with friction still take the fast path.
+      const bool fric = P.friction != 0.0;
+      const T fs = fric ? (T)fmax(0.0, 1.0 - P.friction * P.dt) : T(1);
+      const T tmin_eff = fric ? (fs > T(0) ? h.tmin / fs : Lim<T>::inf()) : h.tmin;
+      if (h.flags == 0u && tmin_eff > dt) {
         // event-free step: Dynamics.move_object for every ball (primitives.py:600-611)
         const V2<T> g = mk<T>((T)P.gx, (T)P.gy);
         T2 *vel = reinterpret_cast<T2 *>(S.vel);
         T *tcol = reinterpret_cast<T *>(S.tcol);
-        const bool has_g = (P.gx != 0.0) || (P.gy != 0.0);
+        const bool has_g = (P.gx != 0.0) || (P.gy != 0.0) || fric;
         if (BPT == 2) {
           typedef typename Vec4<T>::type T4;
           T4 p = ld4(reinterpret_cast<const T4 *>(pos + i));
           T4 v = ld4(reinterpret_cast<const T4 *>(vel + i));
           T2 tc = *reinterpret_cast<const T2 *>(tcol + i);
           V2<T> p0 = mk<T>(p.x, p.y), p1 = mk<T>(p.z, p.w), v0 = mk<T>(v.x, v.y), v1 = mk<T>(v.z, v.w);
+          if (fric) {
+            v0 = v0 * fs; v1 = v1 * fs;
+            tc.x = fs > T(0) ? tc.x / fs : Lim<T>::inf();
+            tc.y = fs > T(0) ? tc.y / fs : Lim<T>::inf();
+          }
           move_ball(p0, v0, dt, g);
           move_ball(p1, v1, dt, g);
           tc.x = tc.x - dt;
@@ -97,6 +109,10 @@ __global__ void __launch_bounds__(256) integrate_kernel(StatePtrs S, int n_balls
           T2 p = pos[i], v = vel[i];
           T tc = tcol[i];
           V2<T> p0 = mk<T>(p.x, p.y), v0 = mk<T>(v.x, v.y);
+          if (fric) {
+            v0 = v0 * fs;
+            tc = fs > T(0) ? tc / fs : Lim<T>::inf();
+          }
           move_ball(p0, v0, dt, g);
           tc = tc - dt;
           p.x = p0.x; p.y = p0.y;
@@ -111,7 +127,7 @@ __global__ void __launch_bounds__(256) integrate_kernel(StatePtrs S, int n_balls
         }
         if (duty) {
           Hdr<T> o = h;
-          o.tmin = h.tmin - dt;   // min_b (tCol_b - dt) == (min_b tCol_b) - dt: rounding is monotone
+          o.tmin = tmin_eff - dt;   // min_b (tCol_b - dt) == (min_b tCol_b) - dt: rounding is monotone
           o.step = k + 1u;
           reinterpret_cast<Hdr<T> *>(S.hdr)[w] = o;
         }
@@ -291,6 +307,12 @@ collide_kernel(StatePtrs S, Layout L, StepParams P, T *traj) {
       fv = mk<T>(a.z, a.w);
       tc = gtcol[base + bi];
       partner = S.partner[base + bi];
+      if (P.friction != 0.0 && !P.scan_only) {   // friction extension: see integrate_kernel
+        const T fs = (T)fmax(0.0, 1.0 - P.friction * P.dt);
+        vel = vel * fs;
+        fv = fv * fs;
+        tc = fs > T(0) ? tc / fs : INF;
+      }
     }
     team_sync<TW>(team);   // the previous world's readers of the staging area are done
     for (int e = wt * 32 + lane; e < nWl * 4; e += TW * 32) {

@@ -239,3 +239,63 @@ def test_energy_and_confinement_properties():
     s0 = np.linalg.norm(W1["vel"], axis=-1)
     s1 = np.linalg.norm(v1, axis=-1)
     assert np.max(np.abs(s1 - s0) / s0) < 1e-5
+
+
+def test_friction_extension():
+    """ppb_config.friction (not in the reference): velocities shrink by s = 1 - mu*dt per step, collisions keep
+    working, mu = 0 is bit-identical with the frictionless engine, and the path of a ball is the frictionless
+    path traversed more slowly (uniform scaling of all velocities keeps the geometry of every contact)."""
+    from pyphy_engine_b200 import sampler
+    from pyphy_engine_b200.engine import WorldBatch
+    n, mu, dt = 1024, 2.0, 0.01
+    W = sampler.sample_rect_worlds(n, 1, seed=31)
+
+    def run(friction, steps, dtype="f64"):
+        wb = WorldBatch(n, 1, 4, dtype=dtype, friction=friction, event_capacity=1 << 20)
+        wb.set_walls(W["wall"]); wb.set_balls(W["pos"], W["vel"], W["rad"], W["mass"])
+        traj, _ = wb.step(steps, record_traj=True)
+        pos, vel = wb.get_balls()
+        ev, _ = wb.read_events()
+        st, _ = wb.get_status()
+        wb.close()
+        return traj.cpu().numpy(), pos, vel, ev, st
+
+    t0, p0, v0, e0, s0 = run(0.0, 150)
+    t1, p1, v1, e1, s1 = run(mu, 150)
+    assert (s1 == 0).all() and (s0 == 0).all()
+    s = 1.0 - mu * dt
+    speed0 = np.linalg.norm(W["vel"], axis=-1)[:, 0]
+    speed1 = np.linalg.norm(v1, axis=-1)[:, 0]
+    assert np.allclose(speed1, speed0 * s ** 150, rtol=1e-9)                 # wall bounces preserve |v|
+    assert len(e1) > 0 and len(e1) < len(e0)                                   # slower balls hit fewer walls
+    # one ball: the frictional trajectory is the frictionless one traversed more slowly, so every world hits
+    # the same walls in the same order -- its event sequence is a prefix of the frictionless one
+    def per_world(ev):
+        out = [[] for _ in range(n)]
+        for w, _, _, partner in ev:
+            out[w].append(int(partner))
+        return out
+    seq0, seq1 = per_world(e0), per_world(e1)
+    assert all(a == b[:len(a)] for a, b in zip(seq1, seq0))
+    assert sum(len(a) for a in seq1) > 200
+    # mu = 0 through the friction-aware kernels is bit-identical with the engine default
+    wb = WorldBatch(n, 1, 4, dtype="f64")
+    wb.set_walls(W["wall"]); wb.set_balls(W["pos"], W["vel"], W["rad"], W["mass"])
+    wb.step(150)
+    assert np.array_equal(wb.get_balls()[0], p0)
+    wb.close()
+    # multi-ball worlds: kinetic energy never grows beyond the reference's own drift and the worlds keep running
+    Wm = sampler.sample_rect_worlds(2048, 4, seed=32)
+    ke = []
+    for fr in (0.0, 5.0):
+        wb = WorldBatch(2048, 4, 4, dtype="f32", friction=fr, max_substeps=256)
+        wb.set_walls(Wm["wall"]); wb.set_balls(Wm["pos"], Wm["vel"], Wm["rad"], Wm["mass"])
+        wb.step(200)
+        _, v = wb.get_balls()
+        ok = wb.get_status()[0] == 0
+        ke.append((0.5 * Wm["mass"] * (v ** 2).sum(-1)).sum(-1)[ok].mean())
+        assert ok.mean() > 0.98
+        wb.close()
+    assert ke[1] < 0.2 * ke[0]            # (1 - 0.05)^400 ~ 1e-9 of the energy without collisions' re-pumping
+    with pytest.raises(Exception):
+        WorldBatch(4, 1, 4, friction=-1.0)
