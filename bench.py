@@ -318,6 +318,20 @@ def run_ours(args, rank, local_rank, world_size):
     else:
         live_total, events_total, launches_total = float(live), float(stats[3]), float(launches)
 
+    # ---- end-of-run gather of the datagen shard (NCCL over NVLink when distributed): the positions every rank
+    #      recorded for its worlds arrive on rank 0 in world order; not part of any timed region ----
+    final_traj = torch.from_numpy(np.ascontiguousarray(traj_host.numpy())).to(dev)     # (1, n_worlds, balls, 2)
+    torch.cuda.synchronize(dev)
+    tg0 = time.perf_counter()
+    gathered = _sh.gather_trajectories(final_traj, n_worlds * world_size, dst=0)
+    torch.cuda.synchronize(dev)
+    gather_ms = 1e3 * (time.perf_counter() - tg0)
+    gather_info = None
+    if rank == 0:
+        gather_info = {"shape": list(gathered.shape), "bytes": int(gathered.numel() * 4), "ms": gather_ms,
+                       "backend": "nccl" if distributed else "none (single rank)",
+                       "checksum": float(gathered.double().sum().item())}
+
     if rank == 0:
         total_worlds = n_worlds * world_size
         ball_steps = live_total * N_BALLS * args.steps          # halted worlds do not count
@@ -362,6 +376,7 @@ def run_ours(args, rank, local_rank, world_size):
                     "h2d_bytes_per_step": int(h2d), "d2h_bytes_per_step": int(d2h), "steps": e2e_steps,
                     "api": "WorldBatch.set_walls/set_balls + simulate_host (ppb_simulate_host), pinned host buffers",
                     "numa_node_rank0": numa_node},
+            "final_gather": gather_info,
             "gpu_launches": int(launches_total),
             "clocks": {"sm_mhz": clk["sm_mhz"], "sm_max_mhz": clk["sm_max_mhz"], "reasons": clk["reasons"]},
         }
