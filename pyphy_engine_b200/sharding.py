@@ -72,6 +72,61 @@ def bind_to_gpu_numa_node(device: int) -> Optional[int]:
         os.sched_setaffinity(0, allowed)
         return node
     except Exception:
+        pass
+    return _bind_from_nvidia_smi(device)
+
+
+def _parse_cpu_list(spec):
+    cpus = set()
+    for part in spec.split(","):
+        part = part.strip()
+        if "-" in part:
+            a, b = part.split("-")
+            cpus.update(range(int(a), int(b) + 1))
+        elif part.isdigit():
+            cpus.add(int(part))
+    return cpus
+
+
+def _parse_topo(out: str, device: int):
+    """``nvidia-smi topo -m`` text -> (cpu set, numa node or -1) of ``GPU<device>``, or None."""
+    import re
+    out = re.sub(r"\x1b\[[0-9;]*m", "", out)
+    lines = [l for l in out.splitlines() if l.strip()]
+    if not lines:
+        return None
+    header = re.split(r"\t+|\s{2,}", lines[0].strip())
+    if "CPU Affinity" not in header:
+        return None
+    ci = header.index("CPU Affinity")
+    ni = header.index("NUMA Affinity") if "NUMA Affinity" in header else None
+    for l in lines[1:]:
+        cols = re.split(r"\t+|\s{2,}", l.strip())
+        # a row has one more leading column (its own label) than the header
+        if cols and cols[0] == "GPU%d" % device and len(cols) > ci + 1:
+            node = -1
+            if ni is not None and len(cols) > ni + 1 and cols[ni + 1].strip().isdigit():
+                node = int(cols[ni + 1])
+            return _parse_cpu_list(cols[ci + 1]), node
+    return None
+
+
+def _bind_from_nvidia_smi(device: int) -> Optional[int]:
+    """Fallback when sysfs hides the NUMA node (containers): the "CPU Affinity" / "NUMA Affinity" columns of
+    ``nvidia-smi topo -m``."""
+    import os
+    import subprocess
+    try:
+        out = subprocess.run(["nvidia-smi", "topo", "-m"], capture_output=True, text=True, timeout=20).stdout
+        hit = _parse_topo(out, device)
+        if hit is None:
+            return None
+        cpus = hit[0] & set(os.sched_getaffinity(0))
+        if not cpus:
+            return None
+        os.sched_setaffinity(0, cpus)
+        return hit[1]
+    except Exception:
         return None
 
 

@@ -88,3 +88,18 @@ def test_single_process_fallbacks():
     assert s["a"].tolist() == [1.0] and s["b"].tolist() == [2.0]
     t = torch.zeros(2, 5, 3, 2)
     assert sharding.gather_trajectories(t, 5) is t
+
+
+def test_parse_topo_table():
+    """The nvidia-smi fallback of bind_to_gpu_numa_node reads the affinity columns of the right row."""
+    from pyphy_engine_b200.sharding import _parse_topo
+    out = ("\x1b[4m\tGPU0\tGPU1\tNIC0\tCPU Affinity\tNUMA Affinity\tGPU NUMA ID\x1b[0m\n"
+           "GPU0\t X \tNV18\tPIX\t0-23,96-119\t0\t\tN/A\n"
+           "GPU1\tNV18\t X \tNODE\t24-47\t1\t\tN/A\n"
+           "NIC0\tPIX\tNODE\t X \t\t\t\t\n\nLegend:\n\n  X    = Self\n")
+    cpus, node = _parse_topo(out, 0)
+    assert node == 0 and cpus == set(range(0, 24)) | set(range(96, 120))
+    cpus, node = _parse_topo(out, 1)
+    assert node == 1 and cpus == set(range(24, 48))
+    assert _parse_topo(out, 5) is None
+    assert _parse_topo("", 0) is None
