@@ -178,6 +178,35 @@ def build_diamond(ns):
     return model
 
 
+def build_ngon(ns, n_sides, n_balls, seed, radius=300.0, w_thick=20, r_ball=18):
+    """BASELINE configs[4] 'polygonal wall layouts': a regular N-gon table through create_cage
+    (primitives.py:199-209; vertices clockwise on screen so the walls thicken inwards), balls at
+    non-overlapping random places inside the inscribed circle, random velocities."""
+    gm, pm = ns.gm, ns.pm
+    rs = np.random.RandomState(seed)
+    cx = cy = 400.0
+    world = pm.World(xSz=800, ySz=800)
+    th0 = rs.rand() * 2 * np.pi
+    pts = [gm.Point(cx + radius * np.cos(th0 + 2 * np.pi * i / n_sides), cy + radius * np.sin(th0 + 2 * np.pi * i / n_sides))
+           for i in range(n_sides)]
+    for w in pm.create_cage(pts, wThick=w_thick):
+        world.add_object(w)
+    free = radius * np.cos(np.pi / n_sides) - w_thick - r_ball - 2
+    placed = []
+    while len(placed) < n_balls:
+        rr, aa = free * np.sqrt(rs.rand()), 2 * np.pi * rs.rand()
+        x, y = np.floor(cx + rr * np.cos(aa)), np.floor(cy + rr * np.sin(aa))
+        if all((x - px) ** 2 + (y - py) ** 2 > (2 * r_ball + 2) ** 2 for px, py in placed):
+            placed.append((x, y))
+    for x, y in placed:
+        world.add_object(pm.BallDef(radius=r_ball, fColor=pm.Color(0.5, 0.5, 0.5)), initPos=gm.Point(x, y))
+    model = pm.Dynamics(world)
+    for j in range(n_balls):
+        sp, aa = 300 + 900 * rs.rand(), 2 * np.pi * rs.rand()
+        model.set_object_velocity('ball-%d' % j, gm.Point(sp * np.cos(aa), sp * np.sin(aa)))
+    return model
+
+
 def build_config1_64(ns):
     """BASELINE config 1: 64x64 world, 1 ball, 4-wall cage."""
     gm, pm = ns.gm, ns.pm
@@ -366,6 +395,11 @@ def main():
         model, extra, seqLen = build_datasaver(ns, seed, tmpdir, **kw)
         name = "rhombval_s%d" % seed
         put(name, run_case(ns, model, seqLen), extra); cases.append(name)
+    # regular N-gon tables through create_cage (BASELINE configs[4]: polygonal wall layouts)
+    for n_sides, n_balls in ((3, 2), (5, 3), (6, 4), (8, 6)):
+        for seed in (800, 801):
+            name = "ngon%d_s%d" % (n_sides, seed)
+            put(name, run_case(ns, build_ngon(ns, n_sides, n_balls, seed), 150)); cases.append(name)
     # crowded worlds: search for seeds on which the reference itself raises, to pin
     # the failure outcomes (status code + step)
     n_fail = 0

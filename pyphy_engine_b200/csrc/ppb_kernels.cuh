@@ -18,6 +18,12 @@
 
 namespace ppb {
 
+// Programmatic dependent launch (sm_90+): a kernel launched with programmatic stream serialisation may start
+// while its predecessor in the stream drains; it must not touch global memory before pdl_wait().  Both are
+// no-ops for a plain launch.
+__device__ __forceinline__ void pdl_wait() { asm volatile("griddepcontrol.wait;" ::: "memory"); }
+__device__ __forceinline__ void pdl_launch_dependents() { asm volatile("griddepcontrol.launch_dependents;" ::: "memory"); }
+
 template <typename T>
 __device__ __forceinline__ T warp_min(T v) {
 #pragma unroll
@@ -45,7 +51,9 @@ __global__ void __launch_bounds__(256) integrate_kernel(StatePtrs S, int n_balls
   __shared__ int s_cnt, s_base;
   __shared__ int s_list[256];
   if (threadIdx.x == 0) s_cnt = 0;
+  pdl_launch_dependents();   // the collide kernel's CTAs may take their places; they wait for this grid to finish
   __syncthreads();
+  pdl_wait();
   const long long total = (long long)S.n_worlds * n_balls;
   const long long i = ((long long)blockIdx.x * blockDim.x + threadIdx.x) * BPT;
   const uint32_t k = (uint32_t)(*S.step_base + P.step_off);
@@ -215,7 +223,7 @@ template <typename T, int TW>
 struct TeamSmem {
   WarpSmem<T> w;                                  // ball / edge staging shared by the team
   ScanPart<T> part[TW > 1 ? TW : 1][TW > 1 ? 32 : 1];
-  int ticket;
+  int ticket, next_world;
 };
 
 template <int TW>
@@ -248,6 +256,7 @@ collide_kernel(StatePtrs S, Layout L, StepParams P, T *traj) {
   const int gid = wt * G + grp;                // this lane's scan group
   const bool writer = (wt == 0) && (grp == 0); // the lane that owns ball bi's global state
   const int nB = L.n_balls, nWl = L.n_walls;
+  pdl_wait();   // the integrate kernel of this step (list, state) is complete and visible
   const uint32_t k = (uint32_t)(*S.step_base + P.step_off);
   const T dt = (T)P.dt;
   const V2<T> g = mk<T>((T)P.gx, (T)P.gy);
@@ -269,21 +278,15 @@ collide_kernel(StatePtrs S, Layout L, StepParams P, T *traj) {
   const T2 *gwall = reinterpret_cast<const T2 *>(S.wall);
 
   unsigned long long cnt_iters = 0, cnt_rescans = 0;
-  int idx = 0;
-  if (TW == 1) {
-    if (lane == 0) idx = atomicAdd(ticket, 1);
-    idx = __shfl_sync(FULL, idx, 0);
-  } else {
-    if (wt == 0 && lane == 0) ts.ticket = atomicAdd(ticket, 1);
-    team_sync<TW>(team);
-    idx = ts.ticket;
-    team_sync<TW>(team);
-  }
+  // the first world of every team is its own index in the grid (no atomic on the way to the first loads);
+  // the ticket counter hands out the worlds after those
+  const int n_teams = (int)gridDim.x * TEAMS;
+  int idx = (int)blockIdx.x * TEAMS + team;
+  int w = idx < count ? S.list[idx] : 0;
 
   while (idx < count) {
     int idx_next = 0;
-    if (wt == 0 && lane == 0) idx_next = atomicAdd(ticket, 1);   // its latency hides behind this world's work
-    const int w = S.list[idx];
+    if (wt == 0 && lane == 0) idx_next = n_teams + atomicAdd(ticket, 1);   // its latency hides behind this world's work
     const bool has_ball = bi < nB;
     const long long base = (long long)w * nB;
 
@@ -336,6 +339,9 @@ collide_kernel(StatePtrs S, Layout L, StepParams P, T *traj) {
     T tStep = T(0), mnt = INF;
     uint32_t nev_local = 0;
     int iters = 0;
+    // the next world's list entry: fetched by the ticket holder while this world is worked on
+    int w_next = 0;
+    if (wt == 0 && lane == 0 && idx_next < count) w_next = S.list[idx_next];
 
     for (;;) {
       if (pending) {
@@ -533,10 +539,15 @@ collide_kernel(StatePtrs S, Layout L, StepParams P, T *traj) {
     }
     if (TW == 1) {
       idx = __shfl_sync(FULL, idx_next, 0);
+      w = __shfl_sync(FULL, w_next, 0);
     } else {
-      if (wt == 0 && lane == 0) ts.ticket = idx_next;
+      if (wt == 0 && lane == 0) {
+        ts.ticket = idx_next;
+        ts.next_world = w_next;
+      }
       team_sync<TW>(team);
       idx = ts.ticket;
+      w = ts.next_world;
       team_sync<TW>(team);
     }
   }

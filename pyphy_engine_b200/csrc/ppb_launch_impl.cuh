@@ -7,6 +7,34 @@
 
 namespace ppb {
 
+// Launch with programmatic stream serialisation (PDL): the grid may be scheduled while the previous kernel
+// of the stream drains; the kernel itself waits (griddepcontrol.wait) before it touches global memory.
+// PPB_NO_PDL=1 in the environment falls back to plain launches (for A/B timing).
+static inline bool pdl_enabled() {
+  static int on = -1;
+  if (on < 0) {
+    const char *e = getenv("PPB_NO_PDL");
+    on = (e && e[0] == '1') ? 0 : 1;
+  }
+  return on == 1;
+}
+
+template <typename... KArgs, typename... Args>
+static inline cudaError_t launch_pdl(void (*kernel)(KArgs...), dim3 grid, dim3 block, size_t smem, cudaStream_t st,
+                                     Args... args) {
+  cudaLaunchConfig_t cfg = {};
+  cfg.gridDim = grid;
+  cfg.blockDim = block;
+  cfg.dynamicSmemBytes = smem;
+  cfg.stream = st;
+  cudaLaunchAttribute attr[1];
+  attr[0].id = cudaLaunchAttributeProgrammaticStreamSerialization;
+  attr[0].val.programmaticStreamSerializationAllowed = 1;
+  cfg.attrs = attr;
+  cfg.numAttrs = pdl_enabled() ? 1 : 0;
+  return cudaLaunchKernelEx(&cfg, kernel, KArgs(args)...);
+}
+
 template <typename T>
 size_t Launch<T>::hdr_size() { return sizeof(Hdr<T>); }
 
@@ -16,11 +44,9 @@ cudaError_t Launch<T>::integrate(const StatePtrs &S, int n_balls, const StepPara
   if (total == 0) return cudaSuccess;
   if ((n_balls & 1) == 0) {
     const long long thr = total / 2;
-    integrate_kernel<T, 2><<<(unsigned)((thr + 255) / 256), 256, 0, st>>>(S, n_balls, P, (T *)traj);
-  } else {
-    integrate_kernel<T, 1><<<(unsigned)((total + 255) / 256), 256, 0, st>>>(S, n_balls, P, (T *)traj);
+    return launch_pdl(integrate_kernel<T, 2>, dim3((unsigned)((thr + 255) / 256)), dim3(256), 0, st, S, n_balls, P, (T *)traj);
   }
-  return cudaGetLastError();
+  return launch_pdl(integrate_kernel<T, 1>, dim3((unsigned)((total + 255) / 256)), dim3(256), 0, st, S, n_balls, P, (T *)traj);
 }
 
 template <typename T>
@@ -40,12 +66,12 @@ cudaError_t Launch<T>::collide(const StatePtrs &S, const Layout &L, const StepPa
   const int nb = L.n_balls;
   const dim3 blk(PPB_COLLIDE_WARPS * 32);
   // lanes per world: one warp up to 8 balls, a team of 2 warps for 16, of 4 warps for 32
-  if (nb <= 1) collide_kernel<T, 1, 1><<<grid, blk, 0, st>>>(S, L, P, (T *)traj);
-  else if (nb <= 2) collide_kernel<T, 2, 1><<<grid, blk, 0, st>>>(S, L, P, (T *)traj);
-  else if (nb <= 4) collide_kernel<T, 4, 1><<<grid, blk, 0, st>>>(S, L, P, (T *)traj);
-  else if (nb <= 8) collide_kernel<T, 8, 1><<<grid, blk, 0, st>>>(S, L, P, (T *)traj);
-  else if (nb <= 16) collide_kernel<T, 16, 2><<<grid, blk, 0, st>>>(S, L, P, (T *)traj);
-  else collide_kernel<T, 32, 4><<<grid, blk, 0, st>>>(S, L, P, (T *)traj);
+  if (nb <= 1) return launch_pdl(collide_kernel<T, 1, 1>, dim3(grid), blk, 0, st, S, L, P, (T *)traj);
+  else if (nb <= 2) return launch_pdl(collide_kernel<T, 2, 1>, dim3(grid), blk, 0, st, S, L, P, (T *)traj);
+  else if (nb <= 4) return launch_pdl(collide_kernel<T, 4, 1>, dim3(grid), blk, 0, st, S, L, P, (T *)traj);
+  else if (nb <= 8) return launch_pdl(collide_kernel<T, 8, 1>, dim3(grid), blk, 0, st, S, L, P, (T *)traj);
+  else if (nb <= 16) return launch_pdl(collide_kernel<T, 16, 2>, dim3(grid), blk, 0, st, S, L, P, (T *)traj);
+  else return launch_pdl(collide_kernel<T, 32, 4>, dim3(grid), blk, 0, st, S, L, P, (T *)traj);
   return cudaGetLastError();
 }
 
