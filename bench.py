@@ -253,7 +253,7 @@ def run_ours(args, rank, local_rank, world_size):
     barrier()
     c0 = wb.counters()
     st0, _ = wb.get_status()
-    wb.set_profiling(True)
+    wb.set_profiling(2)     # events around the render launches only (see the second pass below)
     clocks = ClockSampler(local_rank)
     clocks.start()
     e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
@@ -271,6 +271,16 @@ def run_ours(args, rank, local_rank, world_size):
     st1, steps_done = wb.get_status()
     live = int((st1 == 0).sum())
     launches = c1["launches"] - c0["launches"]
+    # second, untimed pass of the same K steps with events around integrate and collide: an event pair between
+    # two kernels of a stream serialises their launches (about 4 % of this step), so the two small kernels are
+    # timed here and only the dominant one inside the timed region
+    wb.set_profiling(3)
+    wb.step_ring_async(args.steps, frames, 1)
+    torch.cuda.synchronize(dev)
+    kms2, kn2 = wb.kernel_times()
+    wb.set_profiling(False)
+    kms = [kms2[0], kms2[1], kms[2]]
+    kn = [kn2[0], kn2[1], kn[2]]
 
     k_ms, k_n = np.array(kms), np.array(kn)
     avg_us = 1e3 * k_ms / np.maximum(k_n, 1)
@@ -363,8 +373,9 @@ def run_ours(args, rank, local_rank, world_size):
             "roofline": {"bound": "hbm", "kernel": names[dom], "achieved": achieved[dom], "peak": peak,
                          "unit": "GB/s", "frac": achieved[dom] / peak, "traffic": load_traffic(names[dom]), "peak_source": peak_src,
                          "avg_launch_us": float(avg_us[dom]),
-                         "note": "kernel times are CUDA-event times inside the timed region, where the render of step k "
-                                 "shares the SMs with integrate+collide of step k+1; render alone: %.1f us/launch = %.3f of peak"
+                         "note": "render: CUDA-event times of every launch inside the timed region, where the render of step k "
+                                 "shares the SMs with integrate+collide of step k+1 (integrate/collide: event times of a second "
+                                 "pass of the same K steps); render alone: %.1f us/launch = %.3f of peak"
                                  % (render_alone_us, alg_bytes[2] / (render_alone_us * 1e-6) / 1e9 / peak),
                          "render_alone_us": render_alone_us,
                          "all_kernels": {names[i]: {"avg_launch_us": float(avg_us[i]), "achieved_gbs": achieved[i],

@@ -289,8 +289,11 @@ PPB_API int ppb_device_ptr(ppb_batch *b, int32_t which, void **ptr, int64_t *nby
 
 /* time (ms) and launch count of the integrate / collide / render kernels, measured with
  * CUDA events recorded around every launch on the launching stream and summed over all
- * stepping calls since ppb_set_profiling(b, 1) / the previous ppb_get_kernel_times (which
- * waits for the recorded events and resets the accumulation). */
+ * stepping calls since ppb_set_profiling(b, mode) / the previous ppb_get_kernel_times (which
+ * waits for the recorded events and resets the accumulation).
+ * mode: 0 off, 1 every kernel, 2 the render kernel only, 3 integrate + collide only.  An event pair between
+ * two kernels of a stream keeps the second from being scheduled while the first drains (a few us per
+ * launch), so mode 2 is what a throughput measurement that also wants the dominant kernel's time uses. */
 PPB_API int ppb_set_profiling(ppb_batch *b, int32_t on);
 PPB_API int ppb_get_kernel_times(ppb_batch *b, float ms[3], int32_t launches[3]);
 

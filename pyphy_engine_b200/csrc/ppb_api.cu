@@ -5,6 +5,7 @@
 
 #include <cmath>
 #include <cstdarg>
+#include <cstdlib>
 #include <cstdio>
 #include <cstring>
 #include <new>
@@ -66,7 +67,7 @@ struct ppb_batch {
   int64_t launches = 0;
   int32_t host_step = 0;  // mirrors *S.step_base
   // profiling (CUDA events around every kernel of the last ppb_step_async)
-  bool profiling = false;
+  int profiling = 0;   // bit k: CUDA events around kernel kind k (0 integrate, 1 collide, 2 render)
   std::vector<cudaEvent_t> ev_pool;
   std::vector<int> ev_kind;  // kernel kind per (start, stop) pair
   size_t ev_used = 0;
@@ -169,7 +170,7 @@ struct Prof {
   int kind;
   bool on;
   size_t idx = 0;
-  Prof(ppb_batch *b_, cudaStream_t st_, int kind_) : b(b_), st(st_), kind(kind_), on(b_->profiling) {
+  Prof(ppb_batch *b_, cudaStream_t st_, int kind_) : b(b_), st(st_), kind(kind_), on(((b_->profiling >> kind_) & 1) != 0) {
     if (!on) return;
     if (b->ev_used + 2 > b->ev_pool.size()) {
       for (int i = 0; i < 2; ++i) {
@@ -238,7 +239,12 @@ int pipeline_reserve(ppb_batch *b) {
     CU(cudaEventCreateWithFlags(&b->ev_phys[i], cudaEventDisableTiming));
     CU(cudaEventCreateWithFlags(&b->ev_rend[i], cudaEventDisableTiming));
   }
-  CU(cudaStreamCreateWithFlags(&b->render_stream, cudaStreamNonBlocking));
+  // highest priority: the render of step k and the integrate kernel of step k+1 become ready at the same moment;
+  // the renderer's one large CTA per SM should be placed before the small physics CTAs fill the SM (it does not
+  // fit next to more than two collide CTAs).  Measured neutral on the 131,072 x 8 workload (0.4337 vs 0.4345 ms).
+  int prio_lo = 0, prio_hi = 0;
+  CU(cudaDeviceGetStreamPriorityRange(&prio_lo, &prio_hi));
+  CU(cudaStreamCreateWithPriority(&b->render_stream, cudaStreamNonBlocking, prio_hi));
   return PPB_OK;
 }
 
@@ -970,7 +976,9 @@ int ppb_device_ptr(ppb_batch *b, int32_t which, void **ptr, int64_t *nbytes) {
 
 int ppb_set_profiling(ppb_batch *b, int32_t on) {
   if (!b) return fail(PPB_E_INVALID, "null batch");
-  b->profiling = on != 0;
+  if (on < 0 || on > 3) return fail(PPB_E_INVALID, "profiling mode must be 0..3");
+  static const int mask[4] = {0, 7, 4, 3};
+  b->profiling = mask[on];
   b->ev_used = 0;
   return PPB_OK;
 }

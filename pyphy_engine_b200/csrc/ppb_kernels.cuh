@@ -223,7 +223,7 @@ template <typename T, int TW>
 struct TeamSmem {
   WarpSmem<T> w;                                  // ball / edge staging shared by the team
   ScanPart<T> part[TW > 1 ? TW : 1][TW > 1 ? 32 : 1];
-  int ticket, next_world;
+  int ticket;
 };
 
 template <int TW>
@@ -278,15 +278,26 @@ collide_kernel(StatePtrs S, Layout L, StepParams P, T *traj) {
   const T2 *gwall = reinterpret_cast<const T2 *>(S.wall);
 
   unsigned long long cnt_iters = 0, cnt_rescans = 0;
-  // the first world of every team is its own index in the grid (no atomic on the way to the first loads);
-  // the ticket counter hands out the worlds after those
-  const int n_teams = (int)gridDim.x * TEAMS;
-  int idx = (int)blockIdx.x * TEAMS + team;
-  int w = idx < count ? S.list[idx] : 0;
+  // NB: small changes here flip ptxas between a 64-register allocation (two CTAs fit next to the render kernel's
+  // CTA when physics and render overlap) and an 80-register one.  Measured and rejected on B200: the first world
+  // of a warp taken from its grid index instead of a ticket (65,536 x 4 worlds: 26.7 -> 24.6 us per step, but
+  // 131,072 x 8 with frames: 407 -> 418 us) and one first-ticket atomic per CTA (same picture); forcing 64
+  // registers with a minimum-blocks launch bound made every workload slower.
+  int idx = 0;
+  if (TW == 1) {
+    if (lane == 0) idx = atomicAdd(ticket, 1);
+    idx = __shfl_sync(FULL, idx, 0);
+  } else {
+    if (wt == 0 && lane == 0) ts.ticket = atomicAdd(ticket, 1);
+    team_sync<TW>(team);
+    idx = ts.ticket;
+    team_sync<TW>(team);
+  }
 
   while (idx < count) {
     int idx_next = 0;
-    if (wt == 0 && lane == 0) idx_next = n_teams + atomicAdd(ticket, 1);   // its latency hides behind this world's work
+    if (wt == 0 && lane == 0) idx_next = atomicAdd(ticket, 1);   // its latency hides behind this world's work
+    const int w = S.list[idx];
     const bool has_ball = bi < nB;
     const long long base = (long long)w * nB;
 
@@ -339,9 +350,6 @@ collide_kernel(StatePtrs S, Layout L, StepParams P, T *traj) {
     T tStep = T(0), mnt = INF;
     uint32_t nev_local = 0;
     int iters = 0;
-    // the next world's list entry: fetched by the ticket holder while this world is worked on
-    int w_next = 0;
-    if (wt == 0 && lane == 0 && idx_next < count) w_next = S.list[idx_next];
 
     for (;;) {
       if (pending) {
@@ -539,15 +547,10 @@ collide_kernel(StatePtrs S, Layout L, StepParams P, T *traj) {
     }
     if (TW == 1) {
       idx = __shfl_sync(FULL, idx_next, 0);
-      w = __shfl_sync(FULL, w_next, 0);
     } else {
-      if (wt == 0 && lane == 0) {
-        ts.ticket = idx_next;
-        ts.next_world = w_next;
-      }
+      if (wt == 0 && lane == 0) ts.ticket = idx_next;
       team_sync<TW>(team);
       idx = ts.ticket;
-      w = ts.next_world;
       team_sync<TW>(team);
     }
   }

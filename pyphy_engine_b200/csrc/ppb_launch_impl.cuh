@@ -1,5 +1,7 @@
 // ppb_launch_impl.cuh -- body of Launch<T>, included by ppb_f32.cu / ppb_f64.cu
 #pragma once
+#include <cstdlib>
+
 #include "ppb_kernels.cuh"
 #include "ppb_launch.h"
 #include "ppb_post.cuh"

@@ -359,8 +359,9 @@ class WorldBatch:
         self.steps_done += int(n_steps)
 
     # ------------------------------------------------------------------ profiling
-    def set_profiling(self, on: bool):
-        check(self._lib.ppb_set_profiling(self._h, 1 if on else 0))
+    def set_profiling(self, on):
+        """False/0 off, True/1 every kernel, 2 the render kernel only, 3 integrate + collide only."""
+        check(self._lib.ppb_set_profiling(self._h, int(on)))
 
     def kernel_times(self):
         """(ms[3], launches[3]) for integrate / collide / render of the last stepping call."""

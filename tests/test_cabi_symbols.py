@@ -67,3 +67,33 @@ def test_argument_validation_happens_before_cuda():
     assert rc == -1 and b"n_balls" in lib.ppb_last_error()
     cfg.n_balls, cfg.dt = 4, 0.0
     assert lib.ppb_create(ctypes.byref(cfg), ctypes.byref(h)) == -1
+
+
+def test_register_budget_of_overlapping_kernels():
+    """The render kernel (one 384-thread CTA per SM) and two fp32 collide CTAs share an SM when the physics
+    of step k+1 overlaps the render of step k: 384 * 120 + 2 * 128 * 64 <= 65,536 registers.  ptxas reaches
+    the 64 by itself and small source changes make it choose 80 (then only one collide CTA fits and the
+    pipelined step is ~3 % slower on B200) -- this test is the tripwire."""
+    import re
+    import shutil
+    import subprocess
+    from pyphy_engine_b200 import _capi
+    cuobjdump = shutil.which("cuobjdump") or "/usr/local/cuda/bin/cuobjdump"
+    if not os.path.exists(cuobjdump) or not os.path.exists(_capi.LIB_PATH):
+        pytest.skip("cuobjdump or the built library is not available")
+    out = subprocess.run([cuobjdump, "-res-usage", _capi.LIB_PATH], capture_output=True, text=True).stdout
+    regs = {}
+    name = None
+    for line in out.splitlines():
+        m = re.search(r"Function (\S+):", line)
+        if m:
+            name = m.group(1)
+        m = re.search(r"REG:(\d+)", line)
+        if m and name:
+            regs[name] = int(m.group(1))
+    collide = {k: v for k, v in regs.items() if "collide_kernelIfLi" in k and "ELi1E" in k}   # fp32, one warp per world
+    render = {k: v for k, v in regs.items() if "render_tile_kernelIf" in k}
+    assert collide and render, sorted(regs)
+    assert max(collide.values()) <= 64, collide
+    assert max(render.values()) <= 120, render
+    assert 384 * max(render.values()) + 2 * 128 * max(collide.values()) <= 65536

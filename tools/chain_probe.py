@@ -15,7 +15,7 @@ import sys
 import numpy as np
 import torch
 
-sys.path.insert(0, os.path.dirname(os.path.dirname(os.path.abspath(__file__))))
+sys.path.insert(0, os.environ.get("PPB_ROOT") or os.path.dirname(os.path.dirname(os.path.abspath(__file__))))
 from pyphy_engine_b200.engine import WorldBatch  # noqa: E402
 
 ARENA = {4: 700, 8: 1200, 16: 1600, 32: 2400}

@@ -16,6 +16,7 @@ for K in integrate_kernel collide_kernel render_tile_kernel; do
   ncu --set full --import-source on --clock-control none -k regex:$K -s 8 -c 1 -f -o $OUT/${TAG}_full_$K \
       python tools/perf_probe.py --worlds 131072 --balls 8 --steps 12 --render --warm 8 --max-substeps 64 > $OUT/${TAG}_ncu_$K.log 2>&1
 done
+[ -x tools/_bin/store_ceiling ] && tools/_bin/store_ceiling > $OUT/${TAG}_store_ceiling.log 2>&1
 python tools/sweep.py --out $OUT/${TAG}_sweep.json > $OUT/${TAG}_sweep.log 2>&1
 tail -3 $OUT/${TAG}_pytest_gpu.log
 tail -2 $OUT/${TAG}_smoke.log

@@ -21,7 +21,15 @@ EXTRA = ["dram__bytes_read.sum.per_second", "dram__bytes_write.sum.per_second",
          "launch__shared_mem_per_block_static", "sm__warps_active.avg.per_cycle_active",
          "smsp__cycles_active.avg", "l1tex__t_sector_hit_rate.pct", "lts__t_sector_hit_rate.pct",
          "smsp__sass_inst_executed_op_shared_st.sum", "smsp__sass_inst_executed_op_global_st.sum",
-         "sm__sass_inst_executed_op_global_ld.sum", "sm__sass_inst_executed_op_shared_ld.sum"]
+         "sm__sass_inst_executed_op_global_ld.sum", "sm__sass_inst_executed_op_shared_ld.sum",
+         # unit utilisations: which pipe is the busiest
+         "l1tex__data_pipe_lsu_wavefronts.avg.pct_of_peak_sustained_elapsed",
+         "l1tex__data_pipe_lsu_wavefronts_mem_shared_op_ld.sum.pct_of_peak_sustained_elapsed",
+         "l1tex__data_pipe_lsu_wavefronts_mem_shared_op_st.sum.pct_of_peak_sustained_elapsed",
+         "sm__pipe_alu_cycles_active.avg.pct_of_peak_sustained_active",
+         "sm__pipe_fma_cycles_active.avg.pct_of_peak_sustained_active",
+         "sm__inst_executed_pipe_lsu.avg.pct_of_peak_sustained_active",
+         "sm__inst_executed_pipe_xu.avg.pct_of_peak_sustained_active"]
 
 
 def raw_page(rep):
@@ -63,7 +71,7 @@ def main():
                                  "source": "profiles/%s_ncu_%s.txt" % (rnd, kern)}
             fh.write("\n# heaviest SASS runs (instructions executed per launch)\n")
             fh.write(sass_blocks(rep))
-    for name in ("launches.csv", "bench.json", "bench_reference.json", "pytest_gpu.log", "smoke.log", "sweep.json"):
+    for name in ("launches.csv", "bench.json", "bench_reference.json", "pytest_gpu.log", "smoke.log", "sweep.json", "store_ceiling.log"):
         p = os.path.join(src, "%s_%s" % (tag, name))
         if os.path.exists(p):
             shutil.copy(p, os.path.join(dst, "%s_%s" % (rnd, name)))
