@@ -297,23 +297,34 @@ def run_ours(args, rank, local_rank, world_size):
     render_alone_us = 1e3 * iso0.elapsed_time(iso1) / 5.0
 
     # ---- end-to-end through the host-buffer API: H2D of the batch state + step + D2H of positions and frames ----
-    traj_host = torch.empty((1, n_worlds, N_BALLS, 2), dtype=torch.float32).pin_memory()
-    frames_host = torch.empty((1, n_worlds, CANVAS, CANVAS, 4), dtype=torch.uint8).pin_memory()
+    # Two sets of pinned host buffers: the call of step i only enqueues (ppb_simulate_host_async); while its frames
+    # cross PCIe the inputs of step i+1 are uploaded (the other direction) and its kernels run; step i's buffers are
+    # read on the host once ppb_host_sync(keep_in_flight=1) says they are complete.
+    traj_hosts = [torch.empty((1, n_worlds, N_BALLS, 2), dtype=torch.float32).pin_memory() for _ in range(2)]
+    frames_hosts = [torch.empty((1, n_worlds, CANVAS, CANVAS, 4), dtype=torch.uint8).pin_memory() for _ in range(2)]
+    traj_host, frames_host = traj_hosts[0], frames_hosts[0]
     e2e_steps = max(3, min(args.steps, 10))
     h2d = W["pos"].nbytes // 2 + W["vel"].nbytes // 2 + W["rad"].nbytes + W["wall"].nbytes // 2   # fp32 on the wire
     d2h = traj_host.numel() * 4 + frames_host.numel()
     wb.set_walls(W["wall"])
     wb.set_balls(W["pos"], W["vel"], W["rad"], W["mass"])
-    wb.simulate_host(1, traj_host, frames_host, 1)        # warm-up (allocates the staging buffers)
+    wb.simulate_host(1, traj_hosts[0], frames_hosts[0], 1)        # warm-up (allocates the staging buffers)
+    wb.simulate_host(1, traj_hosts[1], frames_hosts[1], 1)
     barrier()
+    e2e_checksum = 0
     t0 = time.perf_counter()
-    for _ in range(e2e_steps):
+    for i in range(e2e_steps):
         wb.set_walls(W["wall"])                                       # host -> device: this step's input tables
         wb.set_balls(W["pos"], W["vel"], W["rad"], W["mass"])
-        wb.simulate_host(1, traj_host, frames_host, 1)                # step + render + device -> host
+        wb.simulate_host(1, traj_hosts[i & 1], frames_hosts[i & 1], 1, wait=False)   # step + render + device -> host, enqueued
+        wb.host_sync(keep_in_flight=1)                                # step i-1 is on the host now
+        if i > 0:
+            e2e_checksum += int(frames_hosts[(i - 1) & 1][0, 0, 0, :8].sum()) + int(traj_hosts[(i - 1) & 1][0, 0, 0, 0] != 0)
+    wb.host_sync()
+    e2e_checksum += int(frames_hosts[(e2e_steps - 1) & 1][0, :64].sum())
     barrier()
     e2e_s = time.perf_counter() - t0
-    e2e_checksum = int(frames_host[0, :64].sum())
+    traj_host = traj_hosts[(e2e_steps - 1) & 1]
 
     # ---- reductions: max time over ranks, totals over ranks ----
     stats = torch.tensor([ms, e2e_s, float(live), float(c1["events"] - c0["events"]), float(launches)],
@@ -385,7 +396,7 @@ def run_ours(args, rank, local_rank, world_size):
             "e2e": {"value": live_total * N_BALLS * e2e_steps / e2e_s, "unit": "ball-steps/s",
                     "frames_per_sec": live_total * e2e_steps / e2e_s,
                     "h2d_bytes_per_step": int(h2d), "d2h_bytes_per_step": int(d2h), "steps": e2e_steps,
-                    "api": "WorldBatch.set_walls/set_balls + simulate_host (ppb_simulate_host), pinned host buffers",
+                    "api": "per step: WorldBatch.set_walls/set_balls (H2D) + simulate_host(wait=False) (ppb_simulate_host_async: step, render, D2H) + host_sync(keep_in_flight=1); two sets of pinned host buffers, so the upload of step i+1 overlaps the download of step i",
                     "numa_node_rank0": numa_node},
             "final_gather": gather_info,
             "gpu_launches": int(launches_total),

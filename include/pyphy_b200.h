@@ -249,6 +249,17 @@ PPB_API int ppb_render_async(ppb_batch *b, uint8_t *frames_dev, void *stream);
 PPB_API int ppb_simulate_host(ppb_batch *b, int32_t n_steps, float *traj_host, uint8_t *frames_host,
                       int32_t render_every, void *stream);
 
+/* The same without waiting: returns once the steps and the device -> host copies are enqueued (the copies run on a
+ * stream owned by the batch, behind the kernels).  The host buffers of a call are complete after
+ * ppb_host_sync(b, 0, stream) -- or after ppb_host_sync(b, 1, stream) once a later call has been enqueued
+ * (keep_in_flight = 1 waits for every call but the most recent one).  Until then they must not be read, and the
+ * next call must be given different host buffers.  Lets a caller upload the inputs of the next batch
+ * (ppb_set_walls / ppb_set_balls on `stream`) while the frames of this one are still crossing PCIe -- the two
+ * directions do not share bandwidth. */
+PPB_API int ppb_simulate_host_async(ppb_batch *b, int32_t n_steps, float *traj_host, uint8_t *frames_host,
+                            int32_t render_every, void *stream);
+PPB_API int ppb_host_sync(ppb_batch *b, int32_t keep_in_flight, void *stream);
+
 /* The ball-centred crops of DataSaver.fetch(cropSz) (dataio.py:160-182) for every frame, world and ball:
  *   frames_dev : [n_frames][n_worlds][H][W][4] uint8 (what ppb_step_async rendered)
  *   traj_dev   : [n_frames][n_worlds][n_balls][2] in the batch dtype -- the ball centres in those frames

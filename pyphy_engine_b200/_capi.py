@@ -93,6 +93,8 @@ SIGNATURES = {
     "ppb_step_ring_async": (ctypes.c_int, [_vp, _i32, _vp, _vp, _i32, _i32, _vp]),
     "ppb_render_async": (ctypes.c_int, [_vp, _vp, _vp]),
     "ppb_simulate_host": (ctypes.c_int, [_vp, _i32, _vp, _vp, _i32, _vp]),
+    "ppb_simulate_host_async": (ctypes.c_int, [_vp, _i32, _vp, _vp, _i32, _vp]),
+    "ppb_host_sync": (ctypes.c_int, [_vp, _i32, _vp]),
     "ppb_crop_async": (ctypes.c_int, [_vp, _vp, _vp, _i32, _i32, _i32, _vp, _vp, _vp]),
     "ppb_collision_flags_async": (ctypes.c_int, [_vp, _i64, _i32, ctypes.c_float, _vp, _vp]),
     "ppb_read_events": (ctypes.c_int, [_vp, ctypes.POINTER(Event), _i64, ctypes.POINTER(_i64), _vp]),

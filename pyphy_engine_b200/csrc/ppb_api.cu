@@ -86,6 +86,9 @@ struct ppb_batch {
   int scr_chunk = 0;
   cudaStream_t copy_stream = nullptr;
   cudaEvent_t ev_done[2] = {nullptr, nullptr}, ev_copied[2] = {nullptr, nullptr};
+  unsigned sim_it = 0;   // staging buffers used so far (they alternate across ppb_simulate_host* calls)
+  cudaEvent_t ev_call[2] = {nullptr, nullptr};   // end of the copies of the last two ppb_simulate_host* calls
+  unsigned sim_calls = 0;
 };
 
 namespace {
@@ -258,12 +261,15 @@ void free_scratch(ppb_batch *b) {
     b->scr_frames[i] = nullptr;
     if (b->ev_done[i]) cudaEventDestroy(b->ev_done[i]);
     if (b->ev_copied[i]) cudaEventDestroy(b->ev_copied[i]);
-    b->ev_done[i] = b->ev_copied[i] = nullptr;
+    if (b->ev_call[i]) cudaEventDestroy(b->ev_call[i]);
+    b->ev_done[i] = b->ev_copied[i] = b->ev_call[i] = nullptr;
   }
   if (b->copy_stream) cudaStreamDestroy(b->copy_stream);
   b->copy_stream = nullptr;
   b->scr_traj_bytes = b->scr_frames_bytes = 0;
   b->scr_chunk = 0;
+  b->sim_it = 0;
+  b->sim_calls = 0;
 }
 
 }  // namespace
@@ -806,8 +812,8 @@ int ppb_render_async(ppb_batch *b, uint8_t *frames_dev, void *stream) {
   return PPB_OK;
 }
 
-int ppb_simulate_host(ppb_batch *b, int32_t n_steps, float *traj_host, uint8_t *frames_host, int32_t render_every,
-                      void *stream) {
+static int simulate_host_impl(ppb_batch *b, int32_t n_steps, float *traj_host, uint8_t *frames_host,
+                              int32_t render_every, void *stream, bool wait) {
   if (!b) return fail(PPB_E_INVALID, "null batch");
   if (n_steps < 0) return fail(PPB_E_INVALID, "n_steps must be >= 0");
   if (frames_host) {
@@ -845,17 +851,18 @@ int ppb_simulate_host(ppb_batch *b, int32_t n_steps, float *traj_host, uint8_t *
       if (need_frames) CU(cudaMalloc((void **)&b->scr_frames[i], need_frames));
       CU(cudaEventCreateWithFlags(&b->ev_done[i], cudaEventDisableTiming));
       CU(cudaEventCreateWithFlags(&b->ev_copied[i], cudaEventDisableTiming));
+      CU(cudaEventCreateWithFlags(&b->ev_call[i], cudaEventDisableTiming));
     }
     CU(cudaStreamCreateWithFlags(&b->copy_stream, cudaStreamNonBlocking));
     b->scr_traj_bytes = need_traj;
     b->scr_frames_bytes = need_frames;
     b->scr_chunk = chunk;
   }
-  int done = 0, it = 0;
+  int done = 0;
   while (done < n_steps) {
     const int cur = (n_steps - done < chunk) ? (n_steps - done) : chunk;
-    const int buf = it & 1;
-    if (it >= 2) CU(cudaStreamWaitEvent(st, b->ev_copied[buf], 0));  // staging buffer free again
+    const int buf = (int)(b->sim_it & 1u);
+    if (b->sim_it >= 2) CU(cudaStreamWaitEvent(st, b->ev_copied[buf], 0));  // staging buffer free again
     for (int s = 0; s < cur; ++s) {
       uint8_t *frame = nullptr;
       const int gs = done + s;
@@ -886,10 +893,39 @@ int ppb_simulate_host(ppb_batch *b, int32_t n_steps, float *traj_host, uint8_t *
     }
     CU(cudaEventRecord(b->ev_copied[buf], b->copy_stream));
     done += cur;
-    ++it;
+    ++b->sim_it;
   }
-  CU(cudaStreamSynchronize(st));
-  CU(cudaStreamSynchronize(b->copy_stream));
+  CU(cudaEventRecord(b->ev_call[b->sim_calls & 1u], b->copy_stream));
+  ++b->sim_calls;
+  if (wait) {
+    CU(cudaStreamSynchronize(st));
+    CU(cudaStreamSynchronize(b->copy_stream));
+  }
+  return PPB_OK;
+}
+
+int ppb_simulate_host(ppb_batch *b, int32_t n_steps, float *traj_host, uint8_t *frames_host, int32_t render_every,
+                      void *stream) {
+  return simulate_host_impl(b, n_steps, traj_host, frames_host, render_every, stream, true);
+}
+
+int ppb_simulate_host_async(ppb_batch *b, int32_t n_steps, float *traj_host, uint8_t *frames_host,
+                            int32_t render_every, void *stream) {
+  return simulate_host_impl(b, n_steps, traj_host, frames_host, render_every, stream, false);
+}
+
+int ppb_host_sync(ppb_batch *b, int32_t keep_in_flight, void *stream) {
+  if (!b) return fail(PPB_E_INVALID, "null batch");
+  if (keep_in_flight < 0 || keep_in_flight > 1) return fail(PPB_E_INVALID, "keep_in_flight must be 0 or 1");
+  CU(cudaSetDevice(b->cfg.device));
+  if (keep_in_flight == 1) {
+    // everything but the most recent call: the copy stream is first-in first-out, so the end of the call before
+    // the last implies all earlier ones (and the kernels they copied from)
+    if (b->sim_calls >= 2 && b->ev_call[b->sim_calls & 1u]) CU(cudaEventSynchronize(b->ev_call[b->sim_calls & 1u]));
+    return PPB_OK;
+  }
+  CU(cudaStreamSynchronize((cudaStream_t)stream));
+  if (b->copy_stream) CU(cudaStreamSynchronize(b->copy_stream));
   return PPB_OK;
 }
 

@@ -341,12 +341,15 @@ class WorldBatch:
                                        _stream_handle(stream, self.device)))
         return crops, pos
 
-    def simulate_host(self, n_steps: int, traj_host=None, frames_host=None, render_every: int = 1, stream=None):
+    def simulate_host(self, n_steps: int, traj_host=None, frames_host=None, render_every: int = 1, stream=None,
+                      wait: bool = True):
         """Host-buffer path (DataSaver.fetch analogue): copies are inside the call.
 
         traj_host: None or float32 array (n_steps, n_worlds, n_balls, 2);
         frames_host: None or uint8 array (n_steps // render_every, n_worlds, H, W, 4).
         numpy arrays or pinned CPU torch tensors are accepted.
+        wait=False returns once everything is enqueued (ppb_simulate_host_async); the host buffers are complete
+        after ``host_sync()`` and must not be reused by another call before that.
         """
         def _ptr(a):
             if a is None:
@@ -354,9 +357,15 @@ class WorldBatch:
             if hasattr(a, "data_ptr"):
                 return ctypes.c_void_p(a.data_ptr())
             return ctypes.c_void_p(a.ctypes.data)
-        check(self._lib.ppb_simulate_host(self._h, int(n_steps), _ptr(traj_host), _ptr(frames_host),
-                                          int(render_every), _stream_handle(stream, self.device)))
+        fn = self._lib.ppb_simulate_host if wait else self._lib.ppb_simulate_host_async
+        check(fn(self._h, int(n_steps), _ptr(traj_host), _ptr(frames_host), int(render_every),
+                 _stream_handle(stream, self.device)))
         self.steps_done += int(n_steps)
+
+    def host_sync(self, keep_in_flight: int = 0, stream=None):
+        """Wait for the steps and device -> host copies of earlier ``simulate_host(..., wait=False)`` calls:
+        all of them (0) or all but the most recent one (1)."""
+        check(self._lib.ppb_host_sync(self._h, int(keep_in_flight), _stream_handle(stream, self.device)))
 
     # ------------------------------------------------------------------ profiling
     def set_profiling(self, on):

@@ -130,3 +130,43 @@ def test_partial_world_range_updates():
     assert np.array_equal(pa[16:32], c.get_balls()[0])
     for wb in (a, b, c):
         wb.close()
+
+
+def test_simulate_host_async_double_buffered():
+    """ppb_simulate_host_async + ppb_host_sync(keep_in_flight): the pipelined host-buffer loop (upload of batch
+    i+1 while batch i downloads) returns the same bytes as the blocking call, batch after batch."""
+    import torch
+    n, nb = 512, 4
+    sets = [sampler.sample_rect_worlds(n, nb, seed=40 + k, **sampler.scaled64_params(nb)) for k in range(5)]
+    styles = ([(1, (.5, .5, .5, 1), (0, 0, 0, 1))] * nb, [(0, (1, 0, 0, 1))] * 4, 3, 3)
+
+    def make():
+        wb = WorldBatch(n, nb, 4, dtype="f32", canvas=(64, 64))
+        wb.set_walls(sets[0]["wall"]); wb.set_balls(sets[0]["pos"], sets[0]["vel"], sets[0]["rad"], sets[0]["mass"])
+        wb.set_styles(*styles)
+        return wb
+
+    ref_t, ref_f = [], []
+    wb = make()
+    for W in sets:
+        wb.set_walls(W["wall"]); wb.set_balls(W["pos"], W["vel"], W["rad"], W["mass"])
+        t = np.empty((3, n, nb, 2), np.float32); f = np.empty((3, n, 64, 64, 4), np.uint8)
+        wb.simulate_host(3, t, f, 1)
+        ref_t.append(t); ref_f.append(f)
+    wb.close()
+
+    wb = make()
+    tb = [torch.empty((3, n, nb, 2), dtype=torch.float32).pin_memory() for _ in range(2)]
+    fb = [torch.empty((3, n, 64, 64, 4), dtype=torch.uint8).pin_memory() for _ in range(2)]
+    for i, W in enumerate(sets):
+        wb.set_walls(W["wall"]); wb.set_balls(W["pos"], W["vel"], W["rad"], W["mass"])
+        wb.simulate_host(3, tb[i & 1], fb[i & 1], 1, wait=False)
+        wb.host_sync(keep_in_flight=1)
+        if i > 0:   # batch i-1 is complete while batch i is still in flight
+            assert np.array_equal(tb[(i - 1) & 1].numpy(), ref_t[i - 1])
+            assert np.array_equal(fb[(i - 1) & 1].numpy(), ref_f[i - 1])
+    wb.host_sync()
+    assert np.array_equal(tb[(len(sets) - 1) & 1].numpy(), ref_t[-1])
+    assert np.array_equal(fb[(len(sets) - 1) & 1].numpy(), ref_f[-1])
+    assert _capi.load().ppb_host_sync(wb._h, 2, None) != 0      # keep_in_flight must be 0 or 1
+    wb.close()
