@@ -56,7 +56,7 @@ def bind_to_gpu_numa_node(device: int) -> Optional[int]:
         with open("/sys/bus/pci/devices/%s/numa_node" % bdf) as fh:
             node = int(fh.read().strip())
         if node < 0:
-            return None
+            raise OSError("no NUMA node in sysfs")      # virtual machines report -1: ask nvidia-smi instead
         with open("/sys/devices/system/node/node%d/cpulist" % node) as fh:
             spec = fh.read().strip()
         cpus = set()
