@@ -199,6 +199,7 @@ struct Prof {
 int step_physics(ppb_batch *b, int step_off, void *traj, void *snap, cudaStream_t st) {
   StepParams P = b->P;
   P.step_off = step_off;
+  P.step_abs = b->host_step + step_off;
   StatePtrs S = b->S;
   S.snap = snap;
   {
@@ -344,6 +345,7 @@ int ppb_create(const ppb_config *cfg, ppb_batch **out) {
   b->P.gy = cfg->gy;
   b->P.friction = cfg->friction;
   b->P.step_off = 0;
+  b->P.step_abs = 0;
   b->P.scan_only = 0;
   b->P.max_substeps = cfg->max_substeps > 0 ? cfg->max_substeps : (1 << 20);
   b->esz = is64(b) ? 8 : 4;
@@ -771,6 +773,7 @@ int ppb_scan_async(ppb_batch *b, void *stream) {
   cudaStream_t st = (cudaStream_t)stream;
   StepParams P = b->P;
   P.step_off = 0;
+  P.step_abs = b->host_step;
   P.scan_only = 1;
   CU(is64(b) ? Launch<double>::list_pending(b->S, st) : Launch<float>::list_pending(b->S, st));
   CU(is64(b) ? Launch<double>::collide(b->S, b->L, P, nullptr, b->collide_grid, st)

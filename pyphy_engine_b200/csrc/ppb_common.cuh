@@ -146,7 +146,9 @@ struct StatePtrs {
 
 struct StepParams {
   double dt, gx, gy, friction;
-  int32_t step_off;   // this launch advances step (*step_base + step_off)
+  int32_t step_off;   // position of this step inside the running call (row of traj)
+  int32_t step_abs;   // index of the step this launch advances (host mirror of *step_base, + step_off): passed by
+                      // value so that no kernel starts with a dependent load of the device counter
   int32_t max_substeps;
   int32_t scan_only;  // collide kernel: drain the collision queue (rescan every ball) and stop; nothing moves
 };

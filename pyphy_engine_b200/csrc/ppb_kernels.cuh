@@ -56,7 +56,7 @@ __global__ void __launch_bounds__(256) integrate_kernel(StatePtrs S, int n_balls
   pdl_wait();
   const long long total = (long long)S.n_worlds * n_balls;
   const long long i = ((long long)blockIdx.x * blockDim.x + threadIdx.x) * BPT;
-  const uint32_t k = (uint32_t)(*S.step_base + P.step_off);
+  const uint32_t k = (uint32_t)P.step_abs;
   if (i < total) {
     const int w = (int)(i / n_balls);
     const bool duty = (i - (long long)w * n_balls) == 0;   // this thread owns the world's header
@@ -257,7 +257,7 @@ collide_kernel(StatePtrs S, Layout L, StepParams P, T *traj) {
   const bool writer = (wt == 0) && (grp == 0); // the lane that owns ball bi's global state
   const int nB = L.n_balls, nWl = L.n_walls;
   pdl_wait();   // the integrate kernel of this step (list, state) is complete and visible
-  const uint32_t k = (uint32_t)(*S.step_base + P.step_off);
+  const uint32_t k = (uint32_t)P.step_abs;
   const T dt = (T)P.dt;
   const V2<T> g = mk<T>((T)P.gx, (T)P.gy);
   const T INF = Lim<T>::inf();
