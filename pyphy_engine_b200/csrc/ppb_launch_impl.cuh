@@ -115,17 +115,23 @@ template <typename T>
 cudaError_t Launch<T>::render(const StatePtrs &S, const Layout &L, const RenderLayout &RL, const uint32_t *atlas,
                               uint8_t *frames, cudaStream_t st) {
   const int tiles = ((RL.W + PPB_TILE - 1) / PPB_TILE) * ((RL.H + PPB_TILE - 1) / PPB_TILE);
-  const long long jobs = (long long)S.n_worlds * tiles;
+  long long jobs = (long long)S.n_worlds * tiles;
   if (jobs == 0) return cudaSuccess;
   // fast path: every wall precedes every ball in the insertion order and rows are 16-byte multiples
   bool walls_first = true;
   for (int k = 0; k < L.n_obj; ++k)
     if (L.order[k] < L.n_walls && k >= L.n_walls) walls_first = false;
   if (walls_first && (reinterpret_cast<uintptr_t>(frames) & 3u) == 0) {
+    // canvases other than 64 pixels wide whose rows are 16-byte multiples: tiles are bands of whole frame rows
+    const bool band = RL.W != PPB_TILE && (RL.W & 3) == 0 && RL.W <= PPB_TILE * PPB_TILE &&
+                      (reinterpret_cast<uintptr_t>(frames) & 15u) == 0 && !getenv("PPB_NO_BAND");
+    if (band) {
+      const int rh = (PPB_TILE * PPB_TILE) / RL.W;
+      jobs = (long long)S.n_worlds * ((RL.H + rh - 1) / rh);
+    }
     const int warps = render_warps(L.n_walls, L.n_balls);
     const int smem = (int)(warps * render_warp_smem_bytes(L.n_walls, L.n_balls));
-    const int smem_max = (int)(PPB_RENDER_MAX_WARPS * render_warp_smem_bytes(0, 0) < 227 * 1024
-                                   ? 227 * 1024 : 227 * 1024);
+    const int smem_max = 227 * 1024;
     // per device (and per instantiation T): SM count, opt-in to the large dynamic shared memory
     static int sm_counts[64] = {0};
     int dev = 0;
@@ -134,7 +140,9 @@ cudaError_t Launch<T>::render(const StatePtrs &S, const Layout &L, const RenderL
     if (!sm_counts[dev]) {
       int n = 0;
       cudaDeviceGetAttribute(&n, cudaDevAttrMultiProcessorCount, dev);
-      cudaError_t e = cudaFuncSetAttribute(render_tile_kernel<T>, cudaFuncAttributeMaxDynamicSharedMemorySize, smem_max);
+      cudaError_t e = cudaFuncSetAttribute(render_tile_kernel<T, false>, cudaFuncAttributeMaxDynamicSharedMemorySize, smem_max);
+      if (e != cudaSuccess) return e;
+      e = cudaFuncSetAttribute(render_tile_kernel<T, true>, cudaFuncAttributeMaxDynamicSharedMemorySize, smem_max);
       if (e != cudaSuccess) return e;
       sm_counts[dev] = n > 0 ? n : 1;
     }
@@ -142,7 +150,8 @@ cudaError_t Launch<T>::render(const StatePtrs &S, const Layout &L, const RenderL
     // persistent: one CTA of `warps` warps per SM, every warp walks the tile list
     long long blocks = (jobs + warps - 1) / warps;
     if (blocks > sm_count) blocks = sm_count;
-    render_tile_kernel<T><<<(unsigned)blocks, warps * 32, smem, st>>>(S, L, RL, atlas, frames);
+    if (band) render_tile_kernel<T, true><<<(unsigned)blocks, warps * 32, smem, st>>>(S, L, RL, atlas, frames);
+    else render_tile_kernel<T, false><<<(unsigned)blocks, warps * 32, smem, st>>>(S, L, RL, atlas, frames);
   } else {
     if (jobs > 2147483647LL) return cudaErrorInvalidValue;
     render_general_kernel<T><<<(unsigned)jobs, 256, 0, st>>>(S, L, RL, atlas, frames);

@@ -223,3 +223,27 @@ def test_full_size_frame_properties():
     hi = np.stack([wall[:, 1, 0, 0], wall[:, 2, 0, 1]], -1)[:, None, :] - 3 - 3 + 0.01
     assert ((pos >= lo) & (pos <= hi)).all(axis=(1, 2))[ok].mean() > 0.999
     wb.close()
+
+
+@pytest.mark.parametrize("canvas", [(32, 48), (128, 70), (700, 333), (1000, 37), (2048, 9), (4096, 5), (4100, 6), (68, 64)])
+def test_frames_band_tiles_identical(canvas):
+    """Canvases that are not 64 pixels wide are drawn in bands of whole frame rows (4096 / W rows per band, one
+    linear bulk copy each; wider than 4096 pixels: square tiles again): every band geometry -- several rows, two
+    rows, one row per band, a last band that is cut short, balls cut by band edges and by the canvas, small sprites
+    composited in pairs -- gives the bytes of the restated renderer."""
+    W, H = canvas
+    rs = np.random.RandomState(W * 7 + H)
+    nw, nb = 3, 6
+    t = max(2, min(W, H) // 12)
+    x1, y1 = W - 3, H - 2
+    wall = np.array([[[[2, 1], [x1, 1], [x1, 1 + t], [2, 1 + t]],
+                      [[x1, 1], [x1, y1], [x1 - t, y1], [x1 - t, 1]],
+                      [[x1, y1], [2, y1], [2, y1 - t], [x1, y1 - t]],
+                      [[2, y1], [2, 1], [2 + t, 1], [2 + t, y1]]]] * nw, np.float64)
+    pos = np.stack([rs.uniform(-4, W + 4, (nw, nb)), rs.uniform(-4, H + 4, (nw, nb))], -1)
+    pos[0, 0] = (W - 0.5, H / 2.0)          # cut by the right edge
+    pos[0, 1] = (W / 2.0, -1.0)             # cut by the top edge
+    pos[1, :2] = [(10.0, H / 2.0), (21.0, H / 2.0)]   # two small sprites with the same geometry side by side
+    for r, st in ((3, 1), (9, 2)):
+        dev, ref = _render_both(wall, pos, r, canvas, st)
+        assert np.array_equal(dev, ref), (canvas, r)

@@ -20,7 +20,7 @@ def run(n_worlds, n_balls, steps, render, dtype="f32", px64=True, warm=100, max_
     t0 = time.time()
     W = sampler.sample_rect_worlds(n_worlds, n_balls, seed=1, **kw)
     t_sample = time.time() - t0
-    canvas = (64, 64) if px64 else (700, 700)
+    canvas = (64, 64) if px64 else ((int(os.environ.get("PPB_PROBE_CANVAS", "700")),) * 2)
     wb = WorldBatch(n_worlds, n_balls, 4, dtype=dtype, canvas=canvas, max_substeps=max_substeps)
     wb.set_walls(W["wall"])
     wb.set_balls(W["pos"], W["vel"], W["rad"], W["mass"])
