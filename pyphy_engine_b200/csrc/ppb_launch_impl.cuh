@@ -122,11 +122,10 @@ cudaError_t Launch<T>::render(const StatePtrs &S, const Layout &L, const RenderL
   for (int k = 0; k < L.n_obj; ++k)
     if (L.order[k] < L.n_walls && k >= L.n_walls) walls_first = false;
   if (walls_first && (reinterpret_cast<uintptr_t>(frames) & 3u) == 0) {
-    // canvases other than 64 pixels wide whose rows are 16-byte multiples: tiles are bands of whole frame rows
-    const bool band = RL.W != PPB_TILE && (RL.W & 3) == 0 && RL.W <= PPB_TILE * PPB_TILE &&
-                      (reinterpret_cast<uintptr_t>(frames) & 15u) == 0 && !getenv("PPB_NO_BAND");
+    // canvases other than 64 pixels wide: tiles are bands of whole frame rows
+    const bool band = RL.W != PPB_TILE && ((RL.W + 3) & ~3) <= PPB_TILE * PPB_TILE && !getenv("PPB_NO_BAND");
     if (band) {
-      const int rh = (PPB_TILE * PPB_TILE) / RL.W;
+      const int rh = (PPB_TILE * PPB_TILE) / ((RL.W + 3) & ~3);
       jobs = (long long)S.n_worlds * ((RL.H + rh - 1) / rh);
     }
     const int warps = render_warps(L.n_walls, L.n_balls);

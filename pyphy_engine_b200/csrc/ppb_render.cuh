@@ -470,15 +470,16 @@ __global__ void __maxnreg__(120) render_tile_kernel(StatePtrs S, Layout L, Rende
     sm.wspan = reinterpret_cast<int2 *>(sm.b + L.n_balls);
     sm.w = reinterpret_cast<SWallGeom *>(sm.wspan + L.n_walls);            // 4-byte aligned members only
   }
-  const int RS = BAND ? RL.W : PPB_TILE;                              // pixels per tile row (row stride in the buffer)
-  const int RH = BAND ? (PPB_TILE * PPB_TILE) / RL.W : PPB_TILE;      // rows per tile
+  // pixels per tile row (row stride in the buffer; a band pads it to a multiple of 4) and rows per tile
+  const int RS = BAND ? ((RL.W + 3) & ~3) : PPB_TILE;
+  const int RH = BAND ? (PPB_TILE * PPB_TILE) / RS : PPB_TILE;
   const int RS4 = RS >> 2;                                            // 4-pixel groups per tile row
   const int tiles_x = BAND ? 1 : (RL.W + PPB_TILE - 1) / PPB_TILE;
   const int tiles_y = (RL.H + RH - 1) / RH;
   const int tiles = tiles_x * tiles_y;
   const long long total = (long long)S.n_worlds * tiles;
   const int nB = L.n_balls, nWl = L.n_walls;
-  const bool whole_rows = BAND || (RL.W == PPB_TILE);   // tile rows are contiguous in the frame
+  const bool whole_rows = (BAND && RS == RL.W) || (RL.W == PPB_TILE);   // the tile is contiguous in the frame
   const bool bulk_ok = ((RL.W & 3) == 0) && ((reinterpret_cast<uintptr_t>(frames) & 15u) == 0);
   // raw state of the world of the current / next tile, held in registers: lane q < nWl keeps wall q's
   // WallRC, lane b keeps ball b's position and radius.  The next tile's loads are
@@ -734,9 +735,42 @@ __global__ void __maxnreg__(120) render_tile_kernel(StatePtrs S, Layout L, Rende
     fence_async_smem();   // this lane's generic-proxy writes become visible to the async proxy
     __syncwarp();
     uint32_t *out = reinterpret_cast<uint32_t *>(frames) + (size_t)w * RL.W * RL.H;
-    if (!bulk_ok) {
-      // rows of this canvas are not 16-byte aligned (e.g. the reference's default arenaSz = 667):
-      // the copy engine cannot take them, the warp stores the tile row by row (coalesced 128-byte stores)
+    if (BAND && !bulk_ok) {
+      // Rows of this canvas are not 16-byte multiples (the reference's default arenaSz = 667) or the frame buffer
+      // is not 16-byte aligned: the copy engine cannot take the band.  It is still one contiguous run of
+      // th * W pixels in the frame, so the warp streams it out with 16-byte stores from the first aligned pixel
+      // on (the four pixels of a store may sit on two rows of the padded buffer), scalar stores at both ends.
+      const int Wp = RL.W, npx = th * Wp;
+      uint32_t *gp = out + (size_t)ty0 * Wp;
+      const int lead = min(npx, (int)(((16u - (uint32_t)(reinterpret_cast<uintptr_t>(gp) & 15u)) & 15u) >> 2));
+      const int nvec = (npx - lead) >> 2;
+      const float inv_w = __frcp_rn((float)Wp);
+      if (lane < lead) {
+        const int r = lane / Wp;
+        gp[lane] = sm.tile[r * RS + (lane - r * Wp)];
+      }
+      for (int v = lane; v < nvec; v += 32) {
+        const int p = lead + (v << 2);
+        int r = (int)(((float)p + 0.5f) * inv_w);
+        int c = p - r * Wp;
+        if (c < 0) { --r; c += Wp; } else if (c >= Wp) { ++r; c -= Wp; }
+        uint32_t q[4];
+#pragma unroll
+        for (int k = 0; k < 4; ++k) {
+          q[k] = sm.tile[r * RS + c];
+          if (++c == Wp) { c = 0; ++r; }
+        }
+        *reinterpret_cast<uint4 *>(gp + p) = make_uint4(q[0], q[1], q[2], q[3]);
+      }
+      {
+        const int p = lead + (nvec << 2) + lane;
+        if (p < npx) {
+          const int r = p / Wp;
+          gp[p] = sm.tile[r * RS + (p - r * Wp)];
+        }
+      }
+    } else if (!bulk_ok) {
+      // square tiles of a canvas whose rows the copy engine cannot take: row by row, coalesced 4-byte stores
       for (int r = 0; r < th; ++r) {
         uint32_t *orow = out + (size_t)(ty0 + r) * RL.W + tx0;
         for (int c = lane; c < tw; c += 32) orow[c] = sm.tile[r * RS + c];
