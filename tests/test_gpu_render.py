@@ -101,7 +101,8 @@ def test_frames_walldef_walls_identical():
 
 
 @pytest.mark.parametrize("name,canvas", [("diamond", (640, 480)), ("rhomb3_s300", (1600, 1600)),
-                                         ("rhomb3_s305", (1600, 1600))])
+                                         ("rhomb3_s305", (1600, 1600)), ("ngon3_s800", (800, 800)),
+                                         ("ngon6_s801", (800, 800)), ("ngon8_s800", (800, 800))])
 def test_frames_rotated_walls_within_one_lsb(name, canvas):
     case = [c for c in load_golden("physics_golden.npz") if c.name == name][0]
     dev, ref = _render_both(case["wall"][None], case["pos0"][None], case["rad"][None], canvas, 2,
