@@ -396,12 +396,12 @@ struct RTBall {      // one ball inside the current tile, already clipped to it 
 struct RenderWarpSmem {
   uint32_t *tile;      // [PPB_TILE * PPB_TILE]  16 KB, source of the bulk store
   int4 *wpaint;        // [n_walls] {PPB_WM_*, colour, first tile row | rows << 16, first column group | groups << 16}
-  int2 *wspan;         // [n_walls] SOLID: tile-local pixel columns [x0, x1)
+  int4 *wspan;         // [n_walls] {tile-local pixel columns x0, x1 (SOLID), 1 / column groups as float bits, items}
   SWallGeom *w;        // [n_walls]
   RTBall *b;           // [n_balls]
 };
 __host__ __device__ inline size_t render_warp_smem_bytes(int n_walls, int n_balls) {
-  size_t meta = (size_t)n_walls * (sizeof(int4) + sizeof(int2) + sizeof(SWallGeom)) + (size_t)n_balls * sizeof(RTBall);
+  size_t meta = (size_t)n_walls * (sizeof(int4) + sizeof(int4) + sizeof(SWallGeom)) + (size_t)n_balls * sizeof(RTBall);
   meta = (meta + 15) & ~(size_t)15;
   return (size_t)PPB_TILE * PPB_TILE * 4 + meta;
 }
@@ -466,9 +466,9 @@ __global__ void __maxnreg__(120) render_tile_kernel(StatePtrs S, Layout L, Rende
     unsigned char *base = render_smem_raw + (size_t)warp * render_warp_smem_bytes(L.n_walls, L.n_balls);
     sm.tile = reinterpret_cast<uint32_t *>(base);
     sm.wpaint = reinterpret_cast<int4 *>(base + (size_t)PPB_TILE * PPB_TILE * 4);
-    sm.b = reinterpret_cast<RTBall *>(sm.wpaint + L.n_walls);              // 16-byte records first
-    sm.wspan = reinterpret_cast<int2 *>(sm.b + L.n_balls);
-    sm.w = reinterpret_cast<SWallGeom *>(sm.wspan + L.n_walls);            // 4-byte aligned members only
+    sm.wspan = sm.wpaint + L.n_walls;                                      // 16-byte records first
+    sm.b = reinterpret_cast<RTBall *>(sm.wspan + L.n_walls);
+    sm.w = reinterpret_cast<SWallGeom *>(sm.b + L.n_balls);                // 4-byte aligned members only
   }
   // pixels per tile row (row stride in the buffer; a band pads it to a multiple of 4) and rows per tile
   const int RS = BAND ? ((RL.W + 3) & ~3) : PPB_TILE;
@@ -541,7 +541,8 @@ __global__ void __maxnreg__(120) render_tile_kernel(StatePtrs S, Layout L, Rende
         mode = ((col >> 24) == 255u && floorf(wx0) == wx0 && floorf(wx1) == wx1) ? PPB_WM_SOLID : PPB_WM_FAST;
       const int g0 = (px0 - tx0) >> 2, g1 = (px1 - tx0 + 3) >> 2;
       sm.wpaint[lane] = make_int4(mode, (int)col, (r0 - ty0) | ((r1 - r0) << 16), g0 | ((g1 - g0) << 16));
-      sm.wspan[lane] = make_int2(px0 - tx0, px1 - tx0);
+      // the per-wall loop constants are derived here, by the wall's own lane, off the painting loop's critical path
+      sm.wspan[lane] = make_int4(px0 - tx0, px1 - tx0, __float_as_int(__frcp_rn((float)max(g1 - g0, 1))), (r1 - r0) * (g1 - g0));
       if (mode >= PPB_WM_FAST) {
         SWallGeom g;
         g.x0 = wx0; g.x1 = wx1; g.y0 = __uint_as_float(c0.z); g.y1 = __uint_as_float(c0.w);
@@ -601,12 +602,12 @@ __global__ void __maxnreg__(120) render_tile_kernel(StatePtrs S, Layout L, Rende
       const int4 h = sm.wpaint[q];
       if (h.x == PPB_WM_SKIP) continue;
       const uint32_t col = (uint32_t)h.y;
-      const int r0 = h.z & 0xffff, nrows = h.z >> 16, g0 = h.w & 0xffff, ncg = h.w >> 16;
-      const int items = nrows * ncg;
-      const float inv_ncg = __frcp_rn((float)ncg);
+      const int r0 = h.z & 0xffff, g0 = h.w & 0xffff, ncg = h.w >> 16;
+      const int4 span = sm.wspan[q];
+      const int items = span.w;
+      const float inv_ncg = __int_as_float(span.z);
       uint4 *base = reinterpret_cast<uint4 *>(sm.tile) + r0 * RS4 + g0;
       if (h.x == PPB_WM_SOLID) {
-        const int2 span = sm.wspan[q];
         const uint32_t width = (uint32_t)(span.y - span.x);
         for (int i = lane; i < items; i += 32) {
           const int r = (int)(((float)i + 0.5f) * inv_ncg);
