@@ -63,6 +63,23 @@ __global__ void __launch_bounds__(256) integrate_kernel(StatePtrs S, int n_balls
     const Hdr<T> h = reinterpret_cast<const Hdr<T> *>(S.hdr)[w];
     const T dt = (T)P.dt;
     T2 *pos = reinterpret_cast<T2 *>(S.pos);
+    T2 *vel = reinterpret_cast<T2 *>(S.vel);
+    T *tcol = reinterpret_cast<T *>(S.tcol);
+    // The state of this thread's balls is fetched together with the header, not after it: one memory round trip
+    // instead of two on the common (event-free) path; the few worlds that go to the collide kernel cost a read.
+    typedef typename Vec4<T>::type T4;
+    T4 sp4, sv4;
+    T2 stc2, sp1, sv1;
+    T stc1 = T(0);
+    if (BPT == 2) {
+      sp4 = ld4(reinterpret_cast<const T4 *>(pos + i));
+      sv4 = ld4(reinterpret_cast<const T4 *>(vel + i));
+      stc2 = *reinterpret_cast<const T2 *>(tcol + i);
+    } else {
+      sp1 = pos[i];
+      sv1 = vel[i];
+      stc1 = tcol[i];
+    }
     if (PPB_STATUS_OF(h.flags) != 0u) {
       // halted world: nothing moves any more; keep recording where it stopped
       if (traj) {
@@ -73,7 +90,12 @@ __global__ void __launch_bounds__(256) integrate_kernel(StatePtrs S, int n_balls
 #pragma unroll
         for (int j = 0; j < BPT; ++j) reinterpret_cast<T2 *>(S.snap)[i + j] = pos[i + j];
       }
-    } else if (h.step == k) {
+    } else if (h.step == k || h.step == k + 1u) {
+      // h.step == k + 1 inside this launch can only mean that the thread owning this world's header has already
+      // taken the event-free branch below and bumped it: the threads of a world sit in different warps -- even in
+      // CTAs of different waves -- when the ball count is not a power of two, and then read the header after that
+      // write.  (Before this launch every running world is at step k; the collide kernel runs after it.)
+      const bool bumped = h.step != k;
       // friction extension (0 = the reference): every velocity is scaled by s = 1 - friction*dt at the start of
       // the step (semi-implicit Euler: the step then moves with the new velocity).  A uniform scaling of all
       // velocities leaves every contact geometry unchanged and stretches every cached time of collision by
@@ -81,17 +103,13 @@ __global__ void __launch_bounds__(256) integrate_kernel(StatePtrs S, int n_balls
       const bool fric = P.friction != 0.0;
       const T fs = fric ? (T)fmax(0.0, 1.0 - P.friction * P.dt) : T(1);
       const T tmin_eff = fric ? (fs > T(0) ? h.tmin / fs : Lim<T>::inf()) : h.tmin;
-      if (h.flags == 0u && tmin_eff > dt) {
+      if (bumped || (h.flags == 0u && tmin_eff > dt)) {
         // event-free step: Dynamics.move_object for every ball (primitives.py:600-611)
         const V2<T> g = mk<T>((T)P.gx, (T)P.gy);
-        T2 *vel = reinterpret_cast<T2 *>(S.vel);
-        T *tcol = reinterpret_cast<T *>(S.tcol);
         const bool has_g = (P.gx != 0.0) || (P.gy != 0.0) || fric;
         if (BPT == 2) {
-          typedef typename Vec4<T>::type T4;
-          T4 p = ld4(reinterpret_cast<const T4 *>(pos + i));
-          T4 v = ld4(reinterpret_cast<const T4 *>(vel + i));
-          T2 tc = *reinterpret_cast<const T2 *>(tcol + i);
+          T4 p = sp4, v = sv4;
+          T2 tc = stc2;
           V2<T> p0 = mk<T>(p.x, p.y), p1 = mk<T>(p.z, p.w), v0 = mk<T>(v.x, v.y), v1 = mk<T>(v.z, v.w);
           if (fric) {
             v0 = v0 * fs; v1 = v1 * fs;
@@ -114,8 +132,8 @@ __global__ void __launch_bounds__(256) integrate_kernel(StatePtrs S, int n_balls
           if (traj) st4(reinterpret_cast<T4 *>(traj + ((long long)P.step_off * total + i) * 2), po);
           if (S.snap) st4(reinterpret_cast<T4 *>(reinterpret_cast<T2 *>(S.snap) + i), po);
         } else {
-          T2 p = pos[i], v = vel[i];
-          T tc = tcol[i];
+          T2 p = sp1, v = sv1;
+          T tc = stc1;
           V2<T> p0 = mk<T>(p.x, p.y), v0 = mk<T>(v.x, v.y);
           if (fric) {
             v0 = v0 * fs;

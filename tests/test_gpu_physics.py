@@ -164,6 +164,42 @@ def test_f64_chunking_is_invisible():
     assert np.array_equal(p1, p2) and np.array_equal(v1, v2)
     assert np.array_equal(wb1.read_events()[0], wb2.read_events()[0])
 
+@pytest.mark.parametrize("n_balls,dtype", [(3, "f32"), (5, "f32"), (6, "f32"), (7, "f64"), (12, "f32")])
+def test_ball_counts_that_are_not_powers_of_two_at_scale(n_balls, dtype):
+    """With 3, 5, 6, ... balls the threads of one world sit in different warps, and at the boundary of two CTAs in
+    different waves of the integrate grid (more CTAs than the GPU holds at once): the world's header, rewritten by
+    the thread that owns it, must not make the late threads skip their balls.  The same worlds stepped as one
+    large batch and as small batches (other CTA boundaries, a single wave) must agree bit for bit."""
+    from pyphy_engine_b200 import sampler
+    from pyphy_engine_b200.engine import WorldBatch
+    n, part, steps = 393216 // n_balls * 2, 4099, 12      # ~ 3,000 CTAs of the integrate kernel
+    kw = dict(arena=1200, mn_wlen=700, mx_wlen=1000) if n_balls > 4 else {}
+    if n_balls > 8:
+        kw = dict(arena=1600, mn_wlen=1000, mx_wlen=1400)
+    base = sampler.sample_rect_worlds(part, n_balls, seed=77, **kw)
+    reps = -(-n // part)
+    W = {k: np.concatenate([v] * reps, 0)[:n] for k, v in base.items() if k in ("wall", "pos", "vel", "rad", "mass")}
+    big = WorldBatch(n, n_balls, 4, dtype=dtype, max_substeps=256)
+    big.set_walls(W["wall"]); big.set_balls(W["pos"], W["vel"], W["rad"], W["mass"])
+    big.step(steps)
+    pb, vb = big.get_balls()
+    sb, _ = big.get_status()
+    big.close()
+    small = WorldBatch(part, n_balls, 4, dtype=dtype, max_substeps=256)
+    small.set_walls(base["wall"]); small.set_balls(base["pos"], base["vel"], base["rad"], base["mass"])
+    small.step(steps)
+    ps, vs = small.get_balls()
+    ss, _ = small.get_status()
+    small.close()
+    assert (ss == 0).mean() > 0.99
+    moved = np.abs(ps - base["pos"]).max(axis=(1, 2)) > 0
+    assert moved[ss == 0].all()                                  # every ball of every running world was advanced
+    for r in range(reps):
+        lo, hi = r * part, min((r + 1) * part, n)
+        assert np.array_equal(sb[lo:hi], ss[:hi - lo])
+        assert np.array_equal(pb[lo:hi], ps[:hi - lo]), (n_balls, r)
+        assert np.array_equal(vb[lo:hi], vs[:hi - lo])
+
 
 @pytest.mark.parametrize("n_worlds,n_balls,kw", [
     (4096, 4, {}),
