@@ -164,18 +164,22 @@ def test_f64_chunking_is_invisible():
     assert np.array_equal(p1, p2) and np.array_equal(v1, v2)
     assert np.array_equal(wb1.read_events()[0], wb2.read_events()[0])
 
-@pytest.mark.parametrize("n_balls,dtype", [(3, "f32"), (5, "f32"), (6, "f32"), (7, "f64"), (12, "f32")])
+@pytest.mark.parametrize("n_balls,dtype", [(3, "f32"), (5, "f32"), (6, "f32"), (7, "f64"), (12, "f32"),
+                                           (16, "f32"), (32, "f32"), (8, "f64")])
 def test_ball_counts_that_are_not_powers_of_two_at_scale(n_balls, dtype):
     """With 3, 5, 6, ... balls the threads of one world sit in different warps, and at the boundary of two CTAs in
     different waves of the integrate grid (more CTAs than the GPU holds at once): the world's header, rewritten by
     the thread that owns it, must not make the late threads skip their balls.  The same worlds stepped as one
-    large batch and as small batches (other CTA boundaries, a single wave) must agree bit for bit."""
+    large batch and as small batches (other CTA boundaries, a single wave) must agree bit for bit.  The 16- and
+    32-ball cases do the same for the collide kernel's warp teams, the fp64 case for the bit-exact policy."""
     from pyphy_engine_b200 import sampler
     from pyphy_engine_b200.engine import WorldBatch
-    n, part, steps = 393216 // n_balls * 2, 4099, 12      # ~ 3,000 CTAs of the integrate kernel
+    n, part, steps = 393216 // n_balls * 2, 4099, 40      # ~ 3,000 CTAs of the integrate kernel
     kw = dict(arena=1200, mn_wlen=700, mx_wlen=1000) if n_balls > 4 else {}
     if n_balls > 8:
         kw = dict(arena=1600, mn_wlen=1000, mx_wlen=1400)
+    if n_balls > 16:
+        kw = dict(arena=2400, mn_wlen=1800, mx_wlen=2200)
     base = sampler.sample_rect_worlds(part, n_balls, seed=77, **kw)
     reps = -(-n // part)
     W = {k: np.concatenate([v] * reps, 0)[:n] for k, v in base.items() if k in ("wall", "pos", "vel", "rad", "mass")}
