@@ -250,3 +250,22 @@ def test_frames_band_tiles_identical(canvas):
     for r, st in ((3, 1), (9, 2)):
         dev, ref = _render_both(wall, pos, r, canvas, st)
         assert np.array_equal(dev, ref), (canvas, r)
+
+
+@pytest.mark.parametrize("canvas", [(64, 64), (200, 96)])
+def test_frames_maximum_object_counts(canvas):
+    """PPB_MAX_WALLS walls and PPB_MAX_BALLS balls per world: the per-warp metadata is at its largest (fewest warps
+    per CTA) and every lane of a warp owns a ball."""
+    W, H = canvas
+    rs = np.random.RandomState(5)
+    nw = 4
+    wall = np.zeros((nw, 16, 4, 2), np.float64)
+    for w in range(nw):
+        for q in range(16):
+            x0, y0 = rs.randint(0, W - 8), rs.randint(0, H - 8)
+            ww, hh = rs.randint(2, 12), rs.randint(2, 12)
+            wall[w, q] = [[x0, y0], [x0 + ww, y0], [x0 + ww, y0 + hh], [x0, y0 + hh]]
+    pos = np.stack([rs.uniform(0, W, (nw, 32)), rs.uniform(0, H, (nw, 32))], -1)
+    cols = [(rs.rand(), rs.rand(), rs.rand(), 1.0) for _ in range(16)]
+    dev, ref = _render_both(wall, pos, 3, canvas, 1, wall_rgba=cols)
+    assert np.array_equal(dev, ref)
