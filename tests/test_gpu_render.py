@@ -140,13 +140,15 @@ def test_sprite_matches_oracle_sprite():
         assert np.array_equal(dev[0, 50 - off:50 + off, 50 - off:50 + off, 0].astype(np.int32), exp)
 
 
-def test_pipelined_ring_equals_serial_stepping():
+@pytest.mark.parametrize("n,nb", [(2048, 8), (40000, 3), (20000, 5)])
+def test_pipelined_ring_equals_serial_stepping(n, nb):
     """ppb_step_ring_async: render of step k overlaps the physics of step k+1 and the frames go
-    round-robin into a ring; the result must equal one-step-at-a-time serial stepping."""
+    round-robin into a ring; the result must equal one-step-at-a-time serial stepping.  The 3- and 5-ball
+    batches are large enough for the integrate grid to run in several waves next to the render kernel."""
     import torch
     from pyphy_engine_b200 import sampler
     from pyphy_engine_b200.engine import WorldBatch
-    n, nb, steps, slots = 2048, 8, 9, 3
+    steps, slots = 9, 3
     W = sampler.sample_rect_worlds(n, nb, seed=12, **sampler.scaled64_params(nb))
 
     def make():
