@@ -123,7 +123,8 @@ cudaError_t Launch<T>::render(const StatePtrs &S, const Layout &L, const RenderL
     if (L.order[k] < L.n_walls && k >= L.n_walls) walls_first = false;
   if (walls_first && (reinterpret_cast<uintptr_t>(frames) & 3u) == 0) {
     // canvases other than 64 pixels wide: tiles are bands of whole frame rows
-    const bool band = RL.W != PPB_TILE && ((RL.W + 3) & ~3) <= PPB_TILE * PPB_TILE && !getenv("PPB_NO_BAND");
+    static const bool no_band = getenv("PPB_NO_BAND") != nullptr;   // developer switch: square tiles everywhere (A/B timing)
+    const bool band = RL.W != PPB_TILE && ((RL.W + 3) & ~3) <= PPB_TILE * PPB_TILE && !no_band;
     if (band) {
       const int rh = (PPB_TILE * PPB_TILE) / ((RL.W + 3) & ~3);
       jobs = (long long)S.n_worlds * ((RL.H + rh - 1) / rh);
