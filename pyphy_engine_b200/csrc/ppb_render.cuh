@@ -558,6 +558,7 @@ __global__ void __maxnreg__(120) render_tile_kernel(StatePtrs S, Layout L, Rende
         sm.w[lane] = g;
       }
     }
+    uint32_t my_dst_sz = 0u, my_aw_ah = 0u;
     if (lane < nB) {
       const int b = lane;
       RTBall rec;
@@ -585,6 +586,23 @@ __global__ void __maxnreg__(120) render_tile_kernel(StatePtrs S, Layout L, Rende
         }
       }
       sm.b[b] = rec;
+      my_dst_sz = rec.dst_sz;
+      my_aw_ah = rec.aw_ah;
+    }
+    // Which balls are composited together with their successor (pass 2)?  Decided here by every ball's own lane:
+    // same visible geometry, small sprite, pixel boxes apart.  Bit b of pair_mask: ball b pairs with ball b + 1.
+    unsigned pair_mask;
+    {
+      const uint32_t n_dst_sz = __shfl_down_sync(0xffffffffu, my_dst_sz, 1), n_aw_ah = __shfl_down_sync(0xffffffffu, my_aw_ah, 1);
+      bool pair_ok = false;
+      if (lane + 1 < nB && my_aw_ah != 0u && n_aw_ah == my_aw_ah && (n_dst_sz >> 16) == (my_dst_sz >> 16)) {
+        const int aw = (int)(my_aw_ah & 0xffffu), ah = (int)(my_aw_ah >> 16);
+        const int dst = (int)(my_dst_sz & 0xffffu), dstn = (int)(n_dst_sz & 0xffffu);
+        const int dsty = BAND ? dst / RS : (dst >> 6), dstny = BAND ? dstn / RS : (dstn >> 6);
+        const int ddx = abs((dst - dsty * RS) - (dstn - dstny * RS)), ddy = abs(dsty - dstny);
+        pair_ok = aw * ah <= 64 && (ddx >= aw || ddy >= ah);
+      }
+      pair_mask = __ballot_sync(0xffffffffu, pair_ok);
     }
     bulk_wait_read0();   // the copy engine is done reading the tile buffer
     __syncwarp();
@@ -677,12 +695,10 @@ __global__ void __maxnreg__(120) render_tile_kernel(StatePtrs S, Layout L, Rende
         // the next ball, when it has the same visible geometry and does not touch this one's pixels, is
         // composited in the same trip: four independent load -> blend -> store chains instead of two
         // (measured: step 0.459 -> 0.421 ms; grouping up to four sprites was slower again, 0.459 ms)
-        if (b + 1 < nB) {
-          const uint4 rn = reinterpret_cast<const uint4 *>(&sm.b[b + 1])[0];
-          const uint32_t dstn = rn.y & 0xffffu;
-          const int dsty = BAND ? (int)dst / RS : (int)(dst >> 6), dstny = BAND ? (int)dstn / RS : (int)(dstn >> 6);
-          const int ddx = abs(((int)dst - dsty * RS) - ((int)dstn - dstny * RS)), ddy = abs(dsty - dstny);
-          if (rn.z == ra.z && (rn.y >> 16) == (ra.y >> 16) && (ddx >= aw || ddy >= ah)) {
+        {
+          if ((pair_mask >> b) & 1u) {
+            const uint2 rn = reinterpret_cast<const uint2 *>(&sm.b[b + 1])[0];   // tex, dst_sz of the partner
+            const uint32_t dstn = rn.y & 0xffffu;
             const uint32_t t1 = v1 ? __ldg(atlas + ra.x + sp_t1) : 0u;
             const uint32_t t2 = v2 ? __ldg(atlas + ra.x + sp_t2) : 0u;
             const uint32_t u1 = v1 ? __ldg(atlas + rn.x + sp_t1) : 0u;
