@@ -65,7 +65,7 @@ struct ppb_batch {
   size_t atlas_bytes = 0;
   uint32_t *d_fill8 = nullptr, *d_stroke8 = nullptr;
   int64_t launches = 0;
-  int32_t host_step = 0;  // mirrors *S.step_base
+  int32_t host_step = 0;  // index of the next step; every launch receives it by value
   // profiling (CUDA events around every kernel of the last ppb_step_async)
   int profiling = 0;   // bit k: CUDA events around kernel kind k (0 integrate, 1 collide, 2 render)
   std::vector<cudaEvent_t> ev_pool;
@@ -366,7 +366,6 @@ int ppb_create(const ppb_config *cfg, ppb_batch **out) {
       {&b->S.hdr, nw * 16},           {(void **)&b->S.partner, nb * 4},
       {(void **)&b->S.nev, nw * 4},   {(void **)&b->S.events, (size_t)(cfg->event_capacity > 0 ? cfg->event_capacity : 1) * sizeof(ppb_event)},
       {(void **)&b->S.counters, 8 * sizeof(unsigned long long)},
-      {(void **)&b->S.step_base, 16},
       {(void **)&b->S.list, nw * 4},
       {(void **)&b->S.list_count, 16},
   };
@@ -421,7 +420,7 @@ int ppb_destroy(ppb_batch *b) {
   }
   if (b->render_stream) cudaStreamDestroy(b->render_stream);
   void *ptrs[] = {b->S.pos, b->S.vel, b->S.aux, b->S.tcol, b->S.rm, b->S.wall, b->S.wall_rc, b->S.hdr, b->S.partner,
-                  b->S.nev, b->S.events, b->S.counters, b->S.step_base, b->S.list, b->S.list_count, b->atlas, b->d_fill8,
+                  b->S.nev, b->S.events, b->S.counters, b->S.list, b->S.list_count, b->atlas, b->d_fill8,
                   b->d_stroke8};
   for (void *p : ptrs)
     if (p) cudaFree(p);
@@ -753,11 +752,7 @@ int ppb_step_ring_async(ppb_batch *b, int32_t n_steps, void *traj_dev, uint8_t *
       if (n_rendered >= 2) CU(cudaStreamWaitEvent(st, b->ev_rend[last_slot ^ 1], 0));
     }
   }
-  if (n_steps > 0) {
-    CU(launch_advance_step_base(b->S.step_base, n_steps, st));
-    ++b->launches;
-    b->host_step += n_steps;
-  }
+  b->host_step += n_steps;   // the kernels take the step index by value (StepParams.step_abs)
   return PPB_OK;
 }
 
@@ -775,7 +770,7 @@ int ppb_scan_async(ppb_batch *b, void *stream) {
   P.step_off = 0;
   P.step_abs = b->host_step;
   P.scan_only = 1;
-  CU(is64(b) ? Launch<double>::list_pending(b->S, st) : Launch<float>::list_pending(b->S, st));
+  CU(is64(b) ? Launch<double>::list_pending(b->S, b->host_step, st) : Launch<float>::list_pending(b->S, b->host_step, st));
   CU(is64(b) ? Launch<double>::collide(b->S, b->L, P, nullptr, b->collide_grid, st)
              : Launch<float>::collide(b->S, b->L, P, nullptr, b->collide_grid, st));
   // the collide kernel zeroed the other parity's list; this one must be empty again for the next step
@@ -874,8 +869,6 @@ static int simulate_host_impl(ppb_batch *b, int32_t n_steps, float *traj_host, u
       int rc = step_once(b, s, traj_host ? b->scr_traj[buf] : nullptr, frame, st);
       if (rc) return rc;
     }
-    CU(launch_advance_step_base(b->S.step_base, cur, st));
-    ++b->launches;
     b->host_step += cur;
     const float *src32 = (const float *)b->scr_traj[buf];
     if (traj_host && is64(b)) {

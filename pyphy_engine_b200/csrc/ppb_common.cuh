@@ -137,7 +137,6 @@ struct StatePtrs {
   uint32_t *nev;      // [n_worlds] events emitted so far (sequence numbers)
   ppb_event *events;  // [event_capacity]
   unsigned long long *counters;  // [0] events produced [1] collide world-steps [2] collide loop iterations [3] rescans
-  int32_t *step_base;            // device scalar: step index of the first step of the running launch group
   int32_t *list;                 // [n_worlds] worlds the collide kernel takes this step (built by integrate)
   int32_t *list_count;           // [0..1] list lengths, [2..3] collide work tickets, indexed by step parity
   long long event_capacity;
@@ -147,8 +146,8 @@ struct StatePtrs {
 struct StepParams {
   double dt, gx, gy, friction;
   int32_t step_off;   // position of this step inside the running call (row of traj)
-  int32_t step_abs;   // index of the step this launch advances (host mirror of *step_base, + step_off): passed by
-                      // value so that no kernel starts with a dependent load of the device counter
+  int32_t step_abs;   // index of the step this launch advances (the batch counts its steps on the host): passed by
+                      // value, so no kernel starts with a dependent load of a device-side counter
   int32_t max_substeps;
   int32_t scan_only;  // collide kernel: drain the collision queue (rescan every ball) and stop; nothing moves
 };

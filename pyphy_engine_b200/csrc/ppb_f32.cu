@@ -3,10 +3,6 @@
 namespace ppb {
 template struct Launch<float>;
 
-cudaError_t launch_advance_step_base(int32_t *step_base, int32_t n, cudaStream_t st) {
-  advance_step_base_kernel<<<1, 1, 0, st>>>(step_base, n);
-  return cudaGetLastError();
-}
 cudaError_t launch_collision_flags(const float *traj, long long n_items, int n_steps, float thresh, uint8_t *flags,
                                    cudaStream_t st) {
   const long long total = n_items * (long long)(n_steps - 2);

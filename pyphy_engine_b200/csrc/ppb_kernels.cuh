@@ -582,17 +582,15 @@ collide_kernel(StatePtrs S, Layout L, StepParams P, T *traj) {
 
 // ppb_scan_async: every running world whose collision queue is non-empty goes on the collide list
 template <typename T>
-__global__ void list_pending_kernel(StatePtrs S, int step_off) {
+__global__ void list_pending_kernel(StatePtrs S, int step_abs) {
   const int w = blockIdx.x * blockDim.x + threadIdx.x;
   if (w >= S.n_worlds) return;
   const Hdr<T> h = reinterpret_cast<const Hdr<T> *>(S.hdr)[w];
-  const uint32_t k = (uint32_t)(*S.step_base + step_off);
+  const uint32_t k = (uint32_t)step_abs;
   if (PPB_STATUS_OF(h.flags) == 0u && (h.flags & PPB_FLAG_PENDING) && h.step == k)
     S.list[atomicAdd(S.list_count + (k & 1u), 1)] = w;
 }
 
-// advance the device-side step counter after a group of step launches
-static __global__ void advance_step_base_kernel(int32_t *step_base, int32_t n) { *step_base += n; }
 
 // Dynamics._include_object for a range of worlds (primitives.py:556-563): tCol_ = 0, objCol_ = None,
 // every ball queued; also used by add_all_dynamic_collision_queue (keep_cache = 1)

@@ -14,7 +14,7 @@ struct Launch {
   static cudaError_t collide(const StatePtrs &S, const Layout &L, const StepParams &P, void *traj, int grid,
                              cudaStream_t st);
   static int collide_grid(int n_worlds, int sm_count);
-  static cudaError_t list_pending(const StatePtrs &S, cudaStream_t st);
+  static cudaError_t list_pending(const StatePtrs &S, int32_t step_abs, cudaStream_t st);
   // WallRC of worlds [world0, world0 + count)
   static cudaError_t wall_cache(const StatePtrs &S, const Layout &L, const RenderLayout &RL, int world0, int count,
                                 cudaStream_t st);
@@ -32,7 +32,6 @@ struct Launch {
 
 cudaError_t launch_collision_flags(const float *traj, long long n_items, int n_steps, float thresh, uint8_t *flags,
                                    cudaStream_t st);
-cudaError_t launch_advance_step_base(int32_t *step_base, int32_t n, cudaStream_t st);
 cudaError_t launch_build_sprites(uint32_t *atlas, const RenderLayout &RL, int n_balls, const uint32_t *fill8,
                                  const uint32_t *stroke8, cudaStream_t st);
 

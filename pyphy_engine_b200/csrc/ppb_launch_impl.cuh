@@ -78,8 +78,8 @@ cudaError_t Launch<T>::collide(const StatePtrs &S, const Layout &L, const StepPa
 }
 
 template <typename T>
-cudaError_t Launch<T>::list_pending(const StatePtrs &S, cudaStream_t st) {
-  list_pending_kernel<T><<<(S.n_worlds + 255) / 256, 256, 0, st>>>(S, 0);
+cudaError_t Launch<T>::list_pending(const StatePtrs &S, int32_t step_abs, cudaStream_t st) {
+  list_pending_kernel<T><<<(S.n_worlds + 255) / 256, 256, 0, st>>>(S, step_abs);
   return cudaGetLastError();
 }
 
