@@ -248,8 +248,8 @@ class DataSaver(object):
         """
         import torch
         H, W = int(self.ySz_), int(self.xSz_)
-        # a batch is bounded by one step of frames fitting the staging buffer: larger jobs run as several batches
-        group = max(1, max_stage_bytes // (H * W * 4)) if want_frames else 1 << 20
+        # a batch is bounded by one step of frames fitting one of the two staging buffers: larger jobs run as several batches
+        group = max(1, (max_stage_bytes // 2) // (H * W * 4)) if want_frames else 1 << 20
         if len(specs) > group:
             position, frames_out = [], ([] if (want_frames and frame_sink is None) else None)
             for g0 in range(0, len(specs), group):
@@ -264,30 +264,49 @@ class DataSaver(object):
         total = int(lens.max()) if n else 0
         wb = self._batch_from_specs(specs, want_frames)
         position = [np.zeros((2 * nB, int(l)), np.float32) for l in lens]
-        frames_out = [np.zeros((int(l), H, W, 4), np.uint8) for l in lens] if (want_frames and frame_sink is None) else None
+        frames_out = [np.empty((int(l), H, W, 4), np.uint8) for l in lens] if (want_frames and frame_sink is None) else None
         per_step = n * nB * 2 * 4 + (n * H * W * 4 if want_frames else 0)
-        k = int(max(1, min(total, max_stage_bytes // max(per_step, 1))))
-        traj_host = torch.empty((k, n, nB, 2), dtype=torch.float32).pin_memory()
-        frames_host = torch.empty((k, n, H, W, 4), dtype=torch.uint8).pin_memory() if want_frames else None
+        # two page-locked staging sets: while the host scatters chunk i into the per-sequence arrays (several
+        # threads: first-touch page faults of the destination dominate that copy), the GPU already steps, draws
+        # and downloads chunk i+1 into the other set (ppb_simulate_host_async / ppb_host_sync)
+        k = int(max(1, min(total, (max_stage_bytes // 2) // max(per_step, 1))))
+        n_sets = 1 if total <= k else 2           # a job of one chunk has nothing to overlap with
+        traj_host = [torch.empty((k, n, nB, 2), dtype=torch.float32).pin_memory() for _ in range(n_sets)]
+        frames_host = [torch.empty((k, n, H, W, 4), dtype=torch.uint8).pin_memory() for _ in range(n_sets)] if want_frames else None
+        pool = ThreadPoolExecutor(max_workers=min(8, max(1, n)))
+
+        def scatter(buf, done, cur):
+            tr = traj_host[buf][:cur].numpy()
+
+            def one(s):
+                m = int(min(cur, lens[s] - done))
+                if m <= 0:
+                    return
+                position[s][:, done:done + m] = tr[:m, s].reshape(m, 2 * nB).T
+                if want_frames:
+                    fr = frames_host[buf][:m, s].numpy()
+                    if frame_sink is None:
+                        frames_out[s][done:done + m] = fr
+                    else:
+                        for i in range(m):
+                            frame_sink(s, done + i, fr[i].copy())
+            list(pool.map(one, range(n)))
+
         try:
-            done = 0
+            done, it, pending = 0, 0, None
             while done < total:
                 cur = min(k, total - done)
-                wb.simulate_host(cur, traj_host[:cur], frames_host[:cur] if want_frames else None, 1)
-                tr = traj_host[:cur].numpy()
-                for s in range(n):
-                    m = int(min(cur, lens[s] - done))
-                    if m <= 0:
-                        continue
-                    position[s][:, done:done + m] = tr[:m, s].reshape(m, 2 * nB).T
-                    if want_frames:
-                        fr = frames_host[:m, s].numpy()
-                        if frame_sink is None:
-                            frames_out[s][done:done + m] = fr
-                        else:
-                            for i in range(m):
-                                frame_sink(s, done + i, fr[i].copy())
+                buf = it & (n_sets - 1)
+                wb.simulate_host(cur, traj_host[buf][:cur], frames_host[buf][:cur] if want_frames else None, 1, wait=False)
+                if pending is not None:
+                    wb.host_sync(keep_in_flight=1)          # the previous chunk is complete on the host
+                    scatter(*pending)
+                pending = (buf, done, cur)
                 done += cur
+                it += 1
+            if pending is not None:
+                wb.host_sync()
+                scatter(*pending)
             status, at = wb.get_status()
             bad = [(s, int(status[s]), int(at[s])) for s in range(n) if status[s] != 0 and at[s] < lens[s]]
             if bad:
@@ -296,6 +315,7 @@ class DataSaver(object):
                 raise AssertionError("sequence %d: the reference raises in step %d (%s); %d sequence(s) affected"
                                      % (s, step, STATUS_NAMES.get(st, st), len(bad)))
         finally:
+            pool.shutdown(wait=True)
             wb.close()
         return position, frames_out
 
