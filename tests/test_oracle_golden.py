@@ -83,3 +83,23 @@ def test_freeze_quirk_is_reproduced():
     assert np.array_equal(tr[-1, 0], tr[-10, 0])      # ball-0 frozen
     ob, traj, ev = run_oracle(case, trig_mode=0)
     assert np.array_equal(traj, tr)
+
+
+EXTRA = load_golden("oracle_extra_golden.npz")
+
+
+@pytest.mark.parametrize("case", EXTRA, ids=[c.name for c in EXTRA])
+def test_oracle_bit_exact_with_reference_extra(case):
+    """oracle/make_golden_extra.py: 16- and 32-ball tables, mixed radii, 8-ball rhombi, regular 6/7/12-gons (one
+    with gravity) -- the shapes BASELINE.json sweeps -- stepped by the unmodified reference.  The C restatement
+    reproduces positions after every step, final velocities, events and, where the reference raises, the failure."""
+    ob, traj, ev = run_oracle(case, trig_mode=0)
+    assert ob.status[0] == case.status
+    assert np.array_equal(ev, case["events"]), "collision event sequence differs"
+    if case.status == 0:
+        assert np.array_equal(traj, case["traj"]), "trajectory is not bit-identical"
+        assert np.array_equal(ob.vel[0], case["vel_final"])
+    else:
+        k = case.status_step
+        assert ob.status_step[0] == k
+        assert np.array_equal(traj[:k], case["traj"][:k])
