@@ -12,7 +12,7 @@ is what makes "1 GPU vs N GPUs give identical per-world results" checkable.
 """
 from __future__ import annotations
 
-from typing import Dict, Optional, Sequence, Tuple
+from typing import Dict, Optional, Tuple
 
 import numpy as np
 
