@@ -97,3 +97,17 @@ def test_register_budget_of_overlapping_kernels():
     assert max(collide.values()) <= 64, collide
     assert max(render.values()) <= 120, render
     assert 384 * max(render.values()) + 2 * 128 * max(collide.values()) <= 65536
+
+
+def test_header_is_plain_c():
+    """include/pyphy_b200.h is the drop-in boundary: it must compile as C99 and as C++17 on its own (no torch /
+    CUDA types in the signatures), so that a cgo / JNI / ctypes binding can include it."""
+    import shutil
+    import subprocess
+    hdr = os.path.join(os.path.dirname(os.path.dirname(os.path.abspath(__file__))), "include", "pyphy_b200.h")
+    for cc, args in (("gcc", ["-std=c99", "-x", "c"]), ("g++", ["-std=c++17", "-x", "c++"])):
+        exe = shutil.which(cc)
+        if not exe:
+            pytest.skip("%s is not available" % cc)
+        r = subprocess.run([exe, "-Wall", "-Wextra", "-Werror", "-fsyntax-only"] + args + [hdr], capture_output=True, text=True)
+        assert r.returncode == 0, r.stderr
