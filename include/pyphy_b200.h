@@ -38,7 +38,7 @@
 extern "C" {
 #endif
 
-#define PPB_VERSION 1
+#define PPB_VERSION 2
 
 #if defined(__GNUC__)
 #define PPB_API __attribute__((visibility("default")))
@@ -139,6 +139,14 @@ PPB_API int ppb_set_walls(ppb_batch *b, int32_t world0, int32_t count, const dou
 PPB_API int ppb_set_balls(ppb_batch *b, int32_t world0, int32_t count, const double *pos, const double *vel,
                   const double *rad, const double *mass, void *stream);
 
+/* Dynamics.apply_force(name, force, forceT) for every ball of worlds [world0, world0+count)
+ * (primitives.py:580-594): `force` is [count][n_balls][2]; vel += ((0.5*forceT)*forceT) * ((1.0/mass)*force),
+ * i.e. the reference's displacement formula used as a velocity increment (quirk Q7), evaluated in fp64 in the
+ * reference's operation order.  Collision caches are NOT refreshed, exactly as in the reference: call it before the
+ * first step (DataSaver does, dataio.py:382-416) or follow it with ppb_requeue.  Empty slots are skipped. */
+PPB_API int ppb_apply_force(ppb_batch *b, int32_t world0, int32_t count, const double *force, double force_t,
+                    void *stream);
+
 /* parameters of the random rectangular tables of DataSaver(isRect=True) (dataio.py:21-27) */
 typedef struct ppb_sampler_params {
   double arena;            /* arenaSz */
@@ -238,7 +246,12 @@ PPB_API int ppb_get_collision_response(ppb_batch *b, int32_t world0, int32_t cou
 PPB_API int ppb_step_ring_async(ppb_batch *b, int32_t n_steps, void *traj_dev, uint8_t *frames_dev, int32_t ring_slots,
                         int32_t render_every, void *stream);
 
-/* World.generate_image() of the current state: [n_worlds][H][W][4] uint8, asynchronous */
+/* World.generate_image() of the current state: [n_worlds][H][W][4] uint8, asynchronous.
+ * Every call that draws frames (this one, ppb_step_async / ppb_step_ring_async with frames_dev, ppb_simulate_host*
+ * with frames_host) fails with PPB_E_STATE when some occupied ball slot has a non-integer radius or one outside the
+ * [r_min, r_max] given to ppb_set_styles: the reference builds a ball's sprite with the radius as an array shape
+ * (primitives.py:39-40), so there is no sprite such a ball could be drawn from.  The radii are measured on the device
+ * the first time frames are requested after ppb_set_balls / ppb_sample_rect_worlds (one short synchronisation). */
 PPB_API int ppb_render_async(ppb_batch *b, uint8_t *frames_dev, void *stream);
 
 /* Host-buffer convenience used by the reference-facing API (DataSaver.fetch,

@@ -311,9 +311,23 @@ typedef struct {
 } evlog_t;
 
 /* Dynamics.step, primitives.py:628-656 (+ step_object :614, resolve_collision :659) */
+static double g_friction = 0.0; /* engine extension (ppb_config.friction); 0 = the reference */
+
 static void world_step(world_t *w, int world_id, int step_idx, evlog_t *ev) {
   if (*w->status != ST_OK) return;
   int err = 0;
+  if (g_friction != 0.0) {
+    /* NOT in the reference: semi-implicit Euler friction as the engine defines it.  At the
+     * start of a step every velocity -- the cached futureVel_ included -- is scaled by s = max(0, 1 - mu*dt);
+     * a uniform scaling leaves every contact geometry unchanged and stretches every cached tCol_ by 1/s. */
+    double s = fmax(0.0, 1.0 - g_friction * w->dt);
+    for (int b = 0; b < w->n_balls; ++b) {
+      if (w->rad[b] < 0) continue;
+      w->vel[2 * b] = w->vel[2 * b] * s; w->vel[2 * b + 1] = w->vel[2 * b + 1] * s;
+      w->fvel[2 * b] = w->fvel[2 * b] * s; w->fvel[2 * b + 1] = w->fvel[2 * b + 1] * s;
+      w->tcol[b] = s > 0 ? w->tcol[b] / s : INFINITY;
+    }
+  }
   double tStep = 0;
   int iters = 0;
   for (;;) {
@@ -405,6 +419,8 @@ int64_t oracle_step_batch(int n_worlds, int n_balls, int n_walls, const int32_t 
   }
   return n_events;
 }
+
+void oracle_set_friction(double mu) { g_friction = mu; }
 
 /* single geometry helpers exported for the known-answer tests (unit_tests.py) */
 int oracle_line_intersection(const double *l1, const double *l2, double *out) {

@@ -65,7 +65,7 @@ class OracleBatch:
     """
 
     def __init__(self, wall, pos, vel, rad, mass, order=None, dt=0.01, g=(0.0, 0.0), trig_mode=0,
-                 max_substeps=0):
+                 max_substeps=0, friction=0.0):
         f8 = np.float64
         self.wall = np.ascontiguousarray(wall, f8)
         self.pos = np.ascontiguousarray(pos, f8).copy()
@@ -81,6 +81,7 @@ class OracleBatch:
         assert self.order.shape == (self.n_walls + self.n_balls,)
         self.dt, self.g, self.trig_mode = float(dt), (float(g[0]), float(g[1])), int(trig_mode)
         self.max_substeps = int(max_substeps)
+        self.friction = float(friction)     # engine extension, 0 = the reference (see billiards_oracle.c)
         nw, nb = self.n_worlds, self.n_balls
         # Dynamics._include_object, primitives.py:556-563
         self.tcol = np.zeros((nw, nb), f8)
@@ -100,6 +101,7 @@ class OracleBatch:
         n_balls, 2); events is (k, 4) int32 rows (world, step, ball, partner).
         """
         L = lib()
+        L.oracle_set_friction(ctypes.c_double(self.friction))
         traj = np.empty((n_steps, self.n_worlds, self.n_balls, 2), np.float64) if record_traj else None
         ev = np.zeros((max_events, 4), np.int32) if max_events > 0 else None
         n = L.oracle_step_batch(

@@ -76,6 +76,7 @@ SIGNATURES = {
     "ppb_destroy": (ctypes.c_int, [_vp]),
     "ppb_set_walls": (ctypes.c_int, [_vp, _i32, _i32, _dp, _vp]),
     "ppb_set_balls": (ctypes.c_int, [_vp, _i32, _i32, _dp, _dp, _dp, _dp, _vp]),
+    "ppb_apply_force": (ctypes.c_int, [_vp, _i32, _i32, _dp, ctypes.c_double, _vp]),
     "ppb_sample_rect_worlds": (ctypes.c_int, [_vp, _i32, _i32, ctypes.POINTER(SamplerParams), _ip, _vp]),
     "ppb_update_balls": (ctypes.c_int, [_vp, _i32, _i32, _dp, _dp, _vp]),
     "ppb_requeue": (ctypes.c_int, [_vp, _i32, _i32, _vp]),

@@ -89,6 +89,11 @@ struct ppb_batch {
   unsigned sim_it = 0;   // staging buffers used so far (they alternate across ppb_simulate_host* calls)
   cudaEvent_t ev_call[2] = {nullptr, nullptr};   // end of the copies of the last two ppb_simulate_host* calls
   unsigned sim_calls = 0;
+  // radii of the occupied ball slots, measured on the device the first time a frame is requested after the balls
+  // changed: {min floor(r), max ceil(r), any non-integer}
+  int32_t *d_rchk = nullptr;
+  bool radii_known = false;
+  int32_t rad_lo = 0, rad_hi = -1, rad_frac = 0;
 };
 
 namespace {
@@ -232,6 +237,33 @@ int step_once(ppb_batch *b, int step_off, void *traj, uint8_t *frame, cudaStream
   int rc = step_physics(b, step_off, traj, nullptr, st);
   if (rc) return rc;
   if (frame) return step_render(b, b->S.pos, frame, st);
+  return PPB_OK;
+}
+
+// A ball is drawn from the pre-rendered sprite of its integer radius; anything else is refused instead of being
+// dropped or truncated silently.  The measurement (one small kernel + a 12-byte read-back) runs once after the
+// balls changed, then the answer is cached.
+int check_radii(ppb_batch *b, cudaStream_t st) {
+  if (!b->radii_known) {
+    if (!b->d_rchk) CU(cudaMalloc((void **)&b->d_rchk, 4 * sizeof(int32_t)));
+    const int32_t init[4] = {0x7fffffff, -1, 0, 0};
+    int32_t got[4];
+    CU(cudaMemcpyAsync(b->d_rchk, init, sizeof init, cudaMemcpyHostToDevice, st));
+    CU(is64(b) ? Launch<double>::radius_range(b->S, b->cfg.n_balls, b->d_rchk, st)
+               : Launch<float>::radius_range(b->S, b->cfg.n_balls, b->d_rchk, st));
+    ++b->launches;
+    CU(cudaMemcpyAsync(got, b->d_rchk, sizeof got, cudaMemcpyDeviceToHost, st));
+    CU(cudaStreamSynchronize(st));
+    b->rad_lo = got[0]; b->rad_hi = got[1]; b->rad_frac = got[2];
+    b->radii_known = true;
+  }
+  if (b->rad_hi < 0) return PPB_OK;   // no ball anywhere
+  if (b->rad_frac)
+    return fail(PPB_E_STATE, "a ball radius is not an integer: the reference uses it as an array shape (get_ball_im, "
+                             "primitives.py:39-40), so only integral radii can be drawn");
+  if (b->rad_lo < b->RL.r_min || b->rad_hi > b->RL.r_max)
+    return fail(PPB_E_STATE, "ball radii span [%d, %d] but ppb_set_styles built sprites for [%d, %d] only", b->rad_lo,
+                b->rad_hi, b->RL.r_min, b->RL.r_max);
   return PPB_OK;
 }
 
@@ -421,7 +453,7 @@ int ppb_destroy(ppb_batch *b) {
   if (b->render_stream) cudaStreamDestroy(b->render_stream);
   void *ptrs[] = {b->S.pos, b->S.vel, b->S.aux, b->S.tcol, b->S.rm, b->S.wall, b->S.wall_rc, b->S.hdr, b->S.partner,
                   b->S.nev, b->S.events, b->S.counters, b->S.list, b->S.list_count, b->atlas, b->d_fill8,
-                  b->d_stroke8};
+                  b->d_stroke8, b->d_rchk};
   for (void *p : ptrs)
     if (p) cudaFree(p);
   for (cudaEvent_t e : b->ev_pool) cudaEventDestroy(e);
@@ -494,6 +526,31 @@ int ppb_set_balls(ppb_batch *b, int32_t world0, int32_t count, const double *pos
   CU(cudaMemcpyAsync((char *)b->S.rm + off * 2 * esz, sr, n * 2 * esz, cudaMemcpyHostToDevice, st));
   CU(do_reset(b, world0, count, 0, st));
   CU(cudaStreamSynchronize(st));
+  b->radii_known = false;
+  return PPB_OK;
+}
+
+int ppb_apply_force(ppb_batch *b, int32_t world0, int32_t count, const double *force, double force_t, void *stream) {
+  int rc = check_range(b, world0, count);
+  if (rc) return rc;
+  if (!force) return fail(PPB_E_INVALID, "force is null");
+  if (!(force_t == force_t)) return fail(PPB_E_INVALID, "force_t is NaN");
+  CU(cudaSetDevice(b->cfg.device));
+  cudaStream_t st = (cudaStream_t)stream;
+  const size_t n = (size_t)count * b->cfg.n_balls * 2;
+  if (n == 0) return PPB_OK;
+  if ((rc = stage_reserve(b, n * sizeof(double)))) return rc;
+  memcpy(b->stage, force, n * sizeof(double));
+  double *d_force = nullptr;
+  CU(cudaMalloc((void **)&d_force, n * sizeof(double)));
+  cudaError_t e = cudaMemcpyAsync(d_force, b->stage, n * sizeof(double), cudaMemcpyHostToDevice, st);
+  if (e == cudaSuccess)
+    e = is64(b) ? Launch<double>::apply_force(b->S, b->cfg.n_balls, world0, count, d_force, force_t, st)
+                : Launch<float>::apply_force(b->S, b->cfg.n_balls, world0, count, d_force, force_t, st);
+  ++b->launches;
+  if (e == cudaSuccess) e = cudaStreamSynchronize(st);
+  cudaFree(d_force);
+  if (e != cudaSuccess) return fail(PPB_E_CUDA, "ppb_apply_force: %s", cudaGetErrorString(e));
   return PPB_OK;
 }
 
@@ -527,6 +584,7 @@ int ppb_sample_rect_worlds(ppb_batch *b, int32_t world0, int32_t count, const pp
   CU(cudaMemcpyAsync(&nf, d_fail, sizeof nf, cudaMemcpyDeviceToHost, st));
   CU(cudaStreamSynchronize(st));
   if (n_failed) *n_failed = nf;
+  b->radii_known = false;
   return PPB_OK;
 }
 
@@ -710,6 +768,10 @@ int ppb_step_ring_async(ppb_batch *b, int32_t n_steps, void *traj_dev, uint8_t *
   }
   CU(cudaSetDevice(b->cfg.device));
   cudaStream_t st = (cudaStream_t)stream;
+  if (frames_dev) {
+    int rc = check_radii(b, st);
+    if (rc) return rc;
+  }
   const size_t frame_bytes = (size_t)b->cfg.n_worlds * b->RL.W * b->RL.H * 4;
   const int n_draws = frames_dev ? n_steps / render_every : 0;
   if (!frames_dev) {
@@ -802,6 +864,10 @@ int ppb_render_async(ppb_batch *b, uint8_t *frames_dev, void *stream) {
   CU(cudaSetDevice(b->cfg.device));
   cudaStream_t st = (cudaStream_t)stream;
   {
+    int rc = check_radii(b, st);
+    if (rc) return rc;
+  }
+  {
     Prof p(b, st, 2);
     CU(is64(b) ? Launch<double>::render(b->S, b->L, b->RL, b->atlas, frames_dev, st)
                : Launch<float>::render(b->S, b->L, b->RL, b->atlas, frames_dev, st));
@@ -817,11 +883,16 @@ static int simulate_host_impl(ppb_batch *b, int32_t n_steps, float *traj_host, u
   if (frames_host) {
     if (!b->styles_set) return fail(PPB_E_STATE, "ppb_set_styles must be called before rendering");
     if (render_every < 1) return fail(PPB_E_INVALID, "render_every must be >= 1");
+    if (b->RL.W < 1 || b->RL.H < 1) return fail(PPB_E_STATE, "batch was created without a canvas");
   } else {
     render_every = 1;
   }
   CU(cudaSetDevice(b->cfg.device));
   cudaStream_t st = (cudaStream_t)stream;
+  if (frames_host) {
+    int rc = check_radii(b, st);
+    if (rc) return rc;
+  }
   const size_t nW = (size_t)b->cfg.n_worlds, nB = (size_t)b->cfg.n_balls;
   const size_t frame_bytes = nW * b->RL.W * b->RL.H * 4;
   const size_t traj_elems = nW * nB * 2;  // per step

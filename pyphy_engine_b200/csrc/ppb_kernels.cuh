@@ -115,6 +115,15 @@ __global__ void __launch_bounds__(256) integrate_kernel(StatePtrs S, int n_balls
             v0 = v0 * fs; v1 = v1 * fs;
             tc.x = fs > T(0) ? tc.x / fs : Lim<T>::inf();
             tc.y = fs > T(0) ? tc.y / fs : Lim<T>::inf();
+            // the cached futureVel_ (dynamics.py:129) is a velocity too: it shrinks with the others, or a ball-ball
+            // contact n event-free steps after the scan would install a response too large by fs^-n
+            T4 *gaux = reinterpret_cast<T4 *>(S.aux);
+#pragma unroll
+            for (int j = 0; j < 2; ++j) {
+              T4 a = ld4(gaux + i + j);
+              a.z = a.z * fs; a.w = a.w * fs;
+              st4(gaux + i + j, a);
+            }
           }
           move_ball(p0, v0, dt, g);
           move_ball(p1, v1, dt, g);
@@ -138,6 +147,10 @@ __global__ void __launch_bounds__(256) integrate_kernel(StatePtrs S, int n_balls
           if (fric) {
             v0 = v0 * fs;
             tc = fs > T(0) ? tc / fs : Lim<T>::inf();
+            T4 *gaux = reinterpret_cast<T4 *>(S.aux);
+            T4 a = ld4(gaux + i);
+            a.z = a.z * fs; a.w = a.w * fs;
+            st4(gaux + i, a);
           }
           move_ball(p0, v0, dt, g);
           tc = tc - dt;
@@ -544,7 +557,7 @@ collide_kernel(StatePtrs S, Layout L, StepParams P, T *traj) {
       gpos[base + bi] = p;
       gvel[base + bi] = v;
       gtcol[base + bi] = tc;
-      if (rescanned) {
+      if (rescanned || (P.friction != 0.0 && !P.scan_only)) {   // friction rescaled the cached futureVel_ above
         T4 a;
         a.x = nrm.x; a.y = nrm.y; a.z = fv.x; a.w = fv.y;
         st4(gaux + base + bi, a);
@@ -618,6 +631,56 @@ __global__ void reset_cache_kernel(StatePtrs S, int n_balls, int world0, int cou
     T4 z;
     z.x = z.y = z.z = z.w = T(0);
     st4(reinterpret_cast<T4 *>(S.aux) + (long long)w * n_balls + b, z);
+  }
+}
+
+// Dynamics.apply_force for every ball of worlds [world0, world0 + count) (primitives.py:580-594):
+//   a = (1.0 / mass) * force;  deltaV = ((0.5 * forceT) * forceT) * a;  vel = vel + deltaV
+// in the reference's operation order, evaluated in fp64 whatever the batch dtype (the force array is fp64) with
+// explicitly rounded multiplies / adds, so no FMA contraction can change a bit.  Collision caches are left alone,
+// as in the reference (quirk Q7: only safe before the first step or together with ppb_requeue).
+template <typename T>
+__global__ void apply_force_kernel(StatePtrs S, int n_balls, int world0, int count, const double *force, double force_t) {
+  typedef typename Vec2<T>::type T2;
+  const long long i = (long long)blockIdx.x * blockDim.x + threadIdx.x;
+  if (i >= (long long)count * n_balls) return;
+  const long long slot = (long long)world0 * n_balls + i;
+  const T2 q = reinterpret_cast<const T2 *>(S.rm)[slot];
+  if (q.x < T(0)) return;   // empty slot
+  const double inv_m = __ddiv_rn(1.0, (double)q.y);
+  const double k = __dmul_rn(__dmul_rn(0.5, force_t), force_t);
+  T2 v = reinterpret_cast<T2 *>(S.vel)[slot];
+  v.x = (T)__dadd_rn((double)v.x, __dmul_rn(__dmul_rn(inv_m, force[2 * i]), k));
+  v.y = (T)__dadd_rn((double)v.y, __dmul_rn(__dmul_rn(inv_m, force[2 * i + 1]), k));
+  reinterpret_cast<T2 *>(S.vel)[slot] = v;
+}
+
+// Range of the radii of all occupied ball slots: out[0] = min floor(r), out[1] = max ceil(r), out[2] = 1 if some radius
+// is not an integer.  The renderer draws a ball from the pre-rendered sprite of its integer radius (get_ball_im takes
+// the radius as an array shape, primitives.py:39-40), so the API refuses to draw anything else (ppb_render_async).
+template <typename T>
+__global__ void radius_range_kernel(StatePtrs S, int n_balls, int32_t *out) {
+  typedef typename Vec2<T>::type T2;
+  const long long i = (long long)blockIdx.x * blockDim.x + threadIdx.x;
+  int lo = 0x7fffffff, hi = -1, frac = 0;
+  if (i < (long long)S.n_worlds * n_balls) {
+    const T r = reinterpret_cast<const T2 *>(S.rm)[i].x;
+    if (r >= T(0)) {
+      const double rd = (double)r;
+      lo = (int)floor(rd);
+      hi = (int)ceil(rd);
+      frac = floor(rd) != rd;
+    }
+  }
+  lo = __reduce_min_sync(0xffffffffu, lo);
+  hi = __reduce_max_sync(0xffffffffu, hi);
+  frac = __any_sync(0xffffffffu, frac);
+  if ((threadIdx.x & 31) == 0) {
+    if (hi >= 0) {
+      atomicMin(out + 0, lo);
+      atomicMax(out + 1, hi);
+    }
+    if (frac) atomicOr(out + 2, 1);
   }
 }
 

@@ -26,6 +26,11 @@ struct Launch {
                                  const SamplerParams &P, int32_t step_value, int32_t *fail_count, cudaStream_t st);
   static cudaError_t crop(const uint8_t *frames, const void *traj, long long n_frames, int n_worlds, int n_balls, int W,
                           int H, int c, int mode, uint8_t *crops, float *pos_out, cudaStream_t st);
+  // Dynamics.apply_force (primitives.py:580-594): force is a device array [count][n_balls][2] of fp64
+  static cudaError_t apply_force(const StatePtrs &S, int n_balls, int world0, int count, const double *force,
+                                 double force_t, cudaStream_t st);
+  // out[0..2] = {min floor(radius), max ceil(radius), any non-integer radius} over the occupied slots (out pre-set)
+  static cudaError_t radius_range(const StatePtrs &S, int n_balls, int32_t *out, cudaStream_t st);
   // traj (batch dtype) -> float32
   static cudaError_t traj_to_f32(const void *src, float *dst, long long n, cudaStream_t st);
 };

@@ -168,6 +168,23 @@ cudaError_t Launch<T>::reset_cache(const StatePtrs &S, int n_balls, int world0, 
 }
 
 template <typename T>
+cudaError_t Launch<T>::apply_force(const StatePtrs &S, int n_balls, int world0, int count, const double *force,
+                                   double force_t, cudaStream_t st) {
+  const long long n = (long long)count * n_balls;
+  if (n <= 0) return cudaSuccess;
+  apply_force_kernel<T><<<(unsigned)((n + 255) / 256), 256, 0, st>>>(S, n_balls, world0, count, force, force_t);
+  return cudaGetLastError();
+}
+
+template <typename T>
+cudaError_t Launch<T>::radius_range(const StatePtrs &S, int n_balls, int32_t *out, cudaStream_t st) {
+  const long long n = (long long)S.n_worlds * n_balls;
+  if (n <= 0) return cudaSuccess;
+  radius_range_kernel<T><<<(unsigned)((n + 255) / 256), 256, 0, st>>>(S, n_balls, out);
+  return cudaGetLastError();
+}
+
+template <typename T>
 __global__ void traj_to_f32_kernel(const T *src, float *dst, long long n) {
   long long i = (long long)blockIdx.x * blockDim.x + threadIdx.x;
   if (i < n) dst[i] = (float)src[i];

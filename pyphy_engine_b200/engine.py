@@ -181,6 +181,15 @@ class WorldBatch:
                 raise ValueError("expected (count, n_balls, 2)")
         check(self._lib.ppb_update_balls(self._h, world0, count, _dp(p), _dp(v), _stream_handle(stream, self.device)))
 
+    def apply_force(self, force, force_t: float, world0: int = 0, stream=None):
+        """Dynamics.apply_force for every ball of ``count`` worlds (primitives.py:580-594): ``force`` is
+        (count, n_balls, 2); vel += 0.5 * force_t**2 * force / mass, caches untouched (quirk Q7)."""
+        f = np.ascontiguousarray(force, np.float64)
+        if f.ndim != 3 or f.shape[1:] != (self.n_balls, 2):
+            raise ValueError("expected (count, n_balls, 2)")
+        check(self._lib.ppb_apply_force(self._h, world0, f.shape[0], _dp(f), float(force_t),
+                                        _stream_handle(stream, self.device)))
+
     def requeue(self, world0: int = 0, count: Optional[int] = None, stream=None):
         """Dynamics.add_all_dynamic_collision_queue (primitives.py:697-700)."""
         count = self.n_worlds - world0 if count is None else count

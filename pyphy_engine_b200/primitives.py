@@ -31,6 +31,8 @@ from __future__ import annotations
 import collections as co
 import copy
 import pickle
+import warnings
+import weakref
 
 import numpy as np
 
@@ -494,6 +496,11 @@ class World(object):
         sig = _DeviceWorld.signature(self, dt, self.dtype_, self.device_)
         if self._dev is None or self._dev.sig != sig:
             if self._dev is not None:
+                # the Dynamics that steps this world keeps the event log: fetch what the old mirror still holds
+                owner = getattr(self, "_dev_owner", None)
+                owner = owner() if owner is not None else None
+                if owner is not None:
+                    owner._drain_events()
                 self._dev.close()
             self._dev = _DeviceWorld(self, dt, g, self.dtype_, self.device_, event_capacity)
             self._dev_params = (dt, g, event_capacity)
@@ -513,6 +520,7 @@ class World(object):
     def __getstate__(self):
         d = dict(self.__dict__)
         d["_dev"] = None
+        d.pop("_dev_owner", None)
         return d
 
 
@@ -523,6 +531,7 @@ class Dynamics(object):
     """Event-driven stepper (primitives.py:535-805), executed by the collide / integrate kernels."""
 
     EVENT_CAPACITY = 1 << 16
+    EVENT_DRAIN_EVERY = 64      # steps between drains of the device event buffer (one world: << 1000 events per step)
 
     def __init__(self, world, g=0, deltaT=0.01):
         self.world_ = world
@@ -548,6 +557,7 @@ class Dynamics(object):
             w._dev.close()
             w._dev = None
         self._force_rebuild = False
+        w._dev_owner = weakref.ref(self)
         dev = w._device(self.deltaT_, self.g_, self.EVENT_CAPACITY)
         if self._requeue:
             dev.batch.requeue()
@@ -559,6 +569,9 @@ class Dynamics(object):
         if dev is None:
             return
         ev, total = dev.batch.read_events()
+        if total > len(ev):
+            warnings.warn("collision event log overflowed: %d of %d events since the last drain were kept"
+                          % (len(ev), total), RuntimeWarning)
         names = dev.wall_names + dev.ball_names
         base = getattr(dev, "step_base", 0)
         for _, step, ball, partner in ev:
@@ -605,6 +618,8 @@ class Dynamics(object):
         dev.batch.step(1)
         dev.steps += 1
         self._nsteps += 1
+        if dev.steps % self.EVENT_DRAIN_EVERY == 0:
+            self._drain_events()      # the device keeps EVENT_CAPACITY records; move them to the host log in time
         status, at = dev.batch.get_status()
         dev.pull(self.world_)
         if status[0] != 0:

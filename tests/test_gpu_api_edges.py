@@ -170,3 +170,108 @@ def test_simulate_host_async_double_buffered():
     assert np.array_equal(fb[(len(sets) - 1) & 1].numpy(), ref_f[-1])
     assert _capi.load().ppb_host_sync(wb._h, 2, None) != 0      # keep_in_flight must be 0 or 1
     wb.close()
+
+
+def _ref_apply_force(vel, mass, force, force_t):
+    """Dynamics.apply_force restated literally (primitives.py:580-594): a = (1.0/mass)*F;
+    deltaV = ((0.5*forceT)*forceT)*a; vel = vel + deltaV -- Python floats, one rounding per operation."""
+    out = np.empty_like(vel)
+    for idx in np.ndindex(vel.shape[:-1]):
+        m = float(mass[idx])
+        for c in range(2):
+            a = (1.0 / m) * float(force[idx + (c,)])
+            out[idx + (c,)] = float(vel[idx + (c,)]) + a * (0.5 * force_t * force_t)
+    return out
+
+
+@pytest.mark.parametrize("dtype", ["f64", "f32"])
+def test_apply_force_matches_the_reference_formula(dtype):
+    """ppb_apply_force (SURVEY 8b export list): bit-identical with the reference's operation order in fp64, the
+    fp64 result rounded to float in fp32 batches; empty slots and the collision caches stay untouched (Q7)."""
+    rng = np.random.RandomState(5)
+    n, nb = 257, 3
+    W = sampler.sample_rect_worlds(n, nb, seed=9, mn_ball=15, mx_ball=35)
+    rad = W["rad"].copy()
+    rad[::7, 1] = -1.0                                    # some empty slots
+    wb = WorldBatch(n, nb, 4, dtype=dtype)
+    wb.set_walls(W["wall"])
+    wb.set_balls(W["pos"], W["vel"], rad, W["mass"])
+    wb.step(3)
+    tc0, pa0 = wb.get_collision_cache()
+    _, v0 = wb.get_balls()
+    F = rng.uniform(-8e4, 8e4, (n, nb, 2))
+    wb.apply_force(F, 0.7)
+    _, v1 = wb.get_balls()
+    want = _ref_apply_force(v0, W["mass"], F, 0.7)
+    if dtype == "f32":
+        want = want.astype(np.float32).astype(np.float64)
+    occupied = rad >= 0
+    assert np.array_equal(v1[occupied], want[occupied])
+    assert np.array_equal(v1[~occupied], v0[~occupied])
+    tc1, pa1 = wb.get_collision_cache()
+    assert np.array_equal(tc0, tc1) and np.array_equal(pa0, pa1)
+    # a sub-range of worlds
+    wb.apply_force(F[10:20], 1.0, world0=10)
+    _, v2 = wb.get_balls()
+    assert np.array_equal(v2[:10], v1[:10]) and np.array_equal(v2[20:], v1[20:])
+    assert not np.array_equal(v2[10:20], v1[10:20])
+    with pytest.raises(_capi.PpbError, match="range"):
+        wb.apply_force(F, 1.0, world0=5)
+    wb.close()
+
+
+def test_apply_force_then_step_matches_datasaver_golden():
+    """DataSaver kicks every ball once before the first step (dataio.py:382-416): worlds built from the golden's
+    ball positions with zero velocity + ppb_apply_force(force, 1.0) step exactly like the recorded reference run."""
+    from conftest import load_golden
+    for case in [c for c in load_golden("physics64_golden.npz")][:6]:
+        nB = case["pos0"].shape[0]
+        wb = WorldBatch(1, nB, 4, dtype="f64", event_capacity=1 << 16)
+        wb.set_walls(case["wall"][None])
+        wb.set_balls(case["ball_pos"][None], np.zeros((1, nB, 2)), case["rad"][None], case["mass"][None])
+        wb.apply_force(case["force"][None], 1.0)
+        _, v = wb.get_balls()
+        assert np.array_equal(v[0], case["vel0"]), case.name
+        traj, _ = wb.step(40, record_traj=True)
+        assert np.max(np.abs(traj.cpu().numpy()[:, 0] - case["traj"][:40])) < 1e-6
+        wb.close()
+
+
+def test_frames_refuse_radii_without_a_sprite():
+    """A radius outside [r_min, r_max] of ppb_set_styles, or a non-integer one, has no pre-rendered sprite
+    (get_ball_im uses the radius as an array shape, primitives.py:39-40): every call that draws frames fails
+    with PPB_E_STATE instead of silently dropping or truncating the ball."""
+    import torch
+    W = sampler.sample_rect_worlds(64, 2, seed=4, **sampler.scaled64_params(2))
+    style = ([(1, (.5, .5, .5, 1), (0, 0, 0, 1))] * 2, [(0, (1, 0, 0, 1))] * 4)
+    wb = WorldBatch(64, 2, 4, dtype="f32", canvas=(64, 64))
+    wb.set_walls(W["wall"])
+    wb.set_balls(W["pos"], W["vel"], W["rad"], W["mass"])
+    wb.set_styles(*style, 4, 6)                                    # radii are 3
+    with pytest.raises(_capi.PpbError, match="sprites for"):
+        wb.render()
+    with pytest.raises(_capi.PpbError, match="sprites for"):
+        wb.step(2, render_every=1)
+    host = torch.empty((1, 64, 64, 64, 4), dtype=torch.uint8).pin_memory()
+    with pytest.raises(_capi.PpbError, match="sprites for"):
+        wb.simulate_host(1, None, host, 1)
+    wb.step(2)                                                     # physics alone is unaffected
+    wb.set_styles(*style, 3, 3)
+    wb.render()                                                    # now fine
+    rad = W["rad"].copy()
+    rad[5, 1] = 3.5
+    wb.set_balls(W["pos"], W["vel"], rad, W["mass"])
+    with pytest.raises(_capi.PpbError, match="not an integer"):
+        wb.render()
+    rad[5, 1] = -1.0                                               # an empty slot is not a radius
+    wb.set_balls(W["pos"], W["vel"], rad, W["mass"])
+    wb.render()
+    wb.close()
+    # no canvas: ppb_simulate_host refuses frames like ppb_step_ring_async does
+    wn = WorldBatch(64, 2, 4, dtype="f32")
+    wn.set_walls(W["wall"])
+    wn.set_balls(W["pos"], W["vel"], W["rad"], W["mass"])
+    wn.set_styles(*style, 3, 3)
+    with pytest.raises(_capi.PpbError, match="canvas"):
+        wn.simulate_host(1, None, host, 1)
+    wn.close()

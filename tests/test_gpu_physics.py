@@ -18,23 +18,32 @@ pytestmark = pytest.mark.gpu
 
 PHYS = load_golden("physics_golden.npz")
 FAIL = load_golden("failure_golden.npz")
+P64 = load_golden("physics64_golden.npz")     # the 64-px tables bench.py runs, stepped by the reference
 
 # fp32 tolerance.  A billiards trajectory is a sequence of discrete decisions (which contact
 # comes next); fp32 and fp64 runs agree to rounding level while they take the same decisions
-# and are unrelated afterwards.  Two things are therefore asserted over FP32_HORIZON steps:
+# and are unrelated afterwards.  Three things are therefore asserted over FP32_HORIZON steps,
+# per table configuration (FP32_BAR below; the measured values are quoted in DESIGN.md section 4):
 #  (1) positions: on the prefix of each world in which the fp32 engine and the fp64 oracle
 #      produced the same collision events, the per-world maximum position error has a median
-#      below FP32_MED px and is below FP32_ABS px for 99% of the worlds;
-#  (2) decisions: at most FP32_MAX_DIVERGED of the worlds take a different decision inside
-#      the horizon.  Most of those are worlds in which the fp64 reference itself hits its
-#      freeze quirk (a re-contact whose time of impact evaluates to exactly 0,
-#      primitives.py:647-650: 1.4% of 4-ball worlds within 60 steps, 6.4% within 300) -- that
-#      outcome hinges on the last bit of the fp64 trig evaluation, so no fp32 code can follow
-#      it; the fp32 engine keeps simulating such worlds.
+#      below `med` px and is below `abs99` px for 99% of the worlds;
+#  (2) decisions: the worlds that take a different decision inside the horizon are of two kinds.
+#      "Frozen" ones, in which the fp64 reference itself hits its freeze quirk (a re-contact whose
+#      time of impact evaluates to exactly 0, primitives.py:647-650) -- that outcome hinges on the
+#      last bit of the fp64 trig evaluation, no fp32 code can follow it, and the fp32 engine keeps
+#      simulating such worlds; and the rest, where fp32 rounding flipped a genuine decision (a graze,
+#      two contacts inside one step).  The second kind is bounded by `flipped`; the first kind is
+#      the reference's property (its fraction is printed, not bounded);
+#  (3) attribution: when a configuration has a sizeable diverged set (> 1 %), at least half of it is
+#      of the frozen kind.
 FP32_HORIZON = 60
-FP32_ABS = 0.1
-FP32_MED = 5e-3
-FP32_MAX_DIVERGED = {4: 0.03, 8: 0.06}
+FP32_BAR = {
+    # name: (abs99 px, med px, max fraction of non-frozen worlds with a flipped decision)
+    "native4": dict(abs99=0.1, med=5e-3, flipped=0.02),
+    "native8": dict(abs99=0.1, med=5e-3, flipped=0.03),
+    "scaled64_4": dict(abs99=0.02, med=1e-3, flipped=0.02),
+    "scaled64_8": dict(abs99=0.02, med=1e-3, flipped=0.04),
+}
 
 
 def _first_divergence(ev_a, ev_b, n_worlds, horizon):
@@ -71,7 +80,7 @@ def _oracle(case, trig_mode=1, n_steps=None):
     return ob, traj[:, 0], ev[:, 1:]
 
 
-@pytest.mark.parametrize("case", PHYS + FAIL, ids=[c.name for c in PHYS + FAIL])
+@pytest.mark.parametrize("case", PHYS + FAIL + P64, ids=[c.name for c in PHYS + FAIL + P64])
 def test_f64_bit_exact_with_oracle(case):
     wb = _batch(case, "f64")
     traj, _ = wb.step(case.n_steps, record_traj=True)
@@ -103,6 +112,22 @@ def test_f64_events_match_reference(case):
     ev, _ = wb.read_events()
     assert np.array_equal(ev[:, 1:], case["events"])
     assert np.max(np.abs(traj.cpu().numpy()[:, 0] - case["traj"])) < 1e-6
+
+
+@pytest.mark.parametrize("case", P64, ids=[c.name for c in P64])
+def test_f64_events_match_reference_64px(case):
+    """The benchmark's tables (64-px arena, r = 3, 4 and 8 balls; oracle/make_golden_64.py) stepped by the
+    UNMODIFIED reference for 200 steps: identical collision events over the whole horizon, except in the three
+    worlds where the portable trig's last bit flips a ~1e-15 re-contact (tests/test_oracle_golden.py names them
+    and the step; the CPU oracle shows the same), and positions within 1e-6 px over the first 40 steps."""
+    from test_oracle_golden import PORTABLE_TRIG_DIVERGES_64
+    wb = _batch(case, "f64")
+    traj, _ = wb.step(case.n_steps, record_traj=True)
+    ev, _ = wb.read_events()
+    ev, ref = ev[:, 1:], case["events"]
+    k = PORTABLE_TRIG_DIVERGES_64.get(case.name, case.n_steps)
+    assert np.array_equal(ev[ev[:, 0] < k], ref[ref[:, 0] < k])
+    assert np.max(np.abs(traj.cpu().numpy()[:40, 0] - case["traj"][:40])) < 1e-6
 
 
 @pytest.mark.parametrize("case", FAIL, ids=[c.name for c in FAIL])
@@ -205,11 +230,18 @@ def test_ball_counts_that_are_not_powers_of_two_at_scale(n_balls, dtype):
         assert np.array_equal(vb[lo:hi], vs[:hi - lo])
 
 
-@pytest.mark.parametrize("n_worlds,n_balls,kw", [
-    (4096, 4, {}),
-    (2048, 8, dict(arena=1200, mn_wlen=700, mx_wlen=1000)),
-])
-def test_f32_trajectories_within_tolerance(n_worlds, n_balls, kw):
+def _fp32_configs():
+    from pyphy_engine_b200 import sampler
+    return [("native4", 4096, 4, {}),
+            ("native8", 2048, 8, dict(arena=1200, mn_wlen=700, mx_wlen=1000)),
+            ("scaled64_4", 4096, 4, sampler.scaled64_params(4)),      # BASELINE config 3's tables at 64 px
+            ("scaled64_8", 4096, 8, sampler.scaled64_params(8))]      # the tables bench.py steps (config 4)
+
+
+@pytest.mark.parametrize("name", ["native4", "native8", "scaled64_4", "scaled64_8"])
+def test_f32_trajectories_within_tolerance(name):
+    _, n_worlds, n_balls, kw = [c for c in _fp32_configs() if c[0] == name][0]
+    bar = FP32_BAR[name]
     H = FP32_HORIZON
     W, wb, ob = _random_batch(n_worlds, n_balls, 11, "f32", **kw)
     traj, _ = wb.step(H, record_traj=True)
@@ -223,15 +255,18 @@ def test_f32_trajectories_within_tolerance(n_worlds, n_balls, kw):
     same = np.arange(H)[:, None] < div[None, :]                         # steps before the first different decision
     err = np.where(same, err_t, 0.0).max(axis=0)
     ok = (status == 0) & (ob.status == 0)
-    print("fp32 per-world max error on decision-identical prefixes, p50/p90/p99/p99.9 (px):",
-          np.percentile(err[ok], [50, 90, 99, 99.9]), " worlds with a different decision within %d steps: %.4f"
-          % (H, diverged.mean()))
-    assert np.median(err[ok]) < FP32_MED
-    assert np.mean(err[ok] < FP32_ABS) > 0.99, np.mean(err[ok] < FP32_ABS)
-    assert diverged.mean() < FP32_MAX_DIVERGED[n_balls], diverged.mean()
-    # the reference's freeze quirk accounts for most of the diverged worlds
-    frozen = ob.tcol.min(axis=1) <= 0
-    assert (frozen & diverged).sum() >= 0.5 * frozen.sum()
+    # the reference's freeze quirk (or an assertion it raised): the fp64 world stopped, the fp32 one goes on
+    frozen = (ob.tcol.min(axis=1) <= 0) | (ob.status != 0)
+    flipped = diverged & ~frozen
+    print("fp32 %s: per-world max error on decision-identical prefixes p50/p90/p99/p99.9 (px): %s; within %d steps "
+          "diverged %.4f = frozen %.4f + flipped %.4f; frozen worlds %.4f; events/world-step %.3f"
+          % (name, np.percentile(err[ok], [50, 90, 99, 99.9]), H, diverged.mean(), (diverged & frozen).mean(),
+             flipped.mean(), frozen.mean(), len(oev) / (n_worlds * H)))
+    assert np.median(err[ok]) < bar["med"]
+    assert np.mean(err[ok] < bar["abs99"]) > 0.99, np.mean(err[ok] < bar["abs99"])
+    assert flipped.mean() < bar["flipped"], flipped.mean()
+    if diverged.mean() > 0.01:
+        assert (frozen & diverged).sum() >= 0.5 * diverged.sum(), ((frozen & diverged).sum(), diverged.sum())
 
 
 def test_f32_event_counts_statistically_match():
@@ -324,18 +359,57 @@ def test_friction_extension():
     wb.step(150)
     assert np.array_equal(wb.get_balls()[0], p0)
     wb.close()
-    # multi-ball worlds: kinetic energy never grows beyond the reference's own drift and the worlds keep running
-    Wm = sampler.sample_rect_worlds(2048, 4, seed=32)
-    ke = []
-    for fr in (0.0, 5.0):
-        wb = WorldBatch(2048, 4, 4, dtype="f32", friction=fr, max_substeps=256)
-        wb.set_walls(Wm["wall"]); wb.set_balls(Wm["pos"], Wm["vel"], Wm["rad"], Wm["mass"])
-        wb.step(200)
-        _, v = wb.get_balls()
-        ok = wb.get_status()[0] == 0
-        ke.append((0.5 * Wm["mass"] * (v ** 2).sum(-1)).sum(-1)[ok].mean())
-        assert ok.mean() > 0.98
-        wb.close()
-    assert ke[1] < 0.2 * ke[0]            # (1 - 0.05)^400 ~ 1e-9 of the energy without collisions' re-pumping
+    # two-ball worlds: every ball-ball response is exact (one candidate partner, so the reference's futureVel_
+    # overwrite quirk Q1 cannot pick a wrong one) and elastic, walls preserve |v|, hence the kinetic energy after
+    # n steps is KE0 * s^(2n) -- to rounding.  A cached futureVel_ that missed the scaling of event-free steps
+    # would install too large a velocity at the next ball-ball contact and break this.
+    W2 = sampler.sample_rect_worlds(2048, 2, seed=33, mn_force=6e4, mx_force=8e4)
+    wb = WorldBatch(2048, 2, 4, dtype="f64", friction=mu, event_capacity=1 << 20, max_substeps=4096)
+    wb.set_walls(W2["wall"]); wb.set_balls(W2["pos"], W2["vel"], W2["rad"], W2["mass"])
+    wb.step(200)
+    _, v = wb.get_balls()
+    ev, _ = wb.read_events()
+    ok = wb.get_status()[0] == 0
+    assert ok.mean() > 0.99
+    assert (ev[:, 3] >= 4).sum() > 500                          # plenty of ball-ball contacts happened
+    ke0 = (0.5 * W2["mass"] * (W2["vel"] ** 2).sum(-1)).sum(-1)
+    ke1 = (0.5 * W2["mass"] * (v ** 2).sum(-1)).sum(-1)
+    assert np.allclose(ke1[ok], ke0[ok] * s ** 400, rtol=1e-7), np.max(np.abs(ke1[ok] / (ke0[ok] * s ** 400) - 1))
+    wb.close()
+
+
+@pytest.mark.parametrize("n_balls,mu", [(4, 2.0), (8, 0.5), (1, 5.0)])
+def test_friction_bit_exact_with_oracle(n_balls, mu):
+    """The friction rule is an engine extension; oracle/billiards_oracle.c states the same rule (scale vel, the cached
+    futureVel_ and 1/tCol_ by s at the start of a step), so the fp64 kernels must match it bit for bit -- positions
+    after every step, events, final velocities and caches -- on multi-ball worlds with ball-ball contacts."""
+    from pyphy_engine_b200 import sampler
+    from pyphy_engine_b200.engine import WorldBatch
+    n, steps = 512, 150
+    kw = dict(arena=1200, mn_wlen=700, mx_wlen=1000) if n_balls > 4 else {}
+    W = sampler.sample_rect_worlds(n, n_balls, seed=40 + n_balls, **kw)
+    wb = WorldBatch(n, n_balls, 4, dtype="f64", friction=mu, event_capacity=1 << 21, max_substeps=4096)
+    wb.set_walls(W["wall"]); wb.set_balls(W["pos"], W["vel"], W["rad"], W["mass"])
+    traj, _ = wb.step(steps, record_traj=True)
+    traj = traj.cpu().numpy()
+    ob = oracle.OracleBatch(W["wall"], W["pos"], W["vel"], W["rad"], W["mass"], trig_mode=1, max_substeps=4096,
+                            friction=mu)
+    otraj, oev = ob.step(steps, record_traj=True, max_events=1 << 21)
+    status, _ = wb.get_status()
+    assert np.array_equal(status, ob.status)
+    alive = ob.status == 0
+    assert alive.mean() > 0.9
+    assert np.array_equal(traj[:, alive], otraj[:, alive])
+    ev, _ = wb.read_events()
+    assert np.array_equal(ev, oev)
+    pos, vel = wb.get_balls()
+    assert np.array_equal(vel[alive], ob.vel[alive])
+    _, fv = wb.get_collision_response()
+    assert np.array_equal(fv[alive], ob.fvel[alive])
+    wb.close()
+
+
+def test_friction_rejects_negative():
+    from pyphy_engine_b200.engine import WorldBatch
     with pytest.raises(Exception):
         WorldBatch(4, 1, 4, friction=-1.0)
