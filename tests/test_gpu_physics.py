@@ -38,11 +38,17 @@ P64 = load_golden("physics64_golden.npz")     # the 64-px tables bench.py runs, 
 #      of the frozen kind.
 FP32_HORIZON = 60
 FP32_BAR = {
-    # name: (abs99 px, med px, max fraction of non-frozen worlds with a flipped decision)
-    "native4": dict(abs99=0.1, med=5e-3, flipped=0.02),
-    "native8": dict(abs99=0.1, med=5e-3, flipped=0.03),
-    "scaled64_4": dict(abs99=0.02, med=1e-3, flipped=0.02),
-    "scaled64_8": dict(abs99=0.02, med=1e-3, flipped=0.04),
+    # name: abs99 px, med px, max fraction of non-frozen worlds with a flipped decision.  Measured on B200 (round 2,
+    # 60 steps, seed 11): p50 / p99 error and diverged = frozen + flipped fractions
+    #   native4    1.0e-3 / 5.1e-2 px   1.39 % = 1.29 % + 0.10 %      (arena 700, r = 25, 4096 worlds)
+    #   native8    1.7e-3 / 4.8e-2 px   0.88 % = 0.78 % + 0.10 %      (arena 1200, r = 25, 2048 worlds)
+    #   scaled64_4 8.8e-5 / 2.4e-3 px   1.88 % = 1.78 % + 0.10 %      (arena 64, r = 3, 4096 worlds)
+    #   scaled64_8 1.9e-4 / 2.0e-2 px  11.13 % = 10.45 % + 0.68 %     (arena 64, r = 3, 4096 worlds: the bench tables;
+    #              the reference itself freezes one 8-ball world in ten within 60 steps at this density)
+    "native4": dict(abs99=0.1, med=5e-3, flipped=0.004),
+    "native8": dict(abs99=0.1, med=5e-3, flipped=0.004),
+    "scaled64_4": dict(abs99=0.01, med=5e-4, flipped=0.004),
+    "scaled64_8": dict(abs99=0.05, med=1e-3, flipped=0.02),
 }
 
 
