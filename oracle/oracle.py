@@ -13,7 +13,8 @@ import numpy as np
 
 HERE = os.path.dirname(os.path.abspath(__file__))
 SO_PATH = os.path.join(HERE, "_oracle.so")
-SOURCES = [os.path.join(HERE, "billiards_oracle.c"), os.path.join(HERE, "render_oracle.c")]
+SOURCES = [os.path.join(HERE, "billiards_oracle.c"), os.path.join(HERE, "render_oracle.c"),
+           os.path.join(HERE, "cairo_oracle.c")]
 
 _c_dp = ctypes.POINTER(ctypes.c_double)
 _c_ip = ctypes.POINTER(ctypes.c_int32)
@@ -44,6 +45,7 @@ def lib():
         _lib.oracle_trig.argtypes = [ctypes.c_int, ctypes.c_double, ctypes.c_int]
         _lib.oracle_disc_box_area.restype = ctypes.c_double
         _lib.oracle_quad_pixel_area.restype = ctypes.c_double
+        _lib.cairo_arc_segments_needed.argtypes = [ctypes.c_double, ctypes.c_double, ctypes.c_double]
     return _lib
 
 
@@ -124,13 +126,20 @@ class OracleBatch:
 
 
 def render_frames(wall, pos, rad, canvas, order=None, wall_kind=None, wall_rgba=None, s_thick=2,
-                  fill=(0.5, 0.5, 0.5, 1.0), stroke=(0.0, 0.0, 0.0, 1.0), n_threads=1):
-    """Restated ``World.generate_image`` (render_oracle.c) -> (n_worlds, H, W, 4) uint8.
+                  fill=(0.5, 0.5, 0.5, 1.0), stroke=(0.0, 0.0, 0.0, 1.0), n_threads=1, model="cairo",
+                  rotated_walls="cairo"):
+    """Restated ``World.generate_image`` -> (n_worlds, H, W, 4) uint8.
 
+    model "cairo": cairo_oracle.c, the published cairo pipeline (arc -> Beziers -> flattening -> tor scan
+    converter -> span compositing); model "area": render_oracle.c, exact shape-pixel areas (kept to measure the
+    difference between the two).  rotated_walls "area" (with model "cairo"): non-rectilinear wall quads are drawn as
+    the engine draws them -- solid colour through the exact pixel-quad area -- everything else the cairo way.
     wall (n_worlds, n_walls, 4, 2); pos (n_worlds, n_balls, 2); rad (n_worlds, n_balls);
     wall_rgba (n_walls, 4) default red; fill / stroke / s_thick per ball slot or shared.
     """
     L = lib()
+    fn = {"cairo": L.cairo_render_frames, "area": L.oracle_render_frames}[model]
+    ctypes.c_int.in_dll(L, "cairo_rotated_wall_model").value = {"cairo": 0, "area": 1}[rotated_walls]
     wall = np.ascontiguousarray(wall, np.float64)
     pos = np.ascontiguousarray(pos, np.float64)
     nw, nb = pos.shape[:2]
@@ -147,24 +156,73 @@ def render_frames(wall, pos, rad, canvas, order=None, wall_kind=None, wall_rgba=
     sk = np.ascontiguousarray(np.broadcast_to(np.asarray(stroke, np.float32), (nb, 4)), np.float32)
     out = np.empty((nw, H, W, 4), np.uint8)
     fp = ctypes.POINTER(ctypes.c_float)
-    L.oracle_render_frames(ctypes.c_int(nw), ctypes.c_int(nb), ctypes.c_int(nwl), _ip(order), _dp(wall),
-                           _ip(wall_kind), wall_rgba.ctypes.data_as(fp), _dp(pos), _dp(rad), _ip(st),
-                           fl.ctypes.data_as(fp), sk.ctypes.data_as(fp), ctypes.c_int(W), ctypes.c_int(H),
-                           out.ctypes.data_as(ctypes.POINTER(ctypes.c_uint8)), ctypes.c_int(n_threads))
+    fn(ctypes.c_int(nw), ctypes.c_int(nb), ctypes.c_int(nwl), _ip(order), _dp(wall),
+       _ip(wall_kind), wall_rgba.ctypes.data_as(fp), _dp(pos), _dp(rad), _ip(st),
+       fl.ctypes.data_as(fp), sk.ctypes.data_as(fp), ctypes.c_int(W), ctypes.c_int(H),
+       out.ctypes.data_as(ctypes.POINTER(ctypes.c_uint8)), ctypes.c_int(n_threads))
+    ctypes.c_int.in_dll(L, "cairo_rotated_wall_model").value = 0
     return out
 
 
-def ball_sprite(r, s_thick=2, fill=(0.5, 0.5, 0.5, 1.0), stroke=(0.0, 0.0, 0.0, 1.0)):
+def ball_sprite(r, s_thick=2, fill=(0.5, 0.5, 0.5, 1.0), stroke=(0.0, 0.0, 0.0, 1.0), model="cairo"):
     """get_ball_im restated: (sz, sz, 4) premultiplied uint8."""
     L = lib()
+    fn = {"cairo": L.cairo_ball_sprite, "area": L.oracle_ball_sprite}[model]
     sz = 2 * (int(r) + int(s_thick))
     out = np.zeros((sz, sz, 4), np.uint8)
     fl = np.asarray(fill, np.float32)
     sk = np.asarray(stroke, np.float32)
     fp = ctypes.POINTER(ctypes.c_float)
-    L.oracle_ball_sprite(ctypes.c_int(int(r)), ctypes.c_int(int(s_thick)), fl.ctypes.data_as(fp),
-                         sk.ctypes.data_as(fp), out.ctypes.data_as(ctypes.POINTER(ctypes.c_uint8)))
+    fn(ctypes.c_int(int(r)), ctypes.c_int(int(s_thick)), fl.ctypes.data_as(fp),
+       sk.ctypes.data_as(fp), out.ctypes.data_as(ctypes.POINTER(ctypes.c_uint8)))
     return out
+
+
+_u8p = ctypes.POINTER(ctypes.c_uint8)
+
+
+def cairo_disc_mask(cx, cy, r, w, h):
+    """a8 coverage of ``arc(cx, cy, r, 0, 2 pi); fill`` on a (h, w) surface (cairo_oracle.c)."""
+    out = np.zeros((h, w), np.uint8)
+    lib().cairo_disc_mask(ctypes.c_double(cx), ctypes.c_double(cy), ctypes.c_double(r), ctypes.c_int(w),
+                          ctypes.c_int(h), out.ctypes.data_as(_u8p))
+    return out
+
+
+def cairo_ring_mask(cx, cy, r, line_width, w, h):
+    """a8 coverage of ``arc(...); set_line_width(line_width); stroke``; also returns the cusp count (0)."""
+    out = np.zeros((h, w), np.uint8)
+    c = lib().cairo_ring_mask(ctypes.c_double(cx), ctypes.c_double(cy), ctypes.c_double(r),
+                              ctypes.c_double(line_width), ctypes.c_int(w), ctypes.c_int(h), out.ctypes.data_as(_u8p))
+    return out, int(c)
+
+
+def cairo_quad_mask(quad, w, h):
+    """a8 coverage of the filled quad (4 x (x, y)) on a (h, w) surface."""
+    q = np.ascontiguousarray(quad, np.float64)
+    out = np.zeros((h, w), np.uint8)
+    lib().cairo_quad_mask(_dp(q), ctypes.c_int(w), ctypes.c_int(h), out.ctypes.data_as(_u8p))
+    return out
+
+
+def cairo_circle_flatten(cx, cy, r):
+    """Vertices (24.8 fixed point, as integers) of the polygon cairo fills for a full-circle arc."""
+    xy = np.zeros((4096, 2), np.int32)
+    n = lib().cairo_circle_flatten(ctypes.c_double(cx), ctypes.c_double(cy), ctypes.c_double(r), ctypes.c_int(4096),
+                                   _ip(xy))
+    return xy[:n]
+
+
+def cairo_block_sprite(verts, rgba=(1.0, 0.0, 0.0, 1.0)):
+    """get_block_im for the wall with world-space vertices ``verts`` (4, 2): (h, w, 4) premultiplied uint8."""
+    v = np.ascontiguousarray(verts, np.float64)
+    col = np.asarray(rgba, np.float32)
+    wh = np.zeros(2, np.int32)
+    buf = np.zeros((2048, 2048, 4), np.uint8)
+    lib().cairo_block_sprite(_dp(v), col.ctypes.data_as(ctypes.POINTER(ctypes.c_float)), ctypes.c_int(2048),
+                             ctypes.c_int(2048), _ip(wh), buf.ctypes.data_as(_u8p))
+    w, h = int(wh[0]), int(wh[1])
+    return buf.reshape(-1)[: w * h * 4].reshape(h, w, 4).copy()
 
 
 def disc_box_area(R, x0, x1, y0, y1):

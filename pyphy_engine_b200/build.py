@@ -22,6 +22,7 @@ COMMON = ["-O3", "-lineinfo", "-std=c++17", "-Xcompiler", "-fPIC", "-Xcompiler",
 UNITS = [
     ("ppb_f32.cu", ["-prec-div=false", "-prec-sqrt=false"]),
     ("ppb_f64.cu", ["-fmad=false"]),
+    ("ppb_cairo.cu", ["-fmad=false"]),
     ("ppb_api.cu", []),
 ]
 

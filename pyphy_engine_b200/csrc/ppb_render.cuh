@@ -10,9 +10,9 @@
 //   * wall: solid fColor through an antialiased mask = exact area of (wall quad ∩ pixel),
 //     clipped to the integer-placed sprite rectangle the reference pastes (primitives.py:242-245,
 //     310-312); 8-bit mask m = floor(255*area + 0.5);
-//   * ball: pre-rendered sprite of side 2*(r+sThick) (ring of sColor between r-sThick/2 and
-//     r+sThick/2, then the fColor disc of radius r, both antialiased with exact pixel-area
-//     coverage), pasted with its centre at the integer-rounded ball position (round half away
+//   * ball: pre-rendered sprite of side 2*(r+sThick) (ring of sColor of width sThick centred on radius r, then
+//     the fColor disc of radius r, rasterised the way cairo's image backend does it -- csrc/ppb_cairo.cu),
+//     pasted with its centre at the integer-rounded ball position (round half away
 //     from zero, geometry.py:25-29, primitives.py:428) and clipped to the canvas.
 //
 // One CTA rasterises one 64x64 tile of one world's canvas; each thread owns runs of 4 pixels
@@ -59,91 +59,7 @@ __host__ __device__ inline uint32_t premul_rgba8(const float c[4]) {
          (color_to_u8(a) << 24);
 }
 
-// ---- exact area of (disc of radius R centred at the origin) ∩ [x0,x1]x[y0,y1] ----
-__device__ inline double circ_H(double x, double R) {  // antiderivative of sqrt(R^2 - x^2)
-  double q = R * R - x * x;
-  q = q > 0 ? q : 0;
-  double s = x / R;
-  s = s > 1 ? 1 : (s < -1 ? -1 : s);
-  return 0.5 * (x * sqrt(q) + R * R * asin(s));
-}
-__device__ inline double disc_box_area(double R, double x0, double x1, double y0, double y1) {
-  if (!(R > 0)) return 0.0;
-  // clip the x range to the disc
-  double a = x0 > -R ? x0 : -R, b = x1 < R ? x1 : R;
-  if (!(a < b)) return 0.0;
-  // breakpoints where the chord end +-h(x) crosses y0 or y1
-  double bp[6];
-  int n = 0;
-  bp[n++] = a;
-  const double ys[2] = {y0, y1};
-  double cand[4];
-  int nc = 0;
-  for (int i = 0; i < 2; ++i) {
-    double q = R * R - ys[i] * ys[i];
-    if (q > 0) {
-      double s = sqrt(q);
-      cand[nc++] = -s;
-      cand[nc++] = s;
-    }
-  }
-  // insertion sort of the candidates inside (a, b)
-  for (int i = 0; i < nc; ++i)
-    for (int j = i + 1; j < nc; ++j)
-      if (cand[j] < cand[i]) {
-        double t = cand[i];
-        cand[i] = cand[j];
-        cand[j] = t;
-      }
-  for (int i = 0; i < nc; ++i)
-    if (cand[i] > bp[n - 1] && cand[i] < b) bp[n++] = cand[i];
-  bp[n++] = b;
-  double area = 0.0;
-  for (int i = 0; i + 1 < n; ++i) {
-    const double u = bp[i], v = bp[i + 1];
-    const double xm = 0.5 * (u + v);
-    double q = R * R - xm * xm;
-    const double h = sqrt(q > 0 ? q : 0);
-    const double top = h < y1 ? h : y1;      // min(y1, h)
-    const double bot = -h > y0 ? -h : y0;    // max(y0, -h)
-    if (!(top > bot)) continue;
-    // integrand = (h<y1 ? h : y1) - (-h>y0 ? -h : y0), constant structure on [u, v]
-    double part = 0.0;
-    const double Hh = circ_H(v, R) - circ_H(u, R);
-    part += (h < y1) ? Hh : y1 * (v - u);
-    part -= (-h > y0) ? -Hh : y0 * (v - u);
-    area += part;
-  }
-  return area;
-}
-
-// get_ball_im (primitives.py:33-61): one thread per sprite pixel
-static __global__ void build_ball_sprites_kernel(uint32_t *atlas, RenderLayout RL, int n_balls, const uint32_t *fill8,
-                                          const uint32_t *stroke8) {
-  const int slot = blockIdx.y;
-  const int ri = blockIdx.z;  // radius index
-  if (slot >= n_balls) return;
-  const int r = RL.r_min + ri;
-  const int sT = RL.s_thick[slot];
-  const int sz = 2 * (r + sT);
-  const int p = blockIdx.x * blockDim.x + threadIdx.x;
-  if (p >= sz * sz) return;
-  const int px = p % sz, py = p / sz;
-  const double c = (double)(r + sT);
-  const double x0 = px - c, x1 = px + 1 - c, y0 = py - c, y1 = py + 1 - c;
-  const double Ro = r + 0.5 * sT, Ri = r - 0.5 * sT;
-  double cs = disc_box_area(Ro, x0, x1, y0, y1) - disc_box_area(Ri > 0 ? Ri : 0, x0, x1, y0, y1);
-  double cf = disc_box_area((double)r, x0, x1, y0, y1);
-  cs = cs < 0 ? 0 : (cs > 1 ? 1 : cs);
-  cf = cf < 0 ? 0 : (cf > 1 ? 1 : cf);
-  const uint32_t ms = (uint32_t)floor(255.0 * cs + 0.5), mf = (uint32_t)floor(255.0 * cf + 0.5);
-  uint32_t px8 = 0u;                                  // transparent (primitives.py:45-46)
-  if (sT > 0) px8 = over_px(in_mask(stroke8[slot], ms), px8);  // stroke (primitives.py:49-55)
-  px8 = over_px(in_mask(fill8[slot], mf), px8);       // fill   (primitives.py:57-59)
-  uint8_t *basep = reinterpret_cast<uint8_t *>(atlas) + (size_t)slot * RL.sprite_slot_stride +
-                   (size_t)ri * RL.sprite_stride;
-  reinterpret_cast<uint32_t *>(basep)[p] = px8;
-}
+// ball sprites (get_ball_im): csrc/ppb_cairo.cu
 
 // ---- exact area of (convex quad ∩ pixel [px,px+1]x[py,py+1]) by Sutherland-Hodgman ----
 static __device__ __noinline__ float quad_pixel_area(const float *qv /*8*/, float px, float py) {

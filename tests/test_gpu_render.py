@@ -1,12 +1,15 @@
-"""GPU parity tests (frames): render kernel through the C ABI vs. the restated renderer
-(oracle/render_oracle.c).
+"""GPU parity tests (frames): render kernel through the C ABI vs. oracle/cairo_oracle.c, the restatement of the
+published cairo pipeline the reference draws through (arc -> Beziers -> flattening -> stroker -> tor scan
+converter -> span compositing; see that file's header).
 
-Frame parity against real Cairo output is UNPINNED (no pycairo/libcairo in the reference
-tree or in this image, no golden images in the reference).  What is tested here is that
-the CUDA rasteriser implements the stated drawing model exactly:
-  * axis-aligned walls and ball sprites: identical bytes;
-  * rotated wall quads: coverage is computed in fp32 on the device and fp64 in the oracle,
-    so the 8-bit mask may differ by one step -> |diff| <= RENDER_TOL per channel.
+Frame parity against libcairo's own output is UNPINNED (no pycairo/libcairo in the reference tree or in this
+image, no golden images in the reference).  What is tested here:
+  * ball sprites, axis-aligned walls (every DataSaver rect table, BASELINE configs 1-4), clipping, insertion
+    order, translucent colours: identical bytes;
+  * rotated wall quads (rhombus / n-gon tables): the engine paints the wall colour through the exact
+    pixel-quad area instead of cairo's sampled coverage of the quad and of its pre-rendered stroked sprite.
+    Against that stated model |diff| <= RENDER_TOL (fp32 on the device, fp64 in the oracle); against the cairo
+    restatement |diff| <= CAIRO_WALL_TOL, only on the walls' edge pixels (measured: tests/test_cairo_oracle.py).
 """
 import numpy as np
 import pytest
@@ -17,6 +20,7 @@ from conftest import load_golden
 pytestmark = pytest.mark.gpu
 
 RENDER_TOL = 1  # LSB per channel, rotated-quad edge pixels only
+CAIRO_WALL_TOL = 32  # per channel, of 255; measured maximum over the golden rotated tables: 30
 
 GRAY = (0.5, 0.5, 0.5, 1.0)
 BLACK = (0.0, 0.0, 0.0, 1.0)
@@ -24,7 +28,7 @@ RED = (1.0, 0.0, 0.0, 1.0)
 
 
 def _render_both(wall, pos, rad, canvas, s_thick, wall_kind=None, wall_rgba=None, fill=GRAY, stroke=BLACK,
-                 order=None, dtype="f32"):
+                 order=None, dtype="f32", rotated_walls="cairo"):
     from pyphy_engine_b200.engine import WorldBatch
     wall = np.asarray(wall, np.float64)
     pos = np.asarray(pos, np.float64)
@@ -40,7 +44,7 @@ def _render_both(wall, pos, rad, canvas, s_thick, wall_kind=None, wall_rgba=None
     wb.set_styles([(s_thick, fill, stroke)] * nb, list(zip(kinds, cols)), int(live.min()), int(live.max()))
     dev = wb.render().cpu().numpy()
     ref = oracle.render_frames(wall, pos, rad, canvas, order=order, wall_kind=kinds, wall_rgba=np.array(cols),
-                               s_thick=s_thick, fill=fill, stroke=stroke, n_threads=8)
+                               s_thick=s_thick, fill=fill, stroke=stroke, n_threads=8, rotated_walls=rotated_walls)
     return dev, ref
 
 
@@ -103,14 +107,22 @@ def test_frames_walldef_walls_identical():
 @pytest.mark.parametrize("name,canvas", [("diamond", (640, 480)), ("rhomb3_s300", (1600, 1600)),
                                          ("rhomb3_s305", (1600, 1600)), ("ngon3_s800", (800, 800)),
                                          ("ngon6_s801", (800, 800)), ("ngon8_s800", (800, 800))])
-def test_frames_rotated_walls_within_one_lsb(name, canvas):
+def test_frames_rotated_walls(name, canvas):
     case = [c for c in load_golden("physics_golden.npz") if c.name == name][0]
     dev, ref = _render_both(case["wall"][None], case["pos0"][None], case["rad"][None], canvas, 2,
-                            order=case["order"], dtype="f64")
+                            order=case["order"], dtype="f64", rotated_walls="area")
     diff = np.abs(dev.astype(np.int32) - ref.astype(np.int32))
-    assert diff.max() <= RENDER_TOL
+    assert diff.max() <= RENDER_TOL                      # the engine's stated model of a rotated quad
     assert (diff > 0).mean() < 1e-3
     assert (ref[..., 1] == 0).any()     # the red walls are there
+    cairo = oracle.render_frames(case["wall"][None], case["pos0"][None], case["rad"][None], canvas, order=case["order"],
+                                 s_thick=2, n_threads=8)
+    dc = np.abs(dev.astype(np.int32) - cairo.astype(np.int32)).max(axis=-1)
+    assert dc.max() <= CAIRO_WALL_TOL
+    # pixels that differ are antialiased wall-edge pixels in one rendering or the other, and few
+    partly = ((cairo[..., 1] > 0) & (cairo[..., 1] < 255)) | ((dev[..., 1] > 0) & (dev[..., 1] < 255))
+    assert not ((dc > 0) & ~partly).any()
+    assert (dc > 0).mean() < 0.01
 
 
 def test_frames_interleaved_order_and_colours():
@@ -119,8 +131,9 @@ def test_frames_interleaved_order_and_colours():
     wall = np.array([[[[20, 20], [60, 20], [60, 60], [20, 60]], [[70, 10], [90, 10], [90, 90], [70, 90]]]], np.float64)
     pos = np.array([[[40.0, 40.0], [80.0, 50.0]]])
     order = [1 + 1, 0, 2 + 1, 1]   # ball-0, wall-0, ball-1, wall-1
+    # (a translucent wall is a WallDef wall: GenericWall sprites are always opaque red in the reference, quirk Q19)
     dev, ref = _render_both(wall, pos, 10, (100, 100), 2, order=order, wall_rgba=[(0.2, 0.4, 0.6, 1.0), (0.9, 0.8, 0.1, 0.5)],
-                            fill=(0.1, 0.7, 0.3, 0.8), stroke=(0.3, 0.0, 0.9, 1.0))
+                            wall_kind=[0, 1], fill=(0.1, 0.7, 0.3, 0.8), stroke=(0.3, 0.0, 0.9, 1.0))
     assert np.array_equal(dev, ref)
     assert tuple(dev[0, 40, 40, :3]) == tuple(ref[0, 40, 40, :3])
     assert dev[0, 40, 40, 0] == 51        # wall-0 (0.2 -> 51) covers ball-0
