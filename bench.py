@@ -8,7 +8,7 @@
 Workload (BASELINE.json configs[3], the configuration the 1/2/4/8-GPU metric is quoted on):
 per GPU 131,072 independent 8-ball worlds on a 64x64 canvas, synthetic random-initialised
 rectangular tables; one "step" = Dynamics.step() + World.generate_image() for every world of
-the shard (3 kernel launches: integrate, collide, render).  Weak scaling: the per-GPU shard is
+the shard (one advance launch per 16 steps + one render launch per step).  Weak scaling: the per-GPU shard is
 fixed, 8 GPUs = the full 1,048,576-world config.  Worlds are independent, so there is no
 collective in the step loop; NCCL only carries the final timing/statistics reduction.
 
@@ -35,12 +35,16 @@ CANVAS = 64
 SEED0 = 20161
 MAX_SUBSTEPS = 64
 # algorithmic bytes (fp32 state, RGBA8 frames), SURVEY.md 8(d) / DESIGN.md "Kernels"
-BYTES_K1_PER_BALL_STEP = 32
 BYTES_K3_PER_FRAME = CANVAS * CANVAS * 4
+DRAWS_PER_ADVANCE = 16        # steps one advance launch covers when a frame is drawn every step (PPB_DRAWS_PER_CHUNK)
 
 
-def _bytes_k2_per_world_step(n_balls, n_seg=16):
-    return 24 * n_balls + 16 * n_seg + 16 * n_balls
+def _bytes_advance_per_launch(n_worlds, n_balls, n_steps, n_snapshots):
+    """What one advance launch materialises in HBM (a multi-step launch divides by its own bytes):
+    per world the 16-byte header read and written, per ball pos + vel + tCol + {radius, mass} read (28 B) and
+    pos + tCol written (12 B; velocities, nrmlCol / futureVel and objCol only for worlds that had an event),
+    plus 8 B per ball and position snapshot."""
+    return n_worlds * (32 + n_balls * 40) + n_snapshots * n_worlds * n_balls * 8
 
 
 def load_traffic(kernel):
@@ -50,10 +54,28 @@ def load_traffic(kernel):
     try:
         with open(p) as fh:
             t = json.load(fh)["kernels"]
-        key = {"integrate": "integrate_kernel", "collide": "collide_kernel", "render": "render_tile_kernel"}[kernel]
+        key = {"advance": "advance_kernel", "render": "render_tile_kernel"}[kernel]
         return float(t[key]["dram_bytes"])
     except Exception:
         return None
+
+
+def load_python_reference():
+    """The UNMODIFIED Python reference timed in the build container (tools/time_reference.py; it cannot travel to the
+    GPU box): the committed record, echoed next to the C port's number."""
+    try:
+        with open(os.path.join(ROOT, "profiles", "r2_python_reference.json")) as fh:
+            rec = json.load(fh)
+        rows = {(r["config"], r["processes"]): r for r in rec["rows"]}
+        ncpu = rec["host"]["cpu_count"]
+        pick = lambda cfg, procs: round(rows[(cfg, procs)]["ball_steps_per_sec"], 1) if (cfg, procs) in rows else None
+        return {"what": rec["what"], "host": rec["host"], "unit": "ball-steps/s",
+                "config4_sample_1_process": pick("config4", 1), "config4_sample_%d_processes" % ncpu: pick("config4", ncpu),
+                "config3_sample_1_process": pick("config3", 1), "config3_sample_%d_processes" % ncpu: pick("config3", ncpu),
+                "config1_1_process": pick("config1", 1), "config2_1_process": pick("config2", 1),
+                "source": "profiles/r2_python_reference.json"}
+    except Exception as e:           # the record is optional
+        return {"unavailable": repr(e)}
 
 
 def load_peaks():
@@ -164,7 +186,7 @@ def cpu_baseline(threads, target_seconds=12.0, n_worlds=4096):
     t = sum(port.step() for _ in range(n_steps))
     live = int((port.ob.status == 0).sum())
     return {"value": live * N_BALLS * n_steps / t, "unit": "ball-steps/s", "cores": threads, "kind": "port",
-            "frames_per_sec": live * n_steps / t,
+            "frames_per_sec": live * n_steps / t, "python_reference": load_python_reference(),
             "sample": "%d worlds x %d balls x %d steps after 3 warm-up steps, step+render per step, OpenMP over worlds "
                       "(C restatement of the reference; the Python reference cannot travel to the GPU box)"
                       % (n_worlds, N_BALLS, n_steps)}
@@ -259,7 +281,7 @@ def run_ours(args, rank, local_rank, world_size):
     e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
     barrier()
     e0.record()
-    wb.step_ring_async(args.steps, frames, 1)      # K steps: 3 kernel launches each
+    wb.step_ring_async(args.steps, frames, 1)      # K steps: K render launches + ceil(K / 16) advance launches
     e1.record()
     barrier()
     ms = e0.elapsed_time(e1)
@@ -271,16 +293,16 @@ def run_ours(args, rank, local_rank, world_size):
     st1, steps_done = wb.get_status()
     live = int((st1 == 0).sum())
     launches = c1["launches"] - c0["launches"]
-    # second, untimed pass of the same K steps with events around integrate and collide: an event pair between
-    # two kernels of a stream serialises their launches (about 4 % of this step), so the two small kernels are
-    # timed here and only the dominant one inside the timed region
+    # second, untimed pass of the same K steps with events around the advance launches: an event pair between two
+    # kernels of a stream keeps the second from being scheduled while the first drains, so inside the timed region
+    # only the dominant kernel is bracketed
     wb.set_profiling(3)
     wb.step_ring_async(args.steps, frames, 1)
     torch.cuda.synchronize(dev)
     kms2, kn2 = wb.kernel_times()
     wb.set_profiling(False)
-    kms = [kms2[0], kms2[1], kms[2]]
-    kn = [kn2[0], kn2[1], kn[2]]
+    kms = [kms2[0], 0.0, kms[2]]
+    kn = [kn2[0], 0, kn[2]]
 
     k_ms, k_n = np.array(kms), np.array(kn)
     avg_us = 1e3 * k_ms / np.maximum(k_n, 1)
@@ -295,6 +317,31 @@ def run_ours(args, rank, local_rank, world_size):
     iso1.record()
     torch.cuda.synchronize(dev)
     render_alone_us = 1e3 * iso0.elapsed_time(iso1) / 5.0
+
+    # ---- the same workload in the bit-exact fp64 mode and under the default sub-step guard (own sub-records; the
+    #      headline `value` is the fp32 run above with the bench's guard of 64) ----
+    def variant(dtype, max_substeps, k_steps, w_steps):
+        vb = WorldBatch(n_worlds, N_BALLS, 4, dtype=dtype, canvas=(CANVAS, CANVAS), device=local_rank,
+                        max_substeps=max_substeps)
+        vb.set_walls(W["wall"])
+        vb.set_balls(W["pos"], W["vel"], W["rad"], W["mass"])
+        vb.set_styles([STYLE_BALL] * N_BALLS, [STYLE_WALL] * 4, 3, 3)
+        vb.step_ring_async(w_steps, frames, 1)
+        torch.cuda.synchronize(dev)
+        v0, v1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+        v0.record()
+        vb.step_ring_async(k_steps, frames, 1)
+        v1.record()
+        torch.cuda.synchronize(dev)
+        vms = v0.elapsed_time(v1)
+        vst, _ = vb.get_status()
+        vlive = int((vst == 0).sum())
+        vb.close()
+        return {"dtype": dtype, "max_substeps": max_substeps, "steps": k_steps, "warmup": w_steps,
+                "ms_per_step": vms / k_steps, "ball_steps_per_sec_rank0": vlive * N_BALLS * k_steps / (vms * 1e-3),
+                "frames_per_sec_rank0": vlive * k_steps / (vms * 1e-3), "halted_worlds_rank0": n_worlds - vlive}
+    f64_mode = variant("f64", MAX_SUBSTEPS, 5, 3) if rank == 0 else None
+    default_guard = variant("f32", 1 << 20, args.steps, args.warmup) if rank == 0 else None
 
     # ---- end-to-end through the host-buffer API: H2D of the batch state + step + D2H of positions and frames ----
     # Two sets of pinned host buffers: the call of step i only enqueues (ppb_simulate_host_async); while its frames
@@ -339,19 +386,30 @@ def run_ours(args, rank, local_rank, world_size):
     else:
         live_total, events_total, launches_total = float(live), float(stats[3]), float(launches)
 
-    # ---- end-of-run gather of the datagen shard (NCCL over NVLink when distributed): the positions every rank
-    #      recorded for its worlds arrive on rank 0 in world order; not part of any timed region ----
-    final_traj = torch.from_numpy(np.ascontiguousarray(traj_host.numpy())).to(dev)     # (1, n_worlds, balls, 2)
+    # ---- end-of-run gather of the datagen shard (NCCL over NVLink when distributed): 100 steps of positions of every
+    #      rank's worlds arrive on rank 0 in world order (`position` (2N, seqLen) fp32 per world).  The
+    #      first gather of a process pays the lazy NCCL connection set-up, so a one-step gather goes first; not part
+    #      of any timed region above ----
+    GATHER_STEPS = 100
+    shard = torch.empty((GATHER_STEPS, n_worlds, N_BALLS, 2), dtype=torch.float32, device=dev)
+    wb.step_async(GATHER_STEPS, traj=shard)
     torch.cuda.synchronize(dev)
+    _sh.gather_trajectories(shard[:1].contiguous(), n_worlds * world_size, dst=0)      # warm-up
+    barrier()
     tg0 = time.perf_counter()
-    gathered = _sh.gather_trajectories(final_traj, n_worlds * world_size, dst=0)
+    gathered = _sh.gather_trajectories(shard, n_worlds * world_size, dst=0)
     torch.cuda.synchronize(dev)
+    barrier()
     gather_ms = 1e3 * (time.perf_counter() - tg0)
     gather_info = None
     if rank == 0:
-        gather_info = {"shape": list(gathered.shape), "bytes": int(gathered.numel() * 4), "ms": gather_ms,
-                       "backend": "nccl" if distributed else "none (single rank)",
-                       "checksum": float(gathered.double().sum().item())}
+        nbytes = int(gathered.numel() * 4)
+        gather_info = {"shape": list(gathered.shape), "bytes": nbytes, "ms": gather_ms,
+                       "gb_per_s": nbytes * (world_size - 1) / max(world_size, 1) / (gather_ms * 1e-3) / 1e9 if distributed else None,
+                       "backend": "nccl (dist.gather to rank 0; GB/s counts the bytes that arrive from the other ranks)"
+                                  if distributed else "none (single rank)",
+                       "checksum": float(gathered[-1].double().sum().item())}
+    del gathered, shard
 
     if rank == 0:
         total_worlds = n_worlds * world_size
@@ -359,14 +417,14 @@ def run_ours(args, rank, local_rank, world_size):
         value = ball_steps / (ms * 1e-3)
         fps = live_total * args.steps / (ms * 1e-3)
         peak, peak_src = load_peaks()
-        # dominant kernel of this workload: the one that moves the bytes (render, 96 % of the step's algorithmic
-        # traffic).  Elapsed times cannot rank the kernels here: under the pipelined schedule the collide kernel
-        # of step k+1 is stretched over the render of step k, whose SMs it shares.
+        # dominant kernel of this workload: the one that moves the bytes and the time (render: 99 % of the step's
+        # algorithmic traffic, about 90 % of its duration)
+        names = {0: "advance", 2: "render"}
+        steps_per_adv = args.steps / max(kn[0], 1)
+        alg_bytes = {0: _bytes_advance_per_launch(n_worlds, N_BALLS, steps_per_adv, steps_per_adv),
+                     2: BYTES_K3_PER_FRAME * n_worlds}
+        achieved = {i: alg_bytes[i] / (avg_us[i] * 1e-6) / 1e9 if avg_us[i] > 0 else 0.0 for i in names}
         dom = 2
-        names = ["integrate", "collide", "render"]
-        alg_bytes = [BYTES_K1_PER_BALL_STEP * n_worlds * N_BALLS, _bytes_k2_per_world_step(N_BALLS) * n_worlds,
-                     BYTES_K3_PER_FRAME * n_worlds]
-        achieved = [alg_bytes[i] / (avg_us[i] * 1e-6) / 1e9 if avg_us[i] > 0 else 0.0 for i in range(3)]
         os.sched_setaffinity(0, full_affinity)     # the CPU baseline may use every host core again
         cpu = cpu_baseline(len(full_affinity))
         line = {
@@ -377,21 +435,23 @@ def run_ours(args, rank, local_rank, world_size):
             "config": {"workload": "configs[3] shard: 131072 worlds/GPU x 8 balls, 64x64 frame rendered every step",
                        "worlds_total": total_worlds, "balls_per_world": N_BALLS, "canvas": [CANVAS, CANVAS],
                        "l2": "per-step working set (2 GiB of frames + 70 MB of state per GPU) exceeds the 126 MB L2",
-                       "schedule": "render of step k on its own stream overlaps integrate+collide of step k+1; frames into a 2-slot ring",
+                       "schedule": "one advance launch per 16 steps leaves 16 position snapshots, 16 render launches follow on their own stream; the next advance launch starts beside the last 2 of them; frames into a 2-slot ring",
                        "max_substeps": MAX_SUBSTEPS, "halted_worlds": int(total_worlds - live_total),
                        "events_per_world_step": events_total / (total_worlds * max(args.steps, 1)),
                        "pair_tests_per_sec_rank0": (c1["pair_tests"] - c0["pair_tests"]) / (ms * 1e-3)},
             "roofline": {"bound": "hbm", "kernel": names[dom], "achieved": achieved[dom], "peak": peak,
                          "unit": "GB/s", "frac": achieved[dom] / peak, "traffic": load_traffic(names[dom]), "peak_source": peak_src,
                          "avg_launch_us": float(avg_us[dom]),
-                         "note": "render: CUDA-event times of every launch inside the timed region, where the render of step k "
-                                 "shares the SMs with integrate+collide of step k+1 (integrate/collide: event times of a second "
-                                 "pass of the same K steps); render alone: %.1f us/launch = %.3f of peak"
-                                 % (render_alone_us, alg_bytes[2] / (render_alone_us * 1e-6) / 1e9 / peak),
+                         "note": "render: CUDA-event times of every launch inside the timed region (2 of every 16 share the SMs "
+                                 "with the next advance launch); advance: event times of a second pass of the same K steps, "
+                                 "%.1f steps per launch, bytes = what that launch materialises (state round trip + snapshots) -- "
+                                 "it is bound by instruction issue and by its longest sub-step chain, not by HBM; "
+                                 "render alone: %.1f us/launch = %.3f of peak"
+                                 % (steps_per_adv, render_alone_us, alg_bytes[2] / (render_alone_us * 1e-6) / 1e9 / peak),
                          "render_alone_us": render_alone_us,
                          "all_kernels": {names[i]: {"avg_launch_us": float(avg_us[i]), "achieved_gbs": achieved[i],
                                                     "frac": achieved[i] / peak, "algorithmic_bytes_per_launch": alg_bytes[i]}
-                                         for i in range(3)}},
+                                         for i in names}},
             "cpu_baseline": cpu,
             "e2e": {"value": live_total * N_BALLS * e2e_steps / e2e_s, "unit": "ball-steps/s",
                     "frames_per_sec": live_total * e2e_steps / e2e_s,
@@ -399,6 +459,8 @@ def run_ours(args, rank, local_rank, world_size):
                     "api": "per step: WorldBatch.set_walls/set_balls (H2D) + simulate_host(wait=False) (ppb_simulate_host_async: step, render, D2H) + host_sync(keep_in_flight=1); two sets of pinned host buffers, so the upload of step i+1 overlaps the download of step i",
                     "numa_node_rank0": numa_node},
             "final_gather": gather_info,
+            "f64_mode": f64_mode,
+            "default_guard": default_guard,
             "gpu_launches": int(launches_total),
             "clocks": {"sm_mhz": clk["sm_mhz"], "sm_max_mhz": clk["sm_max_mhz"], "reasons": clk["reasons"]},
         }

@@ -51,6 +51,12 @@ inline uint32_t h_premul_rgba8(const float c[4]) {
 
 }  // namespace
 
+// Steps per advance launch: long enough to amortise the state round trip and to let the warps that own a world with
+// a long sub-step chain catch up, short enough that a launch stays in the millisecond range.  With frames, a launch
+// covers at most PPB_DRAWS_PER_CHUNK drawn steps (their position snapshots are what the render kernels read).
+#define PPB_STEPS_PER_LAUNCH 64
+#define PPB_DRAWS_PER_CHUNK 16
+
 struct ppb_batch {
   ppb_config cfg;
   Layout L;
@@ -58,7 +64,8 @@ struct ppb_batch {
   StepParams P;
   RenderLayout RL;
   int sm_count = 0;
-  int collide_grid = 1;
+  int advance_grid = 1;
+  int launch_parity = 0;   // work-ticket counter the next advance launch uses
   size_t esz = 4;
   bool styles_set = false;
   uint32_t *atlas = nullptr;
@@ -73,8 +80,10 @@ struct ppb_batch {
   size_t ev_used = 0;
   // software pipeline of ppb_step_async: render of step k on its own stream, overlapped with the physics of step k+1
   cudaStream_t render_stream = nullptr;
-  void *snap[2] = {nullptr, nullptr};
-  cudaEvent_t ev_phys[2] = {nullptr, nullptr}, ev_rend[2] = {nullptr, nullptr};
+  void *snap[2] = {nullptr, nullptr};   // PPB_DRAWS_PER_CHUNK position snapshots each
+  cudaEvent_t ev_phys[2] = {nullptr, nullptr}, ev_rend[2] = {nullptr, nullptr}, ev_gate[2] = {nullptr, nullptr};
+  int draws_per_chunk = PPB_DRAWS_PER_CHUNK;
+  int overlap_renders = 2;   // how many of a chunk's last render launches the next chunk's physics may run beside (-1: all)
   // page-locked staging for host <-> device state transfers (grown on demand)
   void *stage = nullptr;
   size_t stage_bytes = 0;
@@ -201,24 +210,26 @@ struct Prof {
   }
 };
 
-int step_physics(ppb_batch *b, int step_off, void *traj, void *snap, cudaStream_t st) {
+// n_steps x Dynamics.step for every world, one launch.  Positions after step draw_first, draw_first + draw_every, ...
+// (indices inside the launch) go to consecutive snapshot slots of `snap` when it is given.
+int step_physics(ppb_batch *b, int step_off, int n_steps, void *traj, void *snap, int draw_first, int draw_every,
+                 cudaStream_t st) {
+  if (n_steps <= 0) return PPB_OK;
   StepParams P = b->P;
   P.step_off = step_off;
   P.step_abs = b->host_step + step_off;
+  P.n_steps = n_steps;
+  P.draw_first = draw_first;
+  P.draw_every = snap ? draw_every : 0;
+  P.parity = b->launch_parity;
+  b->launch_parity ^= 1;
   StatePtrs S = b->S;
   S.snap = snap;
-  {
-    Prof p(b, st, 0);
-    CU(is64(b) ? Launch<double>::integrate(S, b->cfg.n_balls, P, traj, st)
-               : Launch<float>::integrate(S, b->cfg.n_balls, P, traj, st));
-    ++b->launches;
-  }
-  {
-    Prof p(b, st, 1);
-    CU(is64(b) ? Launch<double>::collide(S, b->L, P, traj, b->collide_grid, st)
-               : Launch<float>::collide(S, b->L, P, traj, b->collide_grid, st));
-    ++b->launches;
-  }
+  const int grid = b->advance_grid;
+  Prof p(b, st, 0);
+  CU(is64(b) ? Launch<double>::advance(S, b->L, P, traj, grid, st)
+             : Launch<float>::advance(S, b->L, P, traj, grid, st));
+  ++b->launches;
   return PPB_OK;
 }
 
@@ -230,13 +241,6 @@ int step_render(ppb_batch *b, void *pos_src, uint8_t *frame, cudaStream_t st) {
   CU(is64(b) ? Launch<double>::render(S, b->L, b->RL, b->atlas, frame, st)
              : Launch<float>::render(S, b->L, b->RL, b->atlas, frame, st));
   ++b->launches;
-  return PPB_OK;
-}
-
-int step_once(ppb_batch *b, int step_off, void *traj, uint8_t *frame, cudaStream_t st) {
-  int rc = step_physics(b, step_off, traj, nullptr, st);
-  if (rc) return rc;
-  if (frame) return step_render(b, b->S.pos, frame, st);
   return PPB_OK;
 }
 
@@ -269,11 +273,12 @@ int check_radii(ppb_batch *b, cudaStream_t st) {
 
 int pipeline_reserve(ppb_batch *b) {
   if (b->render_stream) return PPB_OK;
-  const size_t bytes = (size_t)b->cfg.n_worlds * b->cfg.n_balls * 2 * b->esz;
+  const size_t bytes = (size_t)b->cfg.n_worlds * b->cfg.n_balls * 2 * b->esz * b->draws_per_chunk;
   for (int i = 0; i < 2; ++i) {
     CU(cudaMalloc(&b->snap[i], bytes ? bytes : 16));
     CU(cudaEventCreateWithFlags(&b->ev_phys[i], cudaEventDisableTiming));
     CU(cudaEventCreateWithFlags(&b->ev_rend[i], cudaEventDisableTiming));
+    CU(cudaEventCreateWithFlags(&b->ev_gate[i], cudaEventDisableTiming));
   }
   // highest priority: the render of step k and the integrate kernel of step k+1 become ready at the same moment;
   // the renderer's one large CTA per SM should be placed before the small physics CTAs fill the SM (it does not
@@ -398,7 +403,7 @@ int ppb_create(const ppb_config *cfg, ppb_batch **out) {
       {&b->S.hdr, nw * 16},           {(void **)&b->S.partner, nb * 4},
       {(void **)&b->S.nev, nw * 4},   {(void **)&b->S.events, (size_t)(cfg->event_capacity > 0 ? cfg->event_capacity : 1) * sizeof(ppb_event)},
       {(void **)&b->S.counters, 8 * sizeof(unsigned long long)},
-      {(void **)&b->S.list, nw * 4},
+      {(void **)&b->S.list, 16},
       {(void **)&b->S.list_count, 16},
   };
   for (auto &a : allocs) {
@@ -429,8 +434,13 @@ int ppb_create(const ppb_config *cfg, ppb_batch **out) {
       return fail(PPB_E_CUDA, "initial reset failed: %s", cudaGetErrorString(e));
     }
   }
-  b->collide_grid = is64(b) ? Launch<double>::collide_grid(cfg->n_worlds, b->sm_count)
-                            : Launch<float>::collide_grid(cfg->n_worlds, b->sm_count);
+  b->advance_grid = is64(b) ? Launch<double>::advance_grid(cfg->n_worlds, nB, b->sm_count)
+                            : Launch<float>::advance_grid(cfg->n_worlds, nB, b->sm_count);
+  if (const char *e = getenv("PPB_OVERLAP")) b->overlap_renders = atoi(e);   // developer switch (A/B timing)
+  if (const char *e = getenv("PPB_CHUNK")) {
+    const int v = atoi(e);
+    if (v >= 1 && v <= PPB_STEPS_PER_LAUNCH) b->draws_per_chunk = v;
+  }
   memset(&b->RL, 0, sizeof b->RL);
   b->RL.W = cfg->canvas_w;
   b->RL.H = cfg->canvas_h;
@@ -449,6 +459,7 @@ int ppb_destroy(ppb_batch *b) {
     if (b->snap[i]) cudaFree(b->snap[i]);
     if (b->ev_phys[i]) cudaEventDestroy(b->ev_phys[i]);
     if (b->ev_rend[i]) cudaEventDestroy(b->ev_rend[i]);
+    if (b->ev_gate[i]) cudaEventDestroy(b->ev_gate[i]);
   }
   if (b->render_stream) cudaStreamDestroy(b->render_stream);
   void *ptrs[] = {b->S.pos, b->S.vel, b->S.aux, b->S.tcol, b->S.rm, b->S.wall, b->S.wall_rc, b->S.hdr, b->S.partner,
@@ -756,6 +767,83 @@ int ppb_set_gravity(ppb_batch *b, double gx, double gy) {
   return PPB_OK;
 }
 
+// The body of ppb_step_ring_async after argument checking (also the stepping loop of ppb_simulate_host).
+static int run_steps(ppb_batch *b, int32_t n_steps, void *traj_dev, uint8_t *frames_dev, int32_t ring_slots,
+                     int32_t render_every, cudaStream_t st) {
+  const size_t frame_bytes = (size_t)b->cfg.n_worlds * b->RL.W * b->RL.H * 4;
+  const size_t snap_bytes = (size_t)b->cfg.n_worlds * b->cfg.n_balls * 2 * b->esz;
+  const int n_draws = frames_dev ? n_steps / render_every : 0;
+  if (n_draws <= 1) {
+    // no frame, or a single one: nothing to overlap with, everything on the caller's stream; the frame is drawn from
+    // the live positions between two launches
+    int s = 0;
+    const int draw_at = n_draws == 1 ? render_every : -1;   // steps done when the frame is due
+    while (s < n_steps) {
+      int n = n_steps - s;
+      if (n > PPB_STEPS_PER_LAUNCH) n = PPB_STEPS_PER_LAUNCH;
+      if (draw_at > s && s + n > draw_at) n = draw_at - s;
+      int rc = step_physics(b, s, n, traj_dev, nullptr, 0, 0, st);
+      if (rc) return rc;
+      s += n;
+      if (s == draw_at && (rc = step_render(b, b->S.pos, frames_dev, st))) return rc;
+    }
+  } else {
+    // Chunks of up to `draws_per_chunk` drawn steps: one advance launch on `st` leaves a position snapshot per drawn
+    // step, the chunk's render launches follow on the render stream; two sets of snapshot slots alternate.  The
+    // next chunk's advance launch is released when all but the last `overlap_renders` renders of this chunk are done:
+    // its tail (the few warps that own a world with a long sub-step chain) then hides behind those renders, while the
+    // bulk of the rendering has the SMs to itself -- the render kernel loses about as much time as the physics
+    // instructions it shares the SMs with would take alone.  Measured on B200, 131,072 x 8 worlds with a frame per
+    // step, us per step: chunks of 8 / 16 / 32 draws with overlap 0: 432 / 417 / 411, overlap 2: 412 / 409 / 408,
+    // all renders overlapped: 415 / 411 / 409 (PPB_CHUNK / PPB_OVERLAP in the environment select these for A/B runs).
+    int rc = pipeline_reserve(b);
+    if (rc) return rc;
+    int per_chunk = b->draws_per_chunk;
+    if (per_chunk * render_every > PPB_STEPS_PER_LAUNCH) per_chunk = PPB_STEPS_PER_LAUNCH / render_every;
+    if (per_chunk < 1) per_chunk = 1;
+    // the first chunks of a call are short (1, 2, 4, ... drawn steps): nothing hides the first advance launch, so it
+    // should cover few steps; every later one runs beside the renders of the chunk before it
+    int n_rendered = 0, chunk_i = 0, s = 0, ramp = 1;
+    while (s < n_steps) {
+      int draws = n_draws - n_rendered;
+      if (draws > per_chunk) draws = per_chunk;
+      if (draws > ramp) draws = ramp;
+      ramp *= 2;
+      // (steps after the last drawn one run without snapshots)
+      int n = draws > 0 ? draws * render_every : n_steps - s;
+      if (draws == 0 && n > PPB_STEPS_PER_LAUNCH) n = PPB_STEPS_PER_LAUNCH;
+      const int buf = chunk_i & 1;
+      if (draws > 0 && chunk_i >= 2) CU(cudaStreamWaitEvent(st, b->ev_rend[buf], 0));   // snapshot slots free again
+      // how much of the previous chunk's rendering this launch may run beside (see overlap_renders)
+      const bool gated = b->overlap_renders >= 0 && chunk_i >= 1;
+      if (gated) CU(cudaStreamWaitEvent(st, b->ev_gate[buf ^ 1], 0));
+      rc = step_physics(b, s, n, traj_dev, draws > 0 ? b->snap[buf] : nullptr, render_every - 1, render_every, st);
+      if (rc) return rc;
+      if (draws > 0) {
+        CU(cudaEventRecord(b->ev_phys[buf], st));
+        CU(cudaStreamWaitEvent(b->render_stream, b->ev_phys[buf], 0));
+        const int gate_after = draws - 1 - (b->overlap_renders > 0 ? b->overlap_renders : 0);
+        if (gate_after < 0) CU(cudaEventRecord(b->ev_gate[buf], b->render_stream));
+        for (int d = 0; d < draws; ++d) {
+          uint8_t *frame = frames_dev + (size_t)((n_rendered + d) % ring_slots) * frame_bytes;
+          rc = step_render(b, (char *)b->snap[buf] + (size_t)d * snap_bytes, frame, b->render_stream);
+          if (rc) return rc;
+          if (d == gate_after) CU(cudaEventRecord(b->ev_gate[buf], b->render_stream));
+        }
+        CU(cudaEventRecord(b->ev_rend[buf], b->render_stream));
+        n_rendered += draws;
+        ++chunk_i;
+      }
+      s += n;
+    }
+    // the caller's stream sees every frame complete
+    if (chunk_i >= 1) CU(cudaStreamWaitEvent(st, b->ev_rend[(chunk_i - 1) & 1], 0));
+    if (chunk_i >= 2) CU(cudaStreamWaitEvent(st, b->ev_rend[chunk_i & 1], 0));
+  }
+  b->host_step += n_steps;   // the kernels take the step index by value (StepParams.step_abs)
+  return PPB_OK;
+}
+
 int ppb_step_ring_async(ppb_batch *b, int32_t n_steps, void *traj_dev, uint8_t *frames_dev, int32_t ring_slots,
                         int32_t render_every, void *stream) {
   if (!b) return fail(PPB_E_INVALID, "null batch");
@@ -772,50 +860,7 @@ int ppb_step_ring_async(ppb_batch *b, int32_t n_steps, void *traj_dev, uint8_t *
     int rc = check_radii(b, st);
     if (rc) return rc;
   }
-  const size_t frame_bytes = (size_t)b->cfg.n_worlds * b->RL.W * b->RL.H * 4;
-  const int n_draws = frames_dev ? n_steps / render_every : 0;
-  if (!frames_dev) {
-    for (int s = 0; s < n_steps; ++s) {
-      int rc = step_physics(b, s, traj_dev, nullptr, st);
-      if (rc) return rc;
-    }
-  } else if (n_draws <= 1) {
-    // a single frame in this call: nothing to overlap with, everything on the caller's stream
-    for (int s = 0; s < n_steps; ++s) {
-      int rc = step_once(b, s, traj_dev, ((s + 1) % render_every) == 0 ? frames_dev : nullptr, st);
-      if (rc) return rc;
-    }
-  } else {
-    // physics of step s+1 (K1, K2 on `st`) overlaps the render of step s (K3 on the render stream,
-    // reading the position snapshot K1 / K2 left for it); snapshot slots alternate
-    int rc = pipeline_reserve(b);
-    if (rc) return rc;
-    int n_rendered = 0, last_slot = -1;
-    for (int s = 0; s < n_steps; ++s) {
-      const bool draw = ((s + 1) % render_every) == 0;
-      const int slot = n_rendered & 1;
-      if (draw && n_rendered >= 2) CU(cudaStreamWaitEvent(st, b->ev_rend[slot], 0));   // snapshot slot free again
-      rc = step_physics(b, s, traj_dev, draw ? b->snap[slot] : nullptr, st);
-      if (rc) return rc;
-      if (draw) {
-        uint8_t *frame = frames_dev + (size_t)(n_rendered % ring_slots) * frame_bytes;
-        CU(cudaEventRecord(b->ev_phys[slot], st));
-        CU(cudaStreamWaitEvent(b->render_stream, b->ev_phys[slot], 0));
-        rc = step_render(b, b->snap[slot], frame, b->render_stream);
-        if (rc) return rc;
-        CU(cudaEventRecord(b->ev_rend[slot], b->render_stream));
-        last_slot = slot;
-        ++n_rendered;
-      }
-    }
-    // the caller's stream sees every frame complete
-    if (last_slot >= 0) {
-      CU(cudaStreamWaitEvent(st, b->ev_rend[last_slot], 0));
-      if (n_rendered >= 2) CU(cudaStreamWaitEvent(st, b->ev_rend[last_slot ^ 1], 0));
-    }
-  }
-  b->host_step += n_steps;   // the kernels take the step index by value (StepParams.step_abs)
-  return PPB_OK;
+  return run_steps(b, n_steps, traj_dev, frames_dev, ring_slots, render_every, st);
 }
 
 int ppb_step_async(ppb_batch *b, int32_t n_steps, void *traj_dev, uint8_t *frames_dev, int32_t render_every,
@@ -832,12 +877,14 @@ int ppb_scan_async(ppb_batch *b, void *stream) {
   P.step_off = 0;
   P.step_abs = b->host_step;
   P.scan_only = 1;
-  CU(is64(b) ? Launch<double>::list_pending(b->S, b->host_step, st) : Launch<float>::list_pending(b->S, b->host_step, st));
-  CU(is64(b) ? Launch<double>::collide(b->S, b->L, P, nullptr, b->collide_grid, st)
-             : Launch<float>::collide(b->S, b->L, P, nullptr, b->collide_grid, st));
-  // the collide kernel zeroed the other parity's list; this one must be empty again for the next step
-  CU(cudaMemsetAsync(b->S.list_count, 0, 4 * sizeof(int32_t), st));
-  b->launches += 2;
+  P.n_steps = 1;
+  P.draw_first = 0;
+  P.draw_every = 0;
+  P.parity = b->launch_parity;
+  b->launch_parity ^= 1;
+  CU(is64(b) ? Launch<double>::advance(b->S, b->L, P, nullptr, b->advance_grid, st)
+             : Launch<float>::advance(b->S, b->L, P, nullptr, b->advance_grid, st));
+  b->launches += 1;
   return PPB_OK;
 }
 
@@ -932,15 +979,14 @@ static int simulate_host_impl(ppb_batch *b, int32_t n_steps, float *traj_host, u
     const int cur = (n_steps - done < chunk) ? (n_steps - done) : chunk;
     const int buf = (int)(b->sim_it & 1u);
     if (b->sim_it >= 2) CU(cudaStreamWaitEvent(st, b->ev_copied[buf], 0));  // staging buffer free again
-    for (int s = 0; s < cur; ++s) {
-      uint8_t *frame = nullptr;
-      const int gs = done + s;
-      if (frames_host && ((gs + 1) % render_every) == 0)
-        frame = b->scr_frames[buf] + (size_t)((s + 1) / render_every - 1) * frame_bytes;
-      int rc = step_once(b, s, traj_host ? b->scr_traj[buf] : nullptr, frame, st);
+    {
+      // chunk boundaries are multiples of render_every, so the frames of this chunk fill scr_frames[buf] in order;
+      // run_steps pipelines the renders with the physics of the following steps and advances host_step
+      const int nf = frames_host ? cur / render_every : 0;
+      int rc = run_steps(b, cur, traj_host ? b->scr_traj[buf] : nullptr, nf > 0 ? b->scr_frames[buf] : nullptr,
+                         nf > 0 ? nf : 1, render_every, st);
       if (rc) return rc;
     }
-    b->host_step += cur;
     const float *src32 = (const float *)b->scr_traj[buf];
     if (traj_host && is64(b)) {
       CU(Launch<double>::traj_to_f32(b->scr_traj[buf], b->scr_traj32[buf], (long long)traj_elems * cur, st));

@@ -123,8 +123,8 @@ struct Layout {
 // device state of a batch (raw pointers; T-typed views are made in the kernels)
 struct StatePtrs {
   void *pos;       // [n_worlds][n_balls] {x, y}
-  void *snap;      // NULL or [n_worlds][n_balls] {x, y}: copy of the positions after this step, written by K1 / K2
-                   // (the render kernel of step k reads it while the physics of step k+1 already runs)
+  void *snap;      // NULL or [slots][n_worlds][n_balls] {x, y}: copies of the positions after the steps that are drawn
+                   // (the render kernels read them while the physics of the following steps already runs)
   void *vel;       // [n_worlds][n_balls] {vx, vy}
   void *aux;       // [n_worlds][n_balls] {nrmlCol.x, nrmlCol.y, futureVel.x, futureVel.y}
   void *tcol;      // [n_worlds][n_balls]
@@ -136,9 +136,9 @@ struct StatePtrs {
   int32_t *partner;   // [n_worlds][n_balls]
   uint32_t *nev;      // [n_worlds] events emitted so far (sequence numbers)
   ppb_event *events;  // [event_capacity]
-  unsigned long long *counters;  // [0] events produced [1] collide world-steps [2] collide loop iterations [3] rescans
-  int32_t *list;                 // [n_worlds] worlds the collide kernel takes this step (built by integrate)
-  int32_t *list_count;           // [0..1] list lengths, [2..3] collide work tickets, indexed by step parity
+  unsigned long long *counters;  // [0] events produced [1] world-steps that ran the event loop [2] its iterations [3] rescans
+  int32_t *list;                 // (unused)
+  int32_t *list_count;           // [2..3] work tickets of the advance kernel, indexed by launch parity
   long long event_capacity;
   int32_t n_worlds;
 };
@@ -149,7 +149,11 @@ struct StepParams {
   int32_t step_abs;   // index of the step this launch advances (the batch counts its steps on the host): passed by
                       // value, so no kernel starts with a dependent load of a device-side counter
   int32_t max_substeps;
-  int32_t scan_only;  // collide kernel: drain the collision queue (rescan every ball) and stop; nothing moves
+  int32_t scan_only;  // drain the collision queue (rescan every ball) of the worlds that have one and stop; nothing moves
+  int32_t n_steps;    // steps this launch advances every world by
+  int32_t draw_first; // index inside the launch of the first step whose positions go to a snapshot slot ...
+  int32_t draw_every; // ... then every draw_every-th step (0: no snapshots); slot j lies j * n_worlds * n_balls further on
+  int32_t parity;     // which work-ticket counter this launch uses (it resets the other one for the next launch)
 };
 
 // ---- render ----

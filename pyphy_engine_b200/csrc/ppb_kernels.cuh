@@ -1,18 +1,12 @@
 // ppb_kernels.cuh -- the per-step kernels of the batched billiards engine (sm_100a).
 //
-//   K1 integrate_kernel : Dynamics.move_object (primitives.py:600-611) for every ball of the
-//                         worlds whose step is event-free (no queued rescan and min tCol_ > dt):
-//                         a pure HBM stream, one thread per ball pair / ball.
-//   K2 collide_kernel   : the event-driven step loop (primitives.py:628-733 + dynamics.py:8-136)
-//                         for the remaining worlds; one warp works on one world at a time with
-//                         its balls and wall vertices staged in shared memory, the
-//                         (ball x object) TOC tests spread over the lanes and reduced with
-//                         warp shuffles (lexicographic (t, insertion rank) arg-min).
-//   K3 render_kernel    : World.generate_image (primitives.py:991-1008) -- in ppb_render.cuh.
-//
-// A world is advanced exactly once per step: K1 takes it when its header says the step is
-// event-free and bumps header.step; K2 takes every world whose header.step still equals the
-// step index.
+//   advance_kernel      : n x Dynamics.step (primitives.py:600-733 + dynamics.py:8-136) for every world of the
+//                         batch in ONE launch.  A warp (or a team of warps) keeps a world in registers for all n
+//                         steps: event-free steps are Dynamics.move_object and nothing else, the others run the
+//                         event-driven loop with the world's balls and wall edges staged in shared memory, the
+//                         (ball x object) TOC tests spread over the lanes and reduced with warp shuffles
+//                         (lexicographic (t, insertion rank) arg-min).
+//   render_tile_kernel  : World.generate_image (primitives.py:991-1008) -- in ppb_render.cuh.
 #pragma once
 #include "ppb_math.cuh"
 
@@ -43,148 +37,6 @@ __device__ __forceinline__ void move_ball(V2<T> &pos, V2<T> &vel, T t, V2<T> g) 
 }
 
 // ------------------------------------------------------------------------------------
-// K1: integrate  (+ builds the list of worlds the collide kernel has to take)
-// ------------------------------------------------------------------------------------
-template <typename T, int BPT /* balls per thread: 1 or 2 */>
-__global__ void __launch_bounds__(256) integrate_kernel(StatePtrs S, int n_balls, StepParams P, T *traj) {
-  typedef typename Vec2<T>::type T2;
-  __shared__ int s_cnt, s_base;
-  __shared__ int s_list[256];
-  if (threadIdx.x == 0) s_cnt = 0;
-  pdl_launch_dependents();   // the collide kernel's CTAs may take their places; they wait for this grid to finish
-  __syncthreads();
-  pdl_wait();
-  const long long total = (long long)S.n_worlds * n_balls;
-  const long long i = ((long long)blockIdx.x * blockDim.x + threadIdx.x) * BPT;
-  const uint32_t k = (uint32_t)P.step_abs;
-  if (i < total) {
-    const int w = (int)(i / n_balls);
-    const bool duty = (i - (long long)w * n_balls) == 0;   // this thread owns the world's header
-    const Hdr<T> h = reinterpret_cast<const Hdr<T> *>(S.hdr)[w];
-    const T dt = (T)P.dt;
-    T2 *pos = reinterpret_cast<T2 *>(S.pos);
-    T2 *vel = reinterpret_cast<T2 *>(S.vel);
-    T *tcol = reinterpret_cast<T *>(S.tcol);
-    // The state of this thread's balls is fetched together with the header, not after it: one memory round trip
-    // instead of two on the common (event-free) path; the few worlds that go to the collide kernel cost a read.
-    typedef typename Vec4<T>::type T4;
-    T4 sp4, sv4;
-    T2 stc2, sp1, sv1;
-    T stc1 = T(0);
-    if (BPT == 2) {
-      sp4 = ld4(reinterpret_cast<const T4 *>(pos + i));
-      sv4 = ld4(reinterpret_cast<const T4 *>(vel + i));
-      stc2 = *reinterpret_cast<const T2 *>(tcol + i);
-    } else {
-      sp1 = pos[i];
-      sv1 = vel[i];
-      stc1 = tcol[i];
-    }
-    if (PPB_STATUS_OF(h.flags) != 0u) {
-      // halted world: nothing moves any more; keep recording where it stopped
-      if (traj) {
-#pragma unroll
-        for (int j = 0; j < BPT; ++j) reinterpret_cast<T2 *>(traj)[(long long)P.step_off * total + i + j] = pos[i + j];
-      }
-      if (S.snap) {
-#pragma unroll
-        for (int j = 0; j < BPT; ++j) reinterpret_cast<T2 *>(S.snap)[i + j] = pos[i + j];
-      }
-    } else if (h.step == k || h.step == k + 1u) {
-      // h.step == k + 1 inside this launch can only mean that the thread owning this world's header has already
-      // taken the event-free branch below and bumped it: the threads of a world sit in different warps -- even in
-      // CTAs of different waves -- when the ball count is not a power of two, and then read the header after that
-      // write.  (Before this launch every running world is at step k; the collide kernel runs after it.)
-      const bool bumped = h.step != k;
-      // friction extension (0 = the reference): every velocity is scaled by s = 1 - friction*dt at the start of
-      // the step (semi-implicit Euler: the step then moves with the new velocity).  A uniform scaling of all
-      // velocities leaves every contact geometry unchanged and stretches every cached time of collision by
-      // 1/s, so the event-driven caches stay exact; worlds with friction still take the fast path.
-      const bool fric = P.friction != 0.0;
-      const T fs = fric ? (T)fmax(0.0, 1.0 - P.friction * P.dt) : T(1);
-      const T tmin_eff = fric ? (fs > T(0) ? h.tmin / fs : Lim<T>::inf()) : h.tmin;
-      if (bumped || (h.flags == 0u && tmin_eff > dt)) {
-        // event-free step: Dynamics.move_object for every ball (primitives.py:600-611)
-        const V2<T> g = mk<T>((T)P.gx, (T)P.gy);
-        const bool has_g = (P.gx != 0.0) || (P.gy != 0.0) || fric;
-        if (BPT == 2) {
-          T4 p = sp4, v = sv4;
-          T2 tc = stc2;
-          V2<T> p0 = mk<T>(p.x, p.y), p1 = mk<T>(p.z, p.w), v0 = mk<T>(v.x, v.y), v1 = mk<T>(v.z, v.w);
-          if (fric) {
-            v0 = v0 * fs; v1 = v1 * fs;
-            tc.x = fs > T(0) ? tc.x / fs : Lim<T>::inf();
-            tc.y = fs > T(0) ? tc.y / fs : Lim<T>::inf();
-            // the cached futureVel_ (dynamics.py:129) is a velocity too: it shrinks with the others, or a ball-ball
-            // contact n event-free steps after the scan would install a response too large by fs^-n
-            T4 *gaux = reinterpret_cast<T4 *>(S.aux);
-#pragma unroll
-            for (int j = 0; j < 2; ++j) {
-              T4 a = ld4(gaux + i + j);
-              a.z = a.z * fs; a.w = a.w * fs;
-              st4(gaux + i + j, a);
-            }
-          }
-          move_ball(p0, v0, dt, g);
-          move_ball(p1, v1, dt, g);
-          tc.x = tc.x - dt;
-          tc.y = tc.y - dt;
-          T4 po;
-          po.x = p0.x; po.y = p0.y; po.z = p1.x; po.w = p1.y;
-          st4(reinterpret_cast<T4 *>(pos + i), po);
-          if (has_g) {
-            T4 vo;
-            vo.x = v0.x; vo.y = v0.y; vo.z = v1.x; vo.w = v1.y;
-            st4(reinterpret_cast<T4 *>(vel + i), vo);
-          }
-          *reinterpret_cast<T2 *>(tcol + i) = tc;
-          if (traj) st4(reinterpret_cast<T4 *>(traj + ((long long)P.step_off * total + i) * 2), po);
-          if (S.snap) st4(reinterpret_cast<T4 *>(reinterpret_cast<T2 *>(S.snap) + i), po);
-        } else {
-          T2 p = sp1, v = sv1;
-          T tc = stc1;
-          V2<T> p0 = mk<T>(p.x, p.y), v0 = mk<T>(v.x, v.y);
-          if (fric) {
-            v0 = v0 * fs;
-            tc = fs > T(0) ? tc / fs : Lim<T>::inf();
-            T4 *gaux = reinterpret_cast<T4 *>(S.aux);
-            T4 a = ld4(gaux + i);
-            a.z = a.z * fs; a.w = a.w * fs;
-            st4(gaux + i, a);
-          }
-          move_ball(p0, v0, dt, g);
-          tc = tc - dt;
-          p.x = p0.x; p.y = p0.y;
-          pos[i] = p;
-          if (has_g) {
-            v.x = v0.x; v.y = v0.y;
-            vel[i] = v;
-          }
-          tcol[i] = tc;
-          if (traj) reinterpret_cast<T2 *>(traj)[(long long)P.step_off * total + i] = p;
-          if (S.snap) reinterpret_cast<T2 *>(S.snap)[i] = p;
-        }
-        if (duty) {
-          Hdr<T> o = h;
-          o.tmin = tmin_eff - dt;   // min_b (tCol_b - dt) == (min_b tCol_b) - dt: rounding is monotone
-          o.step = k + 1u;
-          reinterpret_cast<Hdr<T> *>(S.hdr)[w] = o;
-        }
-      } else if (duty) {
-        s_list[atomicAdd(&s_cnt, 1)] = w;   // a queued rescan or a collision inside this step: K2's
-      }
-    }
-  }
-  __syncthreads();
-  const int n = s_cnt;
-  if (n > 0) {
-    if (threadIdx.x == 0) s_base = atomicAdd(S.list_count + (k & 1u), n);
-    __syncthreads();
-    if ((int)threadIdx.x < n) S.list[s_base + threadIdx.x] = s_list[threadIdx.x];
-  }
-}
-
-// ------------------------------------------------------------------------------------
 // K2: collide
 //
 // One warp advances one world.  The 32 lanes are LB x G: LB = next power of two >= n_balls
@@ -211,6 +63,7 @@ struct WarpSmem {
 
 #define PPB_COLLIDE_WARPS 4
 #define PPB_K_NONE 0x7fff
+#define PPB_TICKET_WORLDS 8
 
 template <typename T, int LW>
 __device__ __forceinline__ T seg_min(T v) {
@@ -267,9 +120,16 @@ __device__ __forceinline__ void team_sync(int team) {
 // never has more than a handful of scan items.  Every warp of a team holds the whole (replicated) ball
 // state and takes the same decisions; only the scan is split, and its partial results are exchanged
 // through shared memory.
+//
+// The team keeps its world for all P.n_steps steps of the launch: positions, velocities, tCol_ and the
+// world's min tCol_ live in registers from step to step.  A step whose header says "no queued rescan and
+// min tCol_ > dt" is Dynamics.move_object for every ball (primitives.py:600-611) and nothing else; any
+// other step runs the event loop below.  The collision caches the event loop needs (nrmlCol_, futureVel_,
+// objCol_, the wall edges) are fetched when the first such step comes up.  HBM sees one read and one
+// write of the state per launch, plus the trajectory rows / position snapshots the caller asked for.
 template <typename T, int LB, int TW>
 __global__ void __launch_bounds__(PPB_COLLIDE_WARPS * 32)
-collide_kernel(StatePtrs S, Layout L, StepParams P, T *traj) {
+advance_kernel(StatePtrs S, Layout L, StepParams P, T *traj) {
   typedef typename MathOf<T>::type M;
   typedef typename Vec2<T>::type T2;
   typedef typename Vec4<T>::type T4;
@@ -287,18 +147,24 @@ collide_kernel(StatePtrs S, Layout L, StepParams P, T *traj) {
   const int gid = wt * G + grp;                // this lane's scan group
   const bool writer = (wt == 0) && (grp == 0); // the lane that owns ball bi's global state
   const int nB = L.n_balls, nWl = L.n_walls;
-  pdl_wait();   // the integrate kernel of this step (list, state) is complete and visible
-  const uint32_t k = (uint32_t)P.step_abs;
+  pdl_launch_dependents();   // the next launch of the stream may take its places; it waits for this grid to finish
+  pdl_wait();                // the previous launch (state, ticket counter) is complete and visible
+  const uint32_t k0 = (uint32_t)P.step_abs;
   const T dt = (T)P.dt;
   const V2<T> g = mk<T>((T)P.gx, (T)P.gy);
+  const bool has_g = (P.gx != 0.0) || (P.gy != 0.0);
   const T INF = Lim<T>::inf();
+  // friction extension (0 = the reference): every velocity is scaled by s = 1 - friction*dt at the start of
+  // the step (semi-implicit Euler: the step then moves with the new velocity).  A uniform scaling of all
+  // velocities leaves every contact geometry unchanged and stretches every cached time of collision by
+  // 1/s (the cached futureVel_ shrinks by s), so the event-driven caches stay exact.
+  const bool fric = (P.friction != 0.0) && !P.scan_only;
+  const T fs = fric ? (T)fmax(0.0, 1.0 - P.friction * P.dt) : T(1);
 
-  if (blockIdx.x == 0 && threadIdx.x == 0) {   // next step's list and ticket counter start empty
-    S.list_count[(k + 1u) & 1u] = 0;
-    S.list_count[2 + ((k + 1u) & 1u)] = 0;
-  }
-  const int count = S.list_count[k & 1u];
-  int *ticket = S.list_count + 2 + (k & 1u);
+  if (blockIdx.x == 0 && threadIdx.x == 0) S.list_count[2 + ((P.parity ^ 1) & 1)] = 0;   // next launch's tickets
+  int *ticket = S.list_count + 2 + (P.parity & 1);
+  const int count = S.n_worlds;
+  const long long total = (long long)count * nB;
 
   Hdr<T> *hdr = reinterpret_cast<Hdr<T> *>(S.hdr);
   T2 *gpos = reinterpret_cast<T2 *>(S.pos);
@@ -308,12 +174,7 @@ collide_kernel(StatePtrs S, Layout L, StepParams P, T *traj) {
   T *gtcol = reinterpret_cast<T *>(S.tcol);
   const T2 *gwall = reinterpret_cast<const T2 *>(S.wall);
 
-  unsigned long long cnt_iters = 0, cnt_rescans = 0;
-  // NB: small changes here flip ptxas between a 64-register allocation (two CTAs fit next to the render kernel's
-  // CTA when physics and render overlap) and an 80-register one.  Measured and rejected on B200: the first world
-  // of a warp taken from its grid index instead of a ticket (65,536 x 4 worlds: 26.7 -> 24.6 us per step, but
-  // 131,072 x 8 with frames: 407 -> 418 us) and one first-ticket atomic per CTA (same picture); forcing 64
-  // registers with a minimum-blocks launch bound made every workload slower.
+  unsigned long long cnt_iters = 0, cnt_rescans = 0, cnt_slow = 0;
   int idx = 0;
   if (TW == 1) {
     if (lane == 0) idx = atomicAdd(ticket, 1);
@@ -325,257 +186,313 @@ collide_kernel(StatePtrs S, Layout L, StepParams P, T *traj) {
     team_sync<TW>(team);
   }
 
-  while (idx < count) {
+  // a ticket is PPB_TICKET_WORLDS consecutive worlds: one same-address atomic per world would cost the launch
+  // about as much as eight event-free steps of the whole batch
+  while ((long long)idx * PPB_TICKET_WORLDS < count) {
     int idx_next = 0;
-    if (wt == 0 && lane == 0) idx_next = atomicAdd(ticket, 1);   // its latency hides behind this world's work
-    const int w = S.list[idx];
+    if (wt == 0 && lane == 0) idx_next = atomicAdd(ticket, 1);   // its latency hides behind these worlds' work
+    const int w_first = idx * PPB_TICKET_WORLDS;
+    const int w_end = min(count, w_first + PPB_TICKET_WORLDS);
+    for (int w = w_first; w < w_end; ++w) {
     const bool has_ball = bi < nB;
     const long long base = (long long)w * nB;
 
-    // ---- stage the world: ball state replicated over the lanes of a ball column, wall edges in smem ----
+    // ---- the world's moving state: replicated over the lanes of a ball column ----
+    const Hdr<T> h = hdr[w];
     V2<T> pos = mk<T>(0, 0), vel = pos, nrm = pos, fv = pos;
     T tc = INF, rad = T(-1), mass = T(1);
     int partner = -1;
-    uint32_t flags = 0u, nev_base = 0u;
-    if (lane == 0) {
-      flags = hdr[w].flags;
-      nev_base = S.nev[w];
-    }
     if (has_ball) {
       const T2 p = gpos[base + bi], v = gvel[base + bi], q = grm[base + bi];
-      const T4 a = ld4(gaux + base + bi);
       pos = mk<T>(p.x, p.y);
       vel = mk<T>(v.x, v.y);
       rad = q.x;
       mass = q.y;
-      nrm = mk<T>(a.x, a.y);
-      fv = mk<T>(a.z, a.w);
       tc = gtcol[base + bi];
-      partner = S.partner[base + bi];
-      if (P.friction != 0.0 && !P.scan_only) {   // friction extension: see integrate_kernel
-        const T fs = (T)fmax(0.0, 1.0 - P.friction * P.dt);
-        vel = vel * fs;
-        fv = fv * fs;
-        tc = fs > T(0) ? tc / fs : INF;
-      }
-    }
-    team_sync<TW>(team);   // the previous world's readers of the staging area are done
-    for (int e = wt * 32 + lane; e < nWl * 4; e += TW * 32) {
-      const T2 *wp = gwall + ((long long)w * nWl + (e >> 2)) * 4;
-      const T2 a = wp[e & 3], b = wp[(e + 1) & 3];
-      sm.edge[e] = M::make_edge(mk<T>(a.x, a.y), mk<T>(b.x, b.y));
-    }
-    flags = __shfl_sync(FULL, flags, 0);
-    nev_base = __shfl_sync(FULL, nev_base, 0);
-    if (writer) {
-      T2 q;
-      q.x = rad; q.y = mass;
-      sm.rm[bi] = q;
     }
     const bool active = has_ball && rad >= T(0);
+    int status = (int)PPB_STATUS_OF(h.flags);
+    bool pending = (h.flags & PPB_FLAG_PENDING) != 0u;
+    T mnt = h.tmin;
+    bool warm = false, staged = false, rescanned = false, vel_dirty = has_g || fric;
+    uint32_t nev_base = 0u, nev_local = 0u;
+    int s_done = 0;
+    const bool skip = P.scan_only && (!pending || status != 0);   // ppb_scan_async only drains non-empty queues
 
-    bool done = false;
-    bool pending = (flags & PPB_FLAG_PENDING) != 0u;
-    bool rescanned = false;
-    int err = 0, status = 0;
-    T tStep = T(0), mnt = INF;
-    uint32_t nev_local = 0;
-    int iters = 0;
-
-    for (;;) {
-      if (pending) {
-        // colQueue_ drain: time_to_collide_all for every ball of the world (primitives.py:634-638)
-        team_sync<TW>(team);
-        if (writer) {
-          T2 p, v;
-          p.x = pos.x; p.y = pos.y; v.x = vel.x; v.y = vel.y;
-          sm.pos[bi] = p;
-          sm.vel[bi] = v;
-        }
-        team_sync<TW>(team);
-        tc = INF;
-        partner = -1;
-        int kbest = PPB_K_NONE, kfv = -1, kerr = PPB_K_NONE;
-        V2<T> nb = nrm, fb = fv;
-        if (active) {
-          // The lane's share of the scan items, edges first, then balls.  The order of evaluation is
-          // free: every candidate carries its position k in the reference's visiting order and ties
-          // are broken on k, so the result equals the sequential strict-'<' scan.  Type-pure loops
-          // with independent trips let the tests of several items overlap in the pipeline.
-          const int nE = nWl << 2;
-#pragma unroll 4
-          for (int e = gid; e < nE; e += GT) {
-            // one edge of dynamics.get_toc_ball_wall (dynamics.py:20-59)
-            const int kk = L.edge_k[e];
-            T te;
-            V2<T> ne;
-            const int ee = M::edge_toc(pos, vel, rad, sm.edge[e], te, ne);
-            if (ee) {
-              if (kk < kerr) { kerr = kk; err = ee; }
-            } else if (te < tc || (te == tc && kk < kbest && kbest != PPB_K_NONE)) {
-              tc = te; kbest = kk; partner = e >> 2; nb = ne;
+    for (int s = 0; s < P.n_steps && !skip; ++s) {
+      if (status == 0) {
+        const T mnt_eff = fric ? (fs > T(0) ? mnt / fs : INF) : mnt;
+        if (!pending && !P.scan_only && mnt_eff > dt) {
+          // ---- event-free step: Dynamics.move_object for every ball (primitives.py:600-611) ----
+          if (fric) {
+            if (!warm) {   // the cached futureVel_ shrinks with the velocities
+              if (has_ball) {
+                const T4 a = ld4(gaux + base + bi);
+                nrm = mk<T>(a.x, a.y);
+                fv = mk<T>(a.z, a.w);
+                partner = S.partner[base + bi];
+              }
+              warm = true;
             }
+            vel = vel * fs;
+            fv = fv * fs;
+            tc = fs > T(0) ? tc / fs : INF;
           }
-#pragma unroll 2
-          for (int b2 = gid; b2 < nB; b2 += GT) {
-            const T2 q2 = sm.rm[b2];
-            if (b2 == bi || q2.x < T(0)) continue;
-            const int kk = L.ball_k[b2];
-            const T2 p2 = sm.pos[b2], v2 = sm.vel[b2];
-            const Toc<T> r = M::ball(pos, vel, rad, mass, mk<T>(p2.x, p2.y), mk<T>(v2.x, v2.y), q2.x, q2.y);
-            if (r.err) {
-              if (kk < kerr) { kerr = kk; err = r.err; }
-              continue;
-            }
-            if (r.has_fv && kk > kfv) { fb = r.fv; kfv = kk; }   // futureVel_: last partner in order (dynamics.py:129)
-            if (r.t < tc || (r.t == tc && kk < kbest && kbest != PPB_K_NONE)) {
-              tc = r.t; kbest = kk; partner = nWl + b2; nb = r.n;
-            }
+          if (active) {
+            move_ball(pos, vel, dt, g);
+            tc = tc - dt;
           }
-        }
-        // merge the partial scans of every ball: inside the warp ...
-#pragma unroll
-        for (int o = LB; o < 32; o <<= 1) {
-          const T ot = shfl_xor_t(tc, o);
-          const int ok = __shfl_xor_sync(FULL, kbest, o), op = __shfl_xor_sync(FULL, partner, o);
-          const T onx = shfl_xor_t(nb.x, o), ony = shfl_xor_t(nb.y, o);
-          if (ot < tc || (ot == tc && ok < kbest)) {
-            tc = ot; kbest = ok; partner = op; nb = mk<T>(onx, ony);
-          }
-          const int okf = __shfl_xor_sync(FULL, kfv, o);
-          const T ofx = shfl_xor_t(fb.x, o), ofy = shfl_xor_t(fb.y, o);
-          if (okf > kfv) { kfv = okf; fb = mk<T>(ofx, ofy); }
-          const int oke = __shfl_xor_sync(FULL, kerr, o), oe = __shfl_xor_sync(FULL, err, o);
-          if (oke < kerr) { kerr = oke; err = oe; }
-        }
-        // ... and across the warps of the team
-        if (TW > 1) {
-          if (grp == 0) {
-            ScanPart<T> sp;
-            sp.t = tc; sp.nx = nb.x; sp.ny = nb.y; sp.fx = fb.x; sp.fy = fb.y;
-            sp.k = kbest; sp.partner = partner; sp.kfv = kfv; sp.kerr = kerr; sp.err = err;
-            ts.part[wt][bi] = sp;
-          }
-          team_sync<TW>(team);
-#pragma unroll
-          for (int u = 0; u < TW; ++u) {
-            if (u == wt) continue;
-            const ScanPart<T> o = ts.part[u][bi];
-            if (o.t < tc || (o.t == tc && o.k < kbest)) {
-              tc = o.t; kbest = o.k; partner = o.partner; nb = mk<T>(o.nx, o.ny);
-            }
-            if (o.kfv > kfv) { kfv = o.kfv; fb = mk<T>(o.fx, o.fy); }
-            if (o.kerr < kerr) { kerr = o.kerr; err = o.err; }
-          }
-        }
-        // an item after a raising one is never visited by the reference; the world halts anyway
-        if (kbest != PPB_K_NONE) nrm = nb;
-        if (kfv >= 0) fv = fb;
-        rescanned = true;
-        pending = false;
-        ++cnt_rescans;
-        // the first ball (in order) whose scan raised decides the status
-        const int e = first_error<LB>(err);
-        if (e) {
-          status = e;
-          done = true;
-        }
-      }
-      if (P.scan_only) {   // ppb_scan_async: the caches are up to date, nothing moves
-        if (!done) mnt = warp_min_all(active ? tc : INF);
-        break;
-      }
-      // mntCol / t  (primitives.py:641-650)
-      const T m = warp_min_all(active ? tc : INF);   // every group holds the same ball columns
-      T t = T(0);
-      if (!done) {
-        mnt = m;
-        const T rem = dt - tStep;
-        t = (rem < mnt) ? rem : mnt;
-        if (t <= T(0)) done = true;
-        else if (++iters > P.max_substeps) {
-          status = PPB_ST_ITER_LIMIT;
-          done = true;
-        }
-      }
-      if (done) break;
-      const bool hit = active && (tc <= t);   // step_object, primitives.py:617
-      const unsigned evm = __ballot_sync(FULL, hit && grp == 0);
-      if (evm) {
-        // one record per resolve_collision call, in ball order (written by the first warp of the team)
-        const int n_ev = __popc(evm);
-        if (S.event_capacity > 0 && wt == 0) {
-          unsigned long long slot0 = 0;
-          if (lane == 0) slot0 = atomicAdd(S.counters + 0, (unsigned long long)n_ev);
-          slot0 = __shfl_sync(FULL, slot0, 0);
-          if (hit && grp == 0) {
-            const int ord = __popc(evm & ((1u << lane) - 1u));
-            const unsigned long long slot = slot0 + ord;
-            if ((long long)slot < S.event_capacity) {
-              ppb_event ev;
-              ev.world = w;
-              ev.seq = (int32_t)(nev_base + nev_local + ord);
-              ev.step = (int32_t)k;
-              ev.ball = (int16_t)bi;
-              ev.partner = (int16_t)partner;
-              S.events[slot] = ev;
-            }
-          }
-        }
-        nev_local += n_ev;
-        pending = true;   // add_all_dynamic_collision_queue, primitives.py:697-700
-      }
-      if (active) {
-        if (hit) {  // resolve_collision, primitives.py:659-681
-          if (!(tc == t)) err = PPB_ST_ASSERT_TCOL_EQ;
-          move_ball(pos, vel, tc, g);
-          tc = tc - tc;
-          if (!(tc > T(-1e-8))) err = PPB_ST_ASSERT_TCOL_NEG;
-          if (partner >= 0 && partner < nWl) vel = M::reflect(nrm, vel);
-          else vel = fv;
+          mnt = mnt_eff - dt;   // min_b (tCol_b - dt) == (min_b tCol_b) - dt: rounding is monotone
+          ++s_done;
         } else {
-          move_ball(pos, vel, t, g);
-          tc = tc - t;
-          if (!(tc > T(-1e-8))) err = PPB_ST_ASSERT_TCOL_NEG;  // primitives.py:610
+          // ---- the event-driven loop of Dynamics.step (primitives.py:628-700) ----
+          if (!warm) {
+            if (has_ball) {
+              const T4 a = ld4(gaux + base + bi);
+              nrm = mk<T>(a.x, a.y);
+              fv = mk<T>(a.z, a.w);
+              partner = S.partner[base + bi];
+            }
+            warm = true;
+          }
+          if (!staged) {
+            // first event step of this world in this launch: fetch the event sequence number, stage the wall
+            // edges and radii / masses (the staging area is shared by the team: its previous readers must be done)
+            nev_base = S.nev[w];
+            team_sync<TW>(team);
+            for (int e = wt * 32 + lane; e < nWl * 4; e += TW * 32) {
+              const T2 *wp = gwall + ((long long)w * nWl + (e >> 2)) * 4;
+              const T2 a = wp[e & 3], b = wp[(e + 1) & 3];
+              sm.edge[e] = M::make_edge(mk<T>(a.x, a.y), mk<T>(b.x, b.y));
+            }
+            if (writer) {
+              T2 q;
+              q.x = rad; q.y = mass;
+              sm.rm[bi] = q;
+            }
+            staged = true;
+          }
+          if (fric) {
+            vel = vel * fs;
+            fv = fv * fs;
+            tc = fs > T(0) ? tc / fs : INF;
+          }
+          vel_dirty = true;
+          ++cnt_slow;
+          const uint32_t k = k0 + (uint32_t)s;
+          bool done = false;
+          int err = 0;
+          T tStep = T(0);
+          int iters = 0;
+          for (;;) {
+            if (pending) {
+              // colQueue_ drain: time_to_collide_all for every ball of the world (primitives.py:634-638)
+              team_sync<TW>(team);
+              if (writer) {
+                T2 p, v;
+                p.x = pos.x; p.y = pos.y; v.x = vel.x; v.y = vel.y;
+                sm.pos[bi] = p;
+                sm.vel[bi] = v;
+              }
+              team_sync<TW>(team);
+              tc = INF;
+              partner = -1;
+              int kbest = PPB_K_NONE, kfv = -1, kerr = PPB_K_NONE;
+              V2<T> nb = nrm, fb = fv;
+              if (active) {
+                // The lane's share of the scan items, edges first, then balls.  The order of evaluation is
+                // free: every candidate carries its position k in the reference's visiting order and ties
+                // are broken on k, so the result equals the sequential strict-'<' scan.  Type-pure loops
+                // with independent trips let the tests of several items overlap in the pipeline.
+                const int nE = nWl << 2;
+#pragma unroll 4
+                for (int e = gid; e < nE; e += GT) {
+                  // one edge of dynamics.get_toc_ball_wall (dynamics.py:20-59)
+                  const int kk = L.edge_k[e];
+                  T te;
+                  V2<T> ne;
+                  const int ee = M::edge_toc(pos, vel, rad, sm.edge[e], te, ne);
+                  if (ee) {
+                    if (kk < kerr) { kerr = kk; err = ee; }
+                  } else if (te < tc || (te == tc && kk < kbest && kbest != PPB_K_NONE)) {
+                    tc = te; kbest = kk; partner = e >> 2; nb = ne;
+                  }
+                }
+#pragma unroll 2
+                for (int b2 = gid; b2 < nB; b2 += GT) {
+                  const T2 q2 = sm.rm[b2];
+                  if (b2 == bi || q2.x < T(0)) continue;
+                  const int kk = L.ball_k[b2];
+                  const T2 p2 = sm.pos[b2], v2 = sm.vel[b2];
+                  const Toc<T> r = M::ball(pos, vel, rad, mass, mk<T>(p2.x, p2.y), mk<T>(v2.x, v2.y), q2.x, q2.y);
+                  if (r.err) {
+                    if (kk < kerr) { kerr = kk; err = r.err; }
+                    continue;
+                  }
+                  if (r.has_fv && kk > kfv) { fb = r.fv; kfv = kk; }   // futureVel_: last partner in order (dynamics.py:129)
+                  if (r.t < tc || (r.t == tc && kk < kbest && kbest != PPB_K_NONE)) {
+                    tc = r.t; kbest = kk; partner = nWl + b2; nb = r.n;
+                  }
+                }
+              }
+              // merge the partial scans of every ball: inside the warp ...
+#pragma unroll
+              for (int o = LB; o < 32; o <<= 1) {
+                const T ot = shfl_xor_t(tc, o);
+                const int ok = __shfl_xor_sync(FULL, kbest, o), op = __shfl_xor_sync(FULL, partner, o);
+                const T onx = shfl_xor_t(nb.x, o), ony = shfl_xor_t(nb.y, o);
+                if (ot < tc || (ot == tc && ok < kbest)) {
+                  tc = ot; kbest = ok; partner = op; nb = mk<T>(onx, ony);
+                }
+                const int okf = __shfl_xor_sync(FULL, kfv, o);
+                const T ofx = shfl_xor_t(fb.x, o), ofy = shfl_xor_t(fb.y, o);
+                if (okf > kfv) { kfv = okf; fb = mk<T>(ofx, ofy); }
+                const int oke = __shfl_xor_sync(FULL, kerr, o), oe = __shfl_xor_sync(FULL, err, o);
+                if (oke < kerr) { kerr = oke; err = oe; }
+              }
+              // ... and across the warps of the team
+              if (TW > 1) {
+                if (grp == 0) {
+                  ScanPart<T> sp;
+                  sp.t = tc; sp.nx = nb.x; sp.ny = nb.y; sp.fx = fb.x; sp.fy = fb.y;
+                  sp.k = kbest; sp.partner = partner; sp.kfv = kfv; sp.kerr = kerr; sp.err = err;
+                  ts.part[wt][bi] = sp;
+                }
+                team_sync<TW>(team);
+#pragma unroll
+                for (int u = 0; u < TW; ++u) {
+                  if (u == wt) continue;
+                  const ScanPart<T> o = ts.part[u][bi];
+                  if (o.t < tc || (o.t == tc && o.k < kbest)) {
+                    tc = o.t; kbest = o.k; partner = o.partner; nb = mk<T>(o.nx, o.ny);
+                  }
+                  if (o.kfv > kfv) { kfv = o.kfv; fb = mk<T>(o.fx, o.fy); }
+                  if (o.kerr < kerr) { kerr = o.kerr; err = o.err; }
+                }
+              }
+              // an item after a raising one is never visited by the reference; the world halts anyway
+              if (kbest != PPB_K_NONE) nrm = nb;
+              if (kfv >= 0) fv = fb;
+              rescanned = true;
+              pending = false;
+              ++cnt_rescans;
+              // the first ball (in order) whose scan raised decides the status
+              const int e = first_error<LB>(err);
+              if (e) {
+                status = e;
+                done = true;
+              }
+            }
+            if (P.scan_only) {   // ppb_scan_async: the caches are up to date, nothing moves
+              if (!done) mnt = warp_min_all(active ? tc : INF);
+              break;
+            }
+            // mntCol / t  (primitives.py:641-650)
+            const T m = warp_min_all(active ? tc : INF);   // every group holds the same ball columns
+            T t = T(0);
+            if (!done) {
+              mnt = m;
+              const T rem = dt - tStep;
+              t = (rem < mnt) ? rem : mnt;
+              if (t <= T(0)) done = true;
+              else if (++iters > P.max_substeps) {
+                status = PPB_ST_ITER_LIMIT;
+                done = true;
+              }
+            }
+            if (done) break;
+            const bool hit = active && (tc <= t);   // step_object, primitives.py:617
+            const unsigned evm = __ballot_sync(FULL, hit && grp == 0);
+            if (evm) {
+              // one record per resolve_collision call, in ball order (written by the first warp of the team)
+              const int n_ev = __popc(evm);
+              if (S.event_capacity > 0 && wt == 0) {
+                unsigned long long slot0 = 0;
+                if (lane == 0) slot0 = atomicAdd(S.counters + 0, (unsigned long long)n_ev);
+                slot0 = __shfl_sync(FULL, slot0, 0);
+                if (hit && grp == 0) {
+                  const int ord = __popc(evm & ((1u << lane) - 1u));
+                  const unsigned long long slot = slot0 + ord;
+                  if ((long long)slot < S.event_capacity) {
+                    ppb_event ev;
+                    ev.world = w;
+                    ev.seq = (int32_t)(nev_base + nev_local + ord);
+                    ev.step = (int32_t)k;
+                    ev.ball = (int16_t)bi;
+                    ev.partner = (int16_t)partner;
+                    S.events[slot] = ev;
+                  }
+                }
+              }
+              nev_local += n_ev;
+              pending = true;   // add_all_dynamic_collision_queue, primitives.py:697-700
+            }
+            if (active) {
+              if (hit) {  // resolve_collision, primitives.py:659-681
+                if (!(tc == t)) err = PPB_ST_ASSERT_TCOL_EQ;
+                move_ball(pos, vel, tc, g);
+                tc = tc - tc;
+                if (!(tc > T(-1e-8))) err = PPB_ST_ASSERT_TCOL_NEG;
+                if (partner >= 0 && partner < nWl) vel = M::reflect(nrm, vel);
+                else vel = fv;
+              } else {
+                move_ball(pos, vel, t, g);
+                tc = tc - t;
+                if (!(tc > T(-1e-8))) err = PPB_ST_ASSERT_TCOL_NEG;  // primitives.py:610
+              }
+            }
+            {
+              const int e = first_error<LB>(err);
+              if (e) {
+                status = e;
+                break;
+              }
+            }
+            tStep += t;
+            ++cnt_iters;
+          }
+          if (status == 0 && !P.scan_only) ++s_done;
         }
       }
-      {
-        const int e = first_error<LB>(err);
-        if (e) {
-          status = e;
-          break;
+      // ---- what the caller wants to see of this step (a halted world keeps recording where it stopped) ----
+      if (has_ball && writer && !P.scan_only) {
+        T2 p;
+        p.x = pos.x; p.y = pos.y;
+        if (traj) reinterpret_cast<T2 *>(traj)[(long long)(P.step_off + s) * total + base + bi] = p;
+        if (S.snap && P.draw_every > 0 && s >= P.draw_first) {
+          const int r = s - P.draw_first, slot = r / P.draw_every;
+          if (r == slot * P.draw_every) reinterpret_cast<T2 *>(S.snap)[(long long)slot * total + base + bi] = p;
         }
       }
-      tStep += t;
-      ++cnt_iters;
     }
 
     // ---- write back (the owning lane of every ball) ----
-    if (has_ball && writer) {
-      T2 p, v;
-      p.x = pos.x; p.y = pos.y; v.x = vel.x; v.y = vel.y;
-      gpos[base + bi] = p;
-      gvel[base + bi] = v;
-      gtcol[base + bi] = tc;
-      if (rescanned || (P.friction != 0.0 && !P.scan_only)) {   // friction rescaled the cached futureVel_ above
-        T4 a;
-        a.x = nrm.x; a.y = nrm.y; a.z = fv.x; a.w = fv.y;
-        st4(gaux + base + bi, a);
-        S.partner[base + bi] = partner;
+    if (!skip && (int)PPB_STATUS_OF(h.flags) == 0) {
+      if (has_ball && writer) {
+        T2 p, v;
+        p.x = pos.x; p.y = pos.y; v.x = vel.x; v.y = vel.y;
+        gpos[base + bi] = p;
+        if (vel_dirty) gvel[base + bi] = v;
+        gtcol[base + bi] = tc;
+        if (rescanned || (fric && warm)) {
+          T4 a;
+          a.x = nrm.x; a.y = nrm.y; a.z = fv.x; a.w = fv.y;
+          st4(gaux + base + bi, a);
+          S.partner[base + bi] = partner;
+        }
       }
-      if (traj) reinterpret_cast<T2 *>(traj)[((long long)P.step_off * S.n_worlds + w) * nB + bi] = p;
-      if (S.snap) reinterpret_cast<T2 *>(S.snap)[base + bi] = p;
+      if (wt == 0 && lane == 0) {
+        Hdr<T> o;
+        memset(&o, 0, sizeof o);
+        o.tmin = mnt;
+        o.step = h.step + (uint32_t)s_done;   // a halted world keeps the index of the step it raised in
+        o.flags = status ? ((uint32_t)status << 8) : (pending ? PPB_FLAG_PENDING : 0u);
+        hdr[w] = o;
+        if (nev_local) S.nev[w] = nev_base + nev_local;
+        if (S.event_capacity <= 0 && nev_local) atomicAdd(S.counters + 0, (unsigned long long)nev_local);
+      }
     }
-    if (wt == 0 && lane == 0) {
-      Hdr<T> o;
-      memset(&o, 0, sizeof o);
-      o.tmin = mnt;
-      o.step = (status || P.scan_only) ? k : k + 1u;  // a halted world keeps the index of the step it raised in
-      o.flags = status ? ((uint32_t)status << 8) : (pending ? PPB_FLAG_PENDING : 0u);
-      hdr[w] = o;
-      if (nev_local) S.nev[w] = nev_base + nev_local;
-      if (S.event_capacity <= 0 && nev_local) atomicAdd(S.counters + 0, (unsigned long long)nev_local);
-    }
+    }   // worlds of this ticket
     if (TW == 1) {
       idx = __shfl_sync(FULL, idx_next, 0);
     } else {
@@ -586,24 +503,12 @@ collide_kernel(StatePtrs S, Layout L, StepParams P, T *traj) {
     }
   }
   // per-team statistics (every lane counted the same)
-  if (wt == 0 && lane == 0 && (cnt_iters | cnt_rescans)) {
+  if (wt == 0 && lane == 0 && (cnt_iters | cnt_rescans | cnt_slow)) {
+    atomicAdd(S.counters + 1, cnt_slow);
     atomicAdd(S.counters + 2, cnt_iters);
     atomicAdd(S.counters + 3, cnt_rescans);
   }
-  if (blockIdx.x == 0 && threadIdx.x == 0 && count > 0) atomicAdd(S.counters + 1, (unsigned long long)count);
 }
-
-// ppb_scan_async: every running world whose collision queue is non-empty goes on the collide list
-template <typename T>
-__global__ void list_pending_kernel(StatePtrs S, int step_abs) {
-  const int w = blockIdx.x * blockDim.x + threadIdx.x;
-  if (w >= S.n_worlds) return;
-  const Hdr<T> h = reinterpret_cast<const Hdr<T> *>(S.hdr)[w];
-  const uint32_t k = (uint32_t)step_abs;
-  if (PPB_STATUS_OF(h.flags) == 0u && (h.flags & PPB_FLAG_PENDING) && h.step == k)
-    S.list[atomicAdd(S.list_count + (k & 1u), 1)] = w;
-}
-
 
 // Dynamics._include_object for a range of worlds (primitives.py:556-563): tCol_ = 0, objCol_ = None,
 // every ball queued; also used by add_all_dynamic_collision_queue (keep_cache = 1)

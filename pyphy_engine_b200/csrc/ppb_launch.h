@@ -10,11 +10,11 @@ template <typename T>
 struct Launch {
   static size_t elem_size() { return sizeof(T); }
   static size_t hdr_size();
-  static cudaError_t integrate(const StatePtrs &S, int n_balls, const StepParams &P, void *traj, cudaStream_t st);
-  static cudaError_t collide(const StatePtrs &S, const Layout &L, const StepParams &P, void *traj, int grid,
+  // P.n_steps x Dynamics.step for every world in one launch (grid from advance_grid: persistent CTAs, worlds handed
+  // out by tickets)
+  static cudaError_t advance(const StatePtrs &S, const Layout &L, const StepParams &P, void *traj, int grid,
                              cudaStream_t st);
-  static int collide_grid(int n_worlds, int sm_count);
-  static cudaError_t list_pending(const StatePtrs &S, int32_t step_abs, cudaStream_t st);
+  static int advance_grid(int n_worlds, int n_balls, int sm_count);
   // WallRC of worlds [world0, world0 + count)
   static cudaError_t wall_cache(const StatePtrs &S, const Layout &L, const RenderLayout &RL, int world0, int count,
                                 cudaStream_t st);

@@ -41,46 +41,32 @@ template <typename T>
 size_t Launch<T>::hdr_size() { return sizeof(Hdr<T>); }
 
 template <typename T>
-cudaError_t Launch<T>::integrate(const StatePtrs &S, int n_balls, const StepParams &P, void *traj, cudaStream_t st) {
-  const long long total = (long long)S.n_worlds * n_balls;
-  if (total == 0) return cudaSuccess;
-  if ((n_balls & 1) == 0) {
-    const long long thr = total / 2;
-    return launch_pdl(integrate_kernel<T, 2>, dim3((unsigned)((thr + 255) / 256)), dim3(256), 0, st, S, n_balls, P, (T *)traj);
-  }
-  return launch_pdl(integrate_kernel<T, 1>, dim3((unsigned)((total + 255) / 256)), dim3(256), 0, st, S, n_balls, P, (T *)traj);
-}
-
-template <typename T>
-int Launch<T>::collide_grid(int n_worlds, int sm_count) {
+int Launch<T>::advance_grid(int n_worlds, int n_balls, int sm_count) {
   int occ = 0;
-  cudaOccupancyMaxActiveBlocksPerMultiprocessor(&occ, collide_kernel<T, 8, 1>, PPB_COLLIDE_WARPS * 32, 0);
+  if (n_balls <= 8) cudaOccupancyMaxActiveBlocksPerMultiprocessor(&occ, advance_kernel<T, 8, 1>, PPB_COLLIDE_WARPS * 32, 0);
+  else if (n_balls <= 16) cudaOccupancyMaxActiveBlocksPerMultiprocessor(&occ, advance_kernel<T, 16, 2>, PPB_COLLIDE_WARPS * 32, 0);
+  else cudaOccupancyMaxActiveBlocksPerMultiprocessor(&occ, advance_kernel<T, 32, 4>, PPB_COLLIDE_WARPS * 32, 0);
   if (occ < 1) occ = 1;
-  const int need = (n_worlds + PPB_COLLIDE_WARPS - 1) / PPB_COLLIDE_WARPS;   // one world per warp at a time
+  const int tw = n_balls <= 8 ? 1 : (n_balls <= 16 ? 2 : 4);
+  const int teams = PPB_COLLIDE_WARPS / tw;
+  const int need = (n_worlds + teams * PPB_TICKET_WORLDS - 1) / (teams * PPB_TICKET_WORLDS);   // one ticket per team at a time
   int grid = sm_count * occ;
   if (grid > need) grid = need;
   return grid < 1 ? 1 : grid;
 }
 
 template <typename T>
-cudaError_t Launch<T>::collide(const StatePtrs &S, const Layout &L, const StepParams &P, void *traj, int grid,
+cudaError_t Launch<T>::advance(const StatePtrs &S, const Layout &L, const StepParams &P, void *traj, int grid,
                                cudaStream_t st) {
   const int nb = L.n_balls;
   const dim3 blk(PPB_COLLIDE_WARPS * 32);
   // lanes per world: one warp up to 8 balls, a team of 2 warps for 16, of 4 warps for 32
-  if (nb <= 1) return launch_pdl(collide_kernel<T, 1, 1>, dim3(grid), blk, 0, st, S, L, P, (T *)traj);
-  else if (nb <= 2) return launch_pdl(collide_kernel<T, 2, 1>, dim3(grid), blk, 0, st, S, L, P, (T *)traj);
-  else if (nb <= 4) return launch_pdl(collide_kernel<T, 4, 1>, dim3(grid), blk, 0, st, S, L, P, (T *)traj);
-  else if (nb <= 8) return launch_pdl(collide_kernel<T, 8, 1>, dim3(grid), blk, 0, st, S, L, P, (T *)traj);
-  else if (nb <= 16) return launch_pdl(collide_kernel<T, 16, 2>, dim3(grid), blk, 0, st, S, L, P, (T *)traj);
-  else return launch_pdl(collide_kernel<T, 32, 4>, dim3(grid), blk, 0, st, S, L, P, (T *)traj);
-  return cudaGetLastError();
-}
-
-template <typename T>
-cudaError_t Launch<T>::list_pending(const StatePtrs &S, int32_t step_abs, cudaStream_t st) {
-  list_pending_kernel<T><<<(S.n_worlds + 255) / 256, 256, 0, st>>>(S, step_abs);
-  return cudaGetLastError();
+  if (nb <= 1) return launch_pdl(advance_kernel<T, 1, 1>, dim3(grid), blk, 0, st, S, L, P, (T *)traj);
+  else if (nb <= 2) return launch_pdl(advance_kernel<T, 2, 1>, dim3(grid), blk, 0, st, S, L, P, (T *)traj);
+  else if (nb <= 4) return launch_pdl(advance_kernel<T, 4, 1>, dim3(grid), blk, 0, st, S, L, P, (T *)traj);
+  else if (nb <= 8) return launch_pdl(advance_kernel<T, 8, 1>, dim3(grid), blk, 0, st, S, L, P, (T *)traj);
+  else if (nb <= 16) return launch_pdl(advance_kernel<T, 16, 2>, dim3(grid), blk, 0, st, S, L, P, (T *)traj);
+  else return launch_pdl(advance_kernel<T, 32, 4>, dim3(grid), blk, 0, st, S, L, P, (T *)traj);
 }
 
 template <typename T>

@@ -36,5 +36,8 @@ def test_traffic_and_peaks_helpers():
     assert peak > 1000 and isinstance(src, str)
     t = bench.load_traffic("render")
     assert t is None or t > 1e9
-    assert bench._bytes_k2_per_world_step(4) == 416          # 24N + 16S + 16N at N = 4, S = 16
-    assert bench.BYTES_K3_PER_FRAME == 16384 and bench.BYTES_K1_PER_BALL_STEP == 32
+    assert bench.BYTES_K3_PER_FRAME == 16384
+    # one advance launch: header read + written, 28 B read + 12 B written per ball, 8 B per ball and snapshot
+    assert bench._bytes_advance_per_launch(1, 8, 16, 16) == 32 + 8 * 40 + 16 * 8 * 8
+    ref = bench.load_python_reference()
+    assert "unavailable" in ref or ref["config4_sample_1_process"] > 100

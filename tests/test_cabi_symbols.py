@@ -70,10 +70,9 @@ def test_argument_validation_happens_before_cuda():
 
 
 def test_register_budget_of_overlapping_kernels():
-    """The render kernel (one 384-thread CTA per SM) and two fp32 collide CTAs share an SM when the physics
-    of step k+1 overlaps the render of step k: 384 * 120 + 2 * 128 * 64 <= 65,536 registers.  ptxas reaches
-    the 64 by itself and small source changes make it choose 80 (then only one collide CTA fits and the
-    pipelined step is ~3 % slower on B200) -- this test is the tripwire."""
+    """The render kernel (one 384-thread CTA per SM) and two fp32 advance CTAs share an SM while the physics of
+    the next chunk of steps overlaps the renders of the current one: 384 * 120 + 2 * 128 * regs <= 65,536
+    registers, i.e. at most 76 for the physics kernel -- this test is the tripwire."""
     import re
     import shutil
     import subprocess
@@ -91,10 +90,10 @@ def test_register_budget_of_overlapping_kernels():
         m = re.search(r"REG:(\d+)", line)
         if m and name:
             regs[name] = int(m.group(1))
-    collide = {k: v for k, v in regs.items() if "collide_kernelIfLi" in k and "ELi1E" in k}   # fp32, one warp per world
+    collide = {k: v for k, v in regs.items() if "advance_kernelIfLi" in k and "ELi1E" in k}   # fp32, one warp per world
     render = {k: v for k, v in regs.items() if "render_tile_kernelIf" in k}
     assert collide and render, sorted(regs)
-    assert max(collide.values()) <= 64, collide
+    assert max(collide.values()) <= 76, collide
     assert max(render.values()) <= 120, render
     assert 384 * max(render.values()) + 2 * 128 * max(collide.values()) <= 65536
 

@@ -189,6 +189,49 @@ def test_pipelined_ring_equals_serial_stepping(n, nb):
     assert np.array_equal(pa, pb) and np.array_equal(va, vb)
 
 
+@pytest.mark.parametrize("steps,every,slots", [(40, 1, 5), (50, 3, 16), (70, 7, 3), (33, 2, 40)])
+def test_chunked_advance_launches_equal_single_steps(steps, every, slots):
+    """One advance launch covers up to 16 drawn steps (their position snapshots feed the render launches that follow)
+    and the steps after the last drawn one run without snapshots: frames, trajectories and final state must equal
+    stepping and rendering one step at a time, whatever the render period and the ring size."""
+    import torch
+    from pyphy_engine_b200 import sampler
+    from pyphy_engine_b200.engine import WorldBatch
+    n, nb = 3000, 8
+    W = sampler.sample_rect_worlds(n, nb, seed=21, **sampler.scaled64_params(nb))
+
+    def make():
+        wb = WorldBatch(n, nb, 4, dtype="f32", canvas=(64, 64), max_substeps=64)
+        wb.set_walls(W["wall"])
+        wb.set_balls(W["pos"], W["vel"] * 6.0, W["rad"], W["mass"])
+        wb.set_styles([(1, GRAY, BLACK)] * nb, [(0, RED)] * 4, 3, 3)
+        return wb
+
+    a, b = make(), make()
+    ring = torch.zeros((slots, n, 64, 64, 4), dtype=torch.uint8, device="cuda")
+    traj = torch.zeros((steps, n, nb, 2), dtype=torch.float32, device="cuda")
+    a.step_ring_async(steps, ring, every, traj=traj)
+    torch.cuda.synchronize()
+    n_draws = steps // every
+    frames = {}
+    for s in range(steps):
+        t, _ = b.step(1, record_traj=True)
+        assert torch.equal(traj[s], t[0]), s
+        if (s + 1) % every == 0:
+            frames[(s + 1) // every - 1] = b.render().clone()
+    for d in range(max(0, n_draws - slots), n_draws):                 # the ring keeps the last `slots` frames
+        assert torch.equal(ring[d % slots], frames[d]), d
+    pa, va = a.get_balls()
+    pb, vb = b.get_balls()
+    assert np.array_equal(pa, pb) and np.array_equal(va, vb)
+    sa, ka = a.get_status()
+    sb, kb = b.get_status()
+    assert np.array_equal(sa, sb) and np.array_equal(ka, kb)
+    ea, _ = a.read_events()
+    eb, _ = b.read_events()
+    assert np.array_equal(ea, eb)
+
+
 def test_full_size_frame_properties():
     """BASELINE configs[3] shard at full size (131,072 worlds x 8 balls, 64x64 frames): properties that
     do not need the oracle -- wall pixels per frame equal the analytic area of the cage rectangles, the

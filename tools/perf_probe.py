@@ -29,7 +29,7 @@ def run(n_worlds, n_balls, steps, render, dtype="f32", px64=True, warm=100, max_
                   int(W["rad"].min()), int(W["rad"].max()))
     frames = None
     if render:
-        frames = torch.empty((1, n_worlds, canvas[1], canvas[0], 4), dtype=torch.uint8, device="cuda")
+        frames = torch.empty((2, n_worlds, canvas[1], canvas[0], 4), dtype=torch.uint8, device="cuda")
     wb.step_async(warm)
     torch.cuda.synchronize()
     c0 = wb.counters()
@@ -37,25 +37,21 @@ def run(n_worlds, n_balls, steps, render, dtype="f32", px64=True, warm=100, max_
     e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
     e0.record()
     if render:
-        for _ in range(steps):
-            wb.step_async(1, None, frames, 1)
+        wb.step_ring_async(steps, frames, 1)
     else:
         wb.step_async(steps)
     e1.record()
     torch.cuda.synchronize()
     ms = e0.elapsed_time(e1)
     c1 = wb.counters()
-    if render:
-        kms, kn = [0, 0, 0], [0, 0, 0]
-    else:
-        kms, kn = wb.kernel_times()
+    kms, kn = wb.kernel_times()
     status, _ = wb.get_status()
     cw = c1["collide_world_steps"] - c0["collide_world_steps"]
     it = c1["collide_iterations"] - c0["collide_iterations"]
-    print("worlds %d balls %d dtype %s render %d: %.3f ms/step  %.3e ball-steps/s  | K1 %.1f us K2 %.1f us K3 %.1f us | "
-          "collide worlds/step %.1f%%  iters/collide-world %.2f  events/world-step %.3f  halted %d %s (sample %.1fs)" % (
+    print("worlds %d balls %d dtype %s render %d: %.3f ms/step  %.3e ball-steps/s  | advance %.1f us/launch (%d launches) render %.1f us/launch | "
+          "event-loop world-steps %.1f%%  iters/event-loop step %.2f  events/world-step %.3f  halted %d %s (sample %.1fs)" % (
               n_worlds, n_balls, dtype, render, ms / steps, n_worlds * n_balls * steps / ms * 1e3,
-              1e3 * kms[0] / max(kn[0], 1), 1e3 * kms[1] / max(kn[1], 1), 1e3 * kms[2] / max(kn[2], 1),
+              1e3 * kms[0] / max(kn[0], 1), kn[0], 1e3 * kms[2] / max(kn[2], 1),
               100.0 * cw / (n_worlds * steps), it / max(cw, 1), (c1["events"] - c0["events"]) / (n_worlds * steps),
               int((status != 0).sum()), np.bincount(status, minlength=10).tolist(), t_sample), flush=True)
     wb.close()

@@ -1,0 +1,27 @@
+"""Developer probe: time of one advance launch as a function of the steps it covers (physics only)."""
+import os
+import sys
+
+sys.path.insert(0, os.path.dirname(os.path.dirname(os.path.abspath(__file__))))
+import torch  # noqa: E402
+from pyphy_engine_b200 import sampler  # noqa: E402
+from pyphy_engine_b200.engine import WorldBatch  # noqa: E402
+
+for N, NB in ((131072, 8), (65536, 4)):
+    W = sampler.sample_rect_worlds(N, NB, seed=1, **sampler.scaled64_params(NB))
+    wb = WorldBatch(N, NB, 4, dtype="f32", max_substeps=64)
+    wb.set_walls(W["wall"])
+    wb.set_balls(W["pos"], W["vel"], W["rad"], W["mass"])
+    wb.step_async(100)
+    e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+    for n in (1, 2, 4, 8, 16, 32, 64):
+        reps = max(4, 128 // n)
+        torch.cuda.synchronize()
+        e0.record()
+        for _ in range(reps):
+            wb.step_async(n)
+        e1.record()
+        torch.cuda.synchronize()
+        t = 1e3 * e0.elapsed_time(e1) / reps
+        print("%d x %d: %2d steps per launch: %.1f us per launch, %.1f us per step" % (N, NB, n, t, t / n), flush=True)
+    wb.close()
