@@ -359,6 +359,7 @@ def run_ours(args, rank, local_rank, world_size):
     wb.simulate_host(1, traj_hosts[1], frames_hosts[1], 1)
     barrier()
     e2e_checksum = 0
+    cp0 = wb.counters()
     t0 = time.perf_counter()
     for i in range(e2e_steps):
         wb.set_walls(W["wall"])                                       # host -> device: this step's input tables
@@ -371,7 +372,12 @@ def run_ours(args, rank, local_rank, world_size):
     e2e_checksum += int(frames_hosts[(e2e_steps - 1) & 1][0, :64].sum())
     barrier()
     e2e_s = time.perf_counter() - t0
+    cp1 = wb.counters()
     traj_host = traj_hosts[(e2e_steps - 1) & 1]
+    # bytes that crossed PCIe for the frames (run-length tokens + per-frame table; raw when a batch does not compress)
+    d2h_wire = (cp1["d2h_packed_bytes"] - cp0["d2h_packed_bytes"] + cp1["d2h_raw_bytes"] - cp0["d2h_raw_bytes"]) / e2e_steps \
+        + traj_host.numel() * 4
+    unpack_ms = 1e-3 * (cp1["unpack_us"] - cp0["unpack_us"]) / e2e_steps
 
     # ---- reductions: max time over ranks, totals over ranks ----
     stats = torch.tensor([ms, e2e_s, float(live), float(c1["events"] - c0["events"]), float(launches)],
@@ -455,8 +461,13 @@ def run_ours(args, rank, local_rank, world_size):
             "cpu_baseline": cpu,
             "e2e": {"value": live_total * N_BALLS * e2e_steps / e2e_s, "unit": "ball-steps/s",
                     "frames_per_sec": live_total * e2e_steps / e2e_s,
-                    "h2d_bytes_per_step": int(h2d), "d2h_bytes_per_step": int(d2h), "steps": e2e_steps,
-                    "api": "per step: WorldBatch.set_walls/set_balls (H2D) + simulate_host(wait=False) (ppb_simulate_host_async: step, render, D2H) + host_sync(keep_in_flight=1); two sets of pinned host buffers, so the upload of step i+1 overlaps the download of step i",
+                    "h2d_bytes_per_step": int(h2d), "d2h_bytes_per_step": int(d2h_wire),
+                    "delivered_bytes_per_step": int(d2h), "unpack_ms_per_step_rank0": unpack_ms, "steps": e2e_steps,
+                    "api": "per step: WorldBatch.set_walls/set_balls (H2D) + simulate_host(wait=False) (ppb_simulate_host_async: step, render, "
+                           "run-length pack on the device, D2H of the tokens, RGBA rebuilt in the caller's pinned array by the library's host "
+                           "threads) + host_sync(keep_in_flight=1); two sets of pinned host buffers, so the upload of step i+1 overlaps the "
+                           "download of step i; d2h_bytes_per_step = bytes that crossed PCIe, delivered_bytes_per_step = bytes of "
+                           "positions + RGBA frames the caller receives",
                     "numa_node_rank0": numa_node},
             "final_gather": gather_info,
             "f64_mode": f64_mode,

@@ -262,6 +262,15 @@ PPB_API int ppb_render_async(ppb_batch *b, uint8_t *frames_dev, void *stream);
 PPB_API int ppb_simulate_host(ppb_batch *b, int32_t n_steps, float *traj_host, uint8_t *frames_host,
                       int32_t render_every, void *stream);
 
+/* Frames reach the host run-length packed: a rendered canvas is opaque and mostly flat colour, so ppb_simulate_host*
+ * send rgb | run_length << 24 tokens over PCIe (about a seventh of the bytes of a 64x64 billiards frame) and a pool of
+ * host threads rebuilds the RGBA pixels in `frames_host`; the bytes delivered are exactly the device frames.  Frames
+ * that are not opaque or do not compress travel raw.
+ *
+ * ppb_download_frames: the same path for any device array of `n_frames` canvases ([n_frames][H][W][4] uint8, the
+ * batch's canvas size; e.g. the frames of ppb_step_async or a ring) -> `frames_host`; synchronous. */
+PPB_API int ppb_download_frames(ppb_batch *b, const uint8_t *frames_dev, int64_t n_frames, uint8_t *frames_host, void *stream);
+
 /* The same without waiting: returns once the steps and the device -> host copies are enqueued (the copies run on a
  * stream owned by the batch, behind the kernels).  The host buffers of a call are complete after
  * ppb_host_sync(b, 0, stream) -- or after ppb_host_sync(b, 1, stream) once a later call has been enqueued

@@ -95,6 +95,7 @@ SIGNATURES = {
     "ppb_render_async": (ctypes.c_int, [_vp, _vp, _vp]),
     "ppb_simulate_host": (ctypes.c_int, [_vp, _i32, _vp, _vp, _i32, _vp]),
     "ppb_simulate_host_async": (ctypes.c_int, [_vp, _i32, _vp, _vp, _i32, _vp]),
+    "ppb_download_frames": (ctypes.c_int, [_vp, _vp, ctypes.c_int64, _vp, _vp]),
     "ppb_host_sync": (ctypes.c_int, [_vp, _i32, _vp]),
     "ppb_crop_async": (ctypes.c_int, [_vp, _vp, _vp, _i32, _i32, _i32, _vp, _vp, _vp]),
     "ppb_collision_flags_async": (ctypes.c_int, [_vp, _i64, _i32, ctypes.c_float, _vp, _vp]),

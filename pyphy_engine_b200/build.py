@@ -23,6 +23,7 @@ UNITS = [
     ("ppb_f32.cu", ["-prec-div=false", "-prec-sqrt=false"]),
     ("ppb_f64.cu", ["-fmad=false"]),
     ("ppb_cairo.cu", ["-fmad=false"]),
+    ("ppb_pack.cu", []),
     ("ppb_api.cu", []),
 ]
 

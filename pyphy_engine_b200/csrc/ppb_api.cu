@@ -3,6 +3,7 @@
 // sequences the K1/K2/K3 launches of a step and the copy pipeline of ppb_simulate_host.
 #include <cuda_runtime.h>
 
+#include <algorithm>
 #include <cmath>
 #include <cstdarg>
 #include <cstdlib>
@@ -14,6 +15,7 @@
 #include <vector>
 
 #include "ppb_launch.h"
+#include "ppb_pack.h"
 
 using namespace ppb;
 
@@ -98,6 +100,10 @@ struct ppb_batch {
   unsigned sim_it = 0;   // staging buffers used so far (they alternate across ppb_simulate_host* calls)
   cudaEvent_t ev_call[2] = {nullptr, nullptr};   // end of the copies of the last two ppb_simulate_host* calls
   unsigned sim_calls = 0;
+  // frames of ppb_simulate_host* travel run-length packed and are rebuilt by host threads (ppb_pack.cu)
+  PackPipe *pack = nullptr;
+  bool pack_frames = true;
+  long long pack_mark[2] = {0, 0};   // jobs submitted before each of the last two ppb_simulate_host* calls
   // radii of the occupied ball slots, measured on the device the first time a frame is requested after the balls
   // changed: {min floor(r), max ceil(r), any non-integer}
   int32_t *d_rchk = nullptr;
@@ -436,6 +442,7 @@ int ppb_create(const ppb_config *cfg, ppb_batch **out) {
   }
   b->advance_grid = is64(b) ? Launch<double>::advance_grid(cfg->n_worlds, nB, b->sm_count)
                             : Launch<float>::advance_grid(cfg->n_worlds, nB, b->sm_count);
+  if (const char *e = getenv("PPB_RAW_D2H")) b->pack_frames = !(e[0] == '1');   // developer switch: plain frame copies
   if (const char *e = getenv("PPB_OVERLAP")) b->overlap_renders = atoi(e);   // developer switch (A/B timing)
   if (const char *e = getenv("PPB_CHUNK")) {
     const int v = atoi(e);
@@ -452,6 +459,8 @@ int ppb_destroy(ppb_batch *b) {
   if (!b) return PPB_OK;
   cudaSetDevice(b->cfg.device);
   cudaDeviceSynchronize();
+  if (b->pack) packpipe_destroy(b->pack);   // waits for the frame downloads in flight
+  b->pack = nullptr;
   free_scratch(b);
   if (b->stage) cudaFreeHost(b->stage);
   b->stage = nullptr;
@@ -940,6 +949,11 @@ static int simulate_host_impl(ppb_batch *b, int32_t n_steps, float *traj_host, u
     int rc = check_radii(b, st);
     if (rc) return rc;
   }
+  if (frames_host && b->pack_frames && !b->pack) {
+    b->pack = packpipe_create(b->cfg.device);
+    if (!b->pack) return fail(PPB_E_CUDA, "could not set up the packed frame download");
+  }
+  if (b->pack) b->pack_mark[b->sim_calls & 1u] = packpipe_submitted(b->pack);
   const size_t nW = (size_t)b->cfg.n_worlds, nB = (size_t)b->cfg.n_balls;
   const size_t frame_bytes = nW * b->RL.W * b->RL.H * 4;
   const size_t traj_elems = nW * nB * 2;  // per step
@@ -958,6 +972,11 @@ static int simulate_host_impl(ppb_batch *b, int32_t n_steps, float *traj_host, u
   const size_t need_frames = frames_host ? frame_bytes * (chunk / render_every) : 0;
   if (chunk != b->scr_chunk || need_traj > b->scr_traj_bytes || need_frames > b->scr_frames_bytes) {
     CU(cudaDeviceSynchronize());
+    if (b->pack) {   // the frame downloads in flight read the scratch that is about to go
+      std::string perr;
+      if (packpipe_wait_finished(b->pack, packpipe_submitted(b->pack), &perr))
+        return fail(PPB_E_CUDA, "frame download: %s", perr.c_str());
+    }
     free_scratch(b);
     for (int i = 0; i < 2; ++i) {
       if (need_traj) {
@@ -979,6 +998,10 @@ static int simulate_host_impl(ppb_batch *b, int32_t n_steps, float *traj_host, u
     const int cur = (n_steps - done < chunk) ? (n_steps - done) : chunk;
     const int buf = (int)(b->sim_it & 1u);
     if (b->sim_it >= 2) CU(cudaStreamWaitEvent(st, b->ev_copied[buf], 0));  // staging buffer free again
+    if (frames_host && b->pack) {   // ... and the frames the packed download of this slot's previous chunk reads
+      std::string perr;
+      if (packpipe_wait_slot(b->pack, buf, &perr)) return fail(PPB_E_CUDA, "frame download: %s", perr.c_str());
+    }
     {
       // chunk boundaries are multiples of render_every, so the frames of this chunk fill scr_frames[buf] in order;
       // run_steps pipelines the renders with the physics of the following steps and advances host_step
@@ -1000,9 +1023,16 @@ static int simulate_host_impl(ppb_batch *b, int32_t n_steps, float *traj_host, u
                          b->copy_stream));
     if (frames_host) {
       const int f0 = done / render_every, nf = (done + cur) / render_every - f0;
-      if (nf > 0)
+      if (nf > 0 && b->pack) {
+        std::string perr;
+        if (packpipe_submit(b->pack, buf, b->scr_frames[buf], (long long)nf * (long long)nW, b->RL.W * b->RL.H,
+                            frames_host + (size_t)f0 * frame_bytes, st, &perr))
+          return fail(PPB_E_CUDA, "frame download: %s", perr.c_str());
+        b->launches += 1;
+      } else if (nf > 0) {
         CU(cudaMemcpyAsync(frames_host + (size_t)f0 * frame_bytes, b->scr_frames[buf], frame_bytes * nf,
                            cudaMemcpyDeviceToHost, b->copy_stream));
+      }
     }
     CU(cudaEventRecord(b->ev_copied[buf], b->copy_stream));
     done += cur;
@@ -1013,6 +1043,11 @@ static int simulate_host_impl(ppb_batch *b, int32_t n_steps, float *traj_host, u
   if (wait) {
     CU(cudaStreamSynchronize(st));
     CU(cudaStreamSynchronize(b->copy_stream));
+    if (b->pack) {
+      std::string perr;
+      if (packpipe_wait_finished(b->pack, packpipe_submitted(b->pack), &perr))
+        return fail(PPB_E_CUDA, "frame download: %s", perr.c_str());
+    }
   }
   return PPB_OK;
 }
@@ -1027,6 +1062,35 @@ int ppb_simulate_host_async(ppb_batch *b, int32_t n_steps, float *traj_host, uin
   return simulate_host_impl(b, n_steps, traj_host, frames_host, render_every, stream, false);
 }
 
+int ppb_download_frames(ppb_batch *b, const uint8_t *frames_dev, int64_t n_frames, uint8_t *frames_host, void *stream) {
+  if (!b || !frames_dev || !frames_host) return fail(PPB_E_INVALID, "null argument");
+  if (n_frames < 0) return fail(PPB_E_INVALID, "n_frames must be >= 0");
+  if (b->RL.W < 1 || b->RL.H < 1) return fail(PPB_E_STATE, "batch was created without a canvas");
+  CU(cudaSetDevice(b->cfg.device));
+  cudaStream_t st = (cudaStream_t)stream;
+  const size_t frame_bytes = (size_t)b->RL.W * b->RL.H * 4;
+  if (!b->pack_frames) {
+    CU(cudaMemcpyAsync(frames_host, frames_dev, frame_bytes * (size_t)n_frames, cudaMemcpyDeviceToHost, st));
+    CU(cudaStreamSynchronize(st));
+    return PPB_OK;
+  }
+  if (!b->pack && !(b->pack = packpipe_create(b->cfg.device))) return fail(PPB_E_CUDA, "could not set up the packed frame download");
+  std::string perr;
+  // pieces of at most 1 GiB of raw frames (the token buffers are sized by the piece), alternating job slots
+  const int64_t per = std::max<int64_t>(1, (int64_t)(((size_t)1 << 30) / frame_bytes));
+  int slot = 0;
+  for (int64_t f0 = 0; f0 < n_frames; f0 += per, slot ^= 1) {
+    const int64_t nf = std::min<int64_t>(per, n_frames - f0);
+    if (packpipe_submit(b->pack, slot, frames_dev + (size_t)f0 * frame_bytes, nf, b->RL.W * b->RL.H,
+                        frames_host + (size_t)f0 * frame_bytes, st, &perr))
+      return fail(PPB_E_CUDA, "frame download: %s", perr.c_str());
+    b->launches += 1;
+  }
+  if (packpipe_wait_finished(b->pack, packpipe_submitted(b->pack), &perr))
+    return fail(PPB_E_CUDA, "frame download: %s", perr.c_str());
+  return PPB_OK;
+}
+
 int ppb_host_sync(ppb_batch *b, int32_t keep_in_flight, void *stream) {
   if (!b) return fail(PPB_E_INVALID, "null batch");
   if (keep_in_flight < 0 || keep_in_flight > 1) return fail(PPB_E_INVALID, "keep_in_flight must be 0 or 1");
@@ -1035,10 +1099,20 @@ int ppb_host_sync(ppb_batch *b, int32_t keep_in_flight, void *stream) {
     // everything but the most recent call: the copy stream is first-in first-out, so the end of the call before
     // the last implies all earlier ones (and the kernels they copied from)
     if (b->sim_calls >= 2 && b->ev_call[b->sim_calls & 1u]) CU(cudaEventSynchronize(b->ev_call[b->sim_calls & 1u]));
+    if (b->pack && b->sim_calls >= 1) {   // the frames of every call before the last one are in the caller's arrays
+      std::string perr;
+      if (packpipe_wait_finished(b->pack, b->pack_mark[(b->sim_calls - 1) & 1u], &perr))
+        return fail(PPB_E_CUDA, "frame download: %s", perr.c_str());
+    }
     return PPB_OK;
   }
   CU(cudaStreamSynchronize((cudaStream_t)stream));
   if (b->copy_stream) CU(cudaStreamSynchronize(b->copy_stream));
+  if (b->pack) {
+    std::string perr;
+    if (packpipe_wait_finished(b->pack, packpipe_submitted(b->pack), &perr))
+      return fail(PPB_E_CUDA, "frame download: %s", perr.c_str());
+  }
   return PPB_OK;
 }
 
@@ -1102,6 +1176,13 @@ int ppb_get_counters(ppb_batch *b, int64_t out[8], void *stream) {
   out[3] = (int64_t)c[0];
   out[4] = (int64_t)c[3];
   out[5] = out[6] = out[7] = 0;
+  if (b->pack) {   // frame download: bytes that crossed PCIe packed / raw, time spent rebuilding pixels on the host
+    long long ps[6];
+    packpipe_stats(b->pack, ps);
+    out[5] = ps[2];
+    out[6] = ps[3];
+    out[7] = ps[5];
+  }
   return PPB_OK;
 }
 

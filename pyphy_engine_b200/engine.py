@@ -280,7 +280,8 @@ class WorldBatch:
         check(self._lib.ppb_get_counters(self._h, out, _stream_handle(stream, self.device)))
         per_rescan = self.n_balls * (4 * self.n_walls + self.n_balls - 1)
         return dict(launches=out[0], collide_world_steps=out[1], collide_iterations=out[2], events=out[3],
-                    rescans=out[4], pair_tests=out[4] * per_rescan)
+                    rescans=out[4], pair_tests=out[4] * per_rescan, d2h_packed_bytes=out[5], d2h_raw_bytes=out[6],
+                    unpack_us=out[7])
 
     # ------------------------------------------------------------------ stepping
     def step_async(self, n_steps: int = 1, traj=None, frames=None, render_every: int = 1, stream=None):
@@ -371,6 +372,20 @@ class WorldBatch:
                  _stream_handle(stream, self.device)))
         self.steps_done += int(n_steps)
 
+    def download_frames(self, frames, out=None, stream=None):
+        """Device frames (..., H, W, 4) uint8 -> host array of the same shape through the packed download
+        (ppb_download_frames): run-length tokens over PCIe, pixels rebuilt by host threads.  `out`: a numpy array or a
+        pinned CPU torch tensor to fill (default: a new numpy array)."""
+        assert frames.is_cuda and frames.is_contiguous() and frames.dtype.itemsize == 1
+        assert tuple(frames.shape[-3:]) == (self.canvas_h, self.canvas_w, 4)
+        n = int(np.prod(frames.shape[:-3])) if frames.dim() > 3 else 1
+        if out is None:
+            out = np.empty(tuple(frames.shape), np.uint8)
+        ptr = out.data_ptr() if hasattr(out, "data_ptr") else out.ctypes.data
+        check(self._lib.ppb_download_frames(self._h, ctypes.c_void_p(frames.data_ptr()), n, ctypes.c_void_p(ptr),
+                                            _stream_handle(stream, self.device)))
+        return out
+
     def host_sync(self, keep_in_flight: int = 0, stream=None):
         """Wait for the steps and device -> host copies of earlier ``simulate_host(..., wait=False)`` calls:
         all of them (0) or all but the most recent one (1)."""
@@ -378,11 +393,11 @@ class WorldBatch:
 
     # ------------------------------------------------------------------ profiling
     def set_profiling(self, on):
-        """False/0 off, True/1 every kernel, 2 the render kernel only, 3 integrate + collide only."""
+        """False/0 off, True/1 every kernel, 2 the render kernel only, 3 the advance (physics) kernel only."""
         check(self._lib.ppb_set_profiling(self._h, int(on)))
 
     def kernel_times(self):
-        """(ms[3], launches[3]) for integrate / collide / render of the last stepping call."""
+        """(ms[3], launches[3]) of the last stepping call: [0] advance (physics), [1] unused, [2] render."""
         ms = (ctypes.c_float * 3)()
         n = (ctypes.c_int32 * 3)()
         check(self._lib.ppb_get_kernel_times(self._h, ms, n))

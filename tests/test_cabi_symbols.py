@@ -70,9 +70,9 @@ def test_argument_validation_happens_before_cuda():
 
 
 def test_register_budget_of_overlapping_kernels():
-    """The render kernel (one 384-thread CTA per SM) and two fp32 advance CTAs share an SM while the physics of
-    the next chunk of steps overlaps the renders of the current one: 384 * 120 + 2 * 128 * regs <= 65,536
-    registers, i.e. at most 76 for the physics kernel -- this test is the tripwire."""
+    """The render kernel (one 384-thread CTA per SM, 120 registers) leaves room for an fp32 advance CTA while the
+    physics of the next chunk of steps runs beside the last renders of the current one, and the advance kernel keeps
+    at least 5 CTAs (20 warps) per SM when it runs alone: at most 96 registers -- this test is the tripwire."""
     import re
     import shutil
     import subprocess
@@ -93,9 +93,9 @@ def test_register_budget_of_overlapping_kernels():
     collide = {k: v for k, v in regs.items() if "advance_kernelIfLi" in k and "ELi1E" in k}   # fp32, one warp per world
     render = {k: v for k, v in regs.items() if "render_tile_kernelIf" in k}
     assert collide and render, sorted(regs)
-    assert max(collide.values()) <= 76, collide
+    assert max(collide.values()) <= 96, collide
     assert max(render.values()) <= 120, render
-    assert 384 * max(render.values()) + 2 * 128 * max(collide.values()) <= 65536
+    assert 384 * max(render.values()) + 128 * max(collide.values()) <= 65536
 
 
 def test_header_is_plain_c():

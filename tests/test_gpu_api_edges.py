@@ -277,3 +277,60 @@ def test_frames_refuse_radii_without_a_sprite():
     with pytest.raises(_capi.PpbError, match="canvas"):
         wn.simulate_host(1, None, host, 1)
     wn.close()
+
+
+def test_packed_frame_download_is_lossless():
+    """ppb_download_frames / ppb_simulate_host*: frames cross PCIe as run-length tokens and are rebuilt on the host.
+    Whatever the content -- rendered canvases, runs of every length, runs ending at the 64-pixel group borders, noise
+    that does not compress, pixels that are not opaque (both travel raw) -- the host array equals the device array."""
+    import torch
+    from pyphy_engine_b200 import sampler
+    from pyphy_engine_b200.engine import WorldBatch
+    for canvas in ((64, 64), (100, 37)):
+        Wd, Hd = canvas
+        n, nb = 700, 4
+        wb = WorldBatch(n, nb, 4, dtype="f32", canvas=canvas)
+        rs = np.random.RandomState(Wd)
+        npx = Wd * Hd
+        cases = {}
+        # runs of every length 1..200 cycling through a few colours, starting at a random phase per frame
+        lens = np.concatenate([np.arange(1, 201), rs.randint(1, 9, 4000)])
+        base = np.repeat(rs.randint(0, 1 << 24, len(lens)).astype(np.uint32) | np.uint32(0xff000000), lens)
+        a = np.stack([np.roll(base, int(rs.randint(0, len(base))))[:npx] for _ in range(n)])
+        cases["runs"] = a
+        cases["flat"] = np.full((n, npx), 0xffffffff, np.uint32)
+        noise = rs.randint(0, 1 << 24, (n, npx)).astype(np.uint32) | np.uint32(0xff000000)
+        cases["noise"] = noise                               # does not compress: raw
+        alpha = a.copy()
+        alpha[5, 17] &= np.uint32(0x80ffffff)                # one translucent pixel: raw
+        cases["alpha"] = alpha
+        half = a.copy()
+        half[::2] = noise[::2]                               # every other frame is noise: still below half the raw size?
+        cases["mixed"] = half
+        for name, arr in cases.items():
+            dev = torch.from_numpy(arr.view(np.uint8).reshape(n, Hd, Wd, 4).copy()).cuda()
+            got = wb.download_frames(dev)
+            assert np.array_equal(got, dev.cpu().numpy()), (canvas, name)
+            pinned = torch.empty((n, Hd, Wd, 4), dtype=torch.uint8).pin_memory()
+            wb.download_frames(dev, out=pinned)
+            assert torch.equal(pinned, dev.cpu()), (canvas, name)
+        wb.close()
+    # the stepping path: frames of ppb_simulate_host equal the frames rendered on the device, chunk after chunk
+    n, nb = 5000, 8
+    W = sampler.sample_rect_worlds(n, nb, seed=4, **sampler.scaled64_params(nb))
+
+    def make():
+        wb = WorldBatch(n, nb, 4, dtype="f32", canvas=(64, 64), max_substeps=64)
+        wb.set_walls(W["wall"])
+        wb.set_balls(W["pos"], W["vel"] * 8.0, W["rad"], W["mass"])
+        wb.set_styles([(1, (.5, .5, .5, 1), (0, 0, 0, 1))] * nb, [(0, (1, 0, 0, 1))] * 4, 3, 3)
+        return wb
+    a, b = make(), make()
+    host = np.zeros((20, n, 64, 64, 4), np.uint8)
+    traj = np.zeros((60, n, nb, 2), np.float32)
+    a.simulate_host(60, traj, host, 3)
+    t, f = b.step(60, record_traj=True, render_every=3)
+    assert np.array_equal(host, f.cpu().numpy())
+    assert np.array_equal(traj, t.cpu().numpy())
+    a.close()
+    b.close()

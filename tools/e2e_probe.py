@@ -19,6 +19,7 @@ for _ in range(8):
     wb.simulate_host(1, traj, frames, 1); t3 = time.perf_counter()
     T["set_walls"] += t1 - t0; T["set_balls"] += t2 - t1; T["simulate_host"] += t3 - t2
 print({k: round(1e3 * v / 8, 2) for k, v in T.items()}, "ms per step; D2H", frames.numel() / 1e9, "GB ->", round(frames.numel() / 1e9 / (T["simulate_host"] / 8), 1), "GB/s incl. compute")
+print({k: v for k, v in wb.counters().items() if k.startswith(("d2h", "unpack"))})
 # raw pinned D2H bandwidth for reference
 d = torch.empty(frames.shape, dtype=torch.uint8, device="cuda")
 torch.cuda.synchronize(); t0 = time.perf_counter()
