@@ -38,7 +38,7 @@
 extern "C" {
 #endif
 
-#define PPB_VERSION 2
+#define PPB_VERSION 3
 
 #if defined(__GNUC__)
 #define PPB_API __attribute__((visibility("default")))
@@ -291,6 +291,24 @@ PPB_API int ppb_host_sync(ppb_batch *b, int32_t keep_in_flight, void *stream);
  * offsets truncated with int(), pos_dev = the centres unchanged).  Asynchronous. */
 PPB_API int ppb_crop_async(ppb_batch *b, const uint8_t *frames_dev, const void *traj_dev, int32_t n_frames, int32_t crop_sz,
                    int32_t mode, uint8_t *crops_dev, float *pos_dev, void *stream);
+
+/* The procSz step of DataSaver.fetch(cropSz, procSz) (dataio.py:183-189): scipy.misc.imresize(imBall, (procSz, procSz)),
+ * i.e. PIL's bilinear resize, of every crop ppb_crop_async produced, and the rescaling that goes with it.
+ *   crops_dev : [n_frames][n_worlds][n_balls][crop_sz][crop_sz][3] uint8 (crop_sz <= 255)
+ *   out_dev   : [n_frames][n_worlds][n_balls][proc_sz][proc_sz][3] uint8
+ *   pos_dev   : NULL or the positions ppb_crop_async returned, multiplied in place by proc_sz / crop_sz
+ *   vel_dev   : NULL or [n_frames][n_worlds][n_balls][2] float32; row i-1 receives (centre_i - centre_{i-1}) * proc_sz / crop_sz
+ *               from traj_dev ([n_frames][n_worlds][n_balls][2], batch dtype), the last row is left untouched
+ * The resampler restates Pillow's 8-bit path (libImaging/Resample.c).  Asynchronous. */
+PPB_API int ppb_resize_crops_async(ppb_batch *b, const uint8_t *crops_dev, const void *traj_dev, int32_t n_frames, int32_t crop_sz,
+                           int32_t proc_sz, uint8_t *out_dev, float *pos_dev, float *vel_dev, void *stream);
+
+/* DynamicsHorizon.get_data (primitives.py:839-852) for every frame of a recorded trajectory in one launch:
+ *   traj_dev : [n_rows][n_worlds][n_balls][2] positions in the batch dtype; row 0 = before the first step
+ *   out_dev  : [n_rows - lookahead][n_worlds][n_balls][2 * lookahead] float32;
+ *              out[t][w][b][2k + c] = float32(traj[t + k + 1][w][b][c] - traj[t + k][w][b][c])
+ * Asynchronous. */
+PPB_API int ppb_horizon_async(ppb_batch *b, const void *traj_dev, int32_t n_rows, int32_t lookahead, float *out_dev, void *stream);
 
 /* utils.detect_collision's per-frame test (utils.py:38-49) on a recorded trajectory:
  *   traj_dev  : [n_steps][n_items][2] float32 positions (n_items = worlds x balls)

@@ -98,6 +98,8 @@ SIGNATURES = {
     "ppb_download_frames": (ctypes.c_int, [_vp, _vp, ctypes.c_int64, _vp, _vp]),
     "ppb_host_sync": (ctypes.c_int, [_vp, _i32, _vp]),
     "ppb_crop_async": (ctypes.c_int, [_vp, _vp, _vp, _i32, _i32, _i32, _vp, _vp, _vp]),
+    "ppb_resize_crops_async": (ctypes.c_int, [_vp, _vp, _vp, _i32, _i32, _i32, _vp, _vp, _vp, _vp]),
+    "ppb_horizon_async": (ctypes.c_int, [_vp, _vp, _i32, _i32, _vp, _vp]),
     "ppb_collision_flags_async": (ctypes.c_int, [_vp, _i64, _i32, ctypes.c_float, _vp, _vp]),
     "ppb_read_events": (ctypes.c_int, [_vp, ctypes.POINTER(Event), _i64, ctypes.POINTER(_i64), _vp]),
     "ppb_clear_events": (ctypes.c_int, [_vp, _vp]),

@@ -1130,6 +1130,34 @@ int ppb_crop_async(ppb_batch *b, const uint8_t *frames_dev, const void *traj_dev
   return PPB_OK;
 }
 
+int ppb_resize_crops_async(ppb_batch *b, const uint8_t *crops_dev, const void *traj_dev, int32_t n_frames, int32_t crop_sz,
+                           int32_t proc_sz, uint8_t *out_dev, float *pos_dev, float *vel_dev, void *stream) {
+  if (!b || !crops_dev || !out_dev) return fail(PPB_E_INVALID, "null argument");
+  if (vel_dev && !traj_dev) return fail(PPB_E_INVALID, "displacements need the trajectory");
+  if (n_frames < 0 || crop_sz < 1 || proc_sz < 1 || crop_sz > 255 || proc_sz > 1024) return fail(PPB_E_INVALID, "bad n_frames / crop_sz / proc_sz");
+  CU(cudaSetDevice(b->cfg.device));
+  const long long per = (long long)b->cfg.n_worlds * b->cfg.n_balls;
+  cudaError_t e = is64(b) ? Launch<double>::resize_crops(crops_dev, traj_dev, n_frames, per, crop_sz, proc_sz, out_dev, pos_dev,
+                                                         vel_dev, (cudaStream_t)stream)
+                          : Launch<float>::resize_crops(crops_dev, traj_dev, n_frames, per, crop_sz, proc_sz, out_dev, pos_dev,
+                                                        vel_dev, (cudaStream_t)stream);
+  if (e == cudaErrorInvalidValue) return fail(PPB_E_INVALID, "crop_sz %d -> proc_sz %d is outside what the resize kernel holds in shared memory", crop_sz, proc_sz);
+  CU(e);
+  ++b->launches;
+  return PPB_OK;
+}
+
+int ppb_horizon_async(ppb_batch *b, const void *traj_dev, int32_t n_rows, int32_t lookahead, float *out_dev, void *stream) {
+  if (!b || !traj_dev || !out_dev) return fail(PPB_E_INVALID, "null argument");
+  if (lookahead < 1 || n_rows <= lookahead) return fail(PPB_E_INVALID, "need n_rows > lookahead >= 1");
+  CU(cudaSetDevice(b->cfg.device));
+  const long long per = (long long)b->cfg.n_worlds * b->cfg.n_balls;
+  CU(is64(b) ? Launch<double>::horizon(traj_dev, per, n_rows, lookahead, out_dev, (cudaStream_t)stream)
+             : Launch<float>::horizon(traj_dev, per, n_rows, lookahead, out_dev, (cudaStream_t)stream));
+  ++b->launches;
+  return PPB_OK;
+}
+
 int ppb_collision_flags_async(const float *traj_dev, int64_t n_items, int32_t n_steps, float thresh, uint8_t *flags_dev,
                               void *stream) {
   if (!traj_dev || !flags_dev) return fail(PPB_E_INVALID, "null argument");

@@ -26,6 +26,12 @@ struct Launch {
                                  const SamplerParams &P, int32_t step_value, int32_t *fail_count, cudaStream_t st);
   static cudaError_t crop(const uint8_t *frames, const void *traj, long long n_frames, int n_worlds, int n_balls, int W,
                           int H, int c, int mode, uint8_t *crops, float *pos_out, cudaStream_t st);
+  // fetch(cropSz, procSz): PIL-bilinear resize of crops [items][c][c][3] -> [items][p][p][3], positions scaled in place,
+  // displacements between consecutive frames scaled into vel_out (may be NULL)
+  static cudaError_t resize_crops(const uint8_t *crops, const void *traj, long long n_frames, long long items_per_frame, int c,
+                                  int p, uint8_t *out, float *pos, float *vel_out, cudaStream_t st);
+  // DynamicsHorizon look-ahead matrices of every row of a trajectory [n_rows][n_items][2]
+  static cudaError_t horizon(const void *traj, long long n_items, int n_rows, int lookahead, float *out, cudaStream_t st);
   // Dynamics.apply_force (primitives.py:580-594): force is a device array [count][n_balls][2] of fp64
   static cudaError_t apply_force(const StatePtrs &S, int n_balls, int world0, int count, const double *force,
                                  double force_t, cudaStream_t st);

@@ -89,6 +89,31 @@ cudaError_t Launch<T>::crop(const uint8_t *frames, const void *traj, long long n
 }
 
 template <typename T>
+cudaError_t Launch<T>::resize_crops(const uint8_t *crops, const void *traj, long long n_frames, long long items_per_frame,
+                                    int c, int p, uint8_t *out, float *pos, float *vel_out, cudaStream_t st) {
+  const long long items = n_frames * items_per_frame;
+  if (items <= 0) return cudaSuccess;
+  if (items > 2147483647LL) return cudaErrorInvalidValue;
+  const double scale = (double)c / (double)p;
+  const int ksize = (int)ceil(scale < 1.0 ? 1.0 : scale) * 2 + 1;
+  if (ksize > 32) return cudaErrorInvalidValue;
+  const size_t smem = (size_t)(2 * p + p * ksize) * sizeof(int) + (size_t)3 * c * c + (size_t)3 * c * p;
+  if (smem > 200 * 1024) return cudaErrorInvalidValue;
+  cudaError_t e = cudaFuncSetAttribute(resize_crops_kernel<T>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
+  if (e != cudaSuccess) return e;
+  resize_crops_kernel<T><<<(unsigned)items, 128, smem, st>>>(crops, (const T *)traj, items_per_frame, c, p, ksize, out, pos, vel_out);
+  return cudaGetLastError();
+}
+
+template <typename T>
+cudaError_t Launch<T>::horizon(const void *traj, long long n_items, int n_rows, int lookahead, float *out, cudaStream_t st) {
+  const long long total = (long long)(n_rows - lookahead) * n_items * lookahead;
+  if (total <= 0) return cudaSuccess;
+  horizon_kernel<T><<<(unsigned)((total + 255) / 256), 256, 0, st>>>((const T *)traj, n_items, n_rows, lookahead, out);
+  return cudaGetLastError();
+}
+
+template <typename T>
 cudaError_t Launch<T>::wall_cache(const StatePtrs &S, const Layout &L, const RenderLayout &RL, int world0, int count,
                                   cudaStream_t st) {
   const long long n = (long long)count * L.n_walls;

@@ -2,6 +2,13 @@
 //
 //   crop_kernel        : the ball-centred, white-padded crops of DataSaver.fetch(cropSz)
 //                        (dataio.py:160-182) for every (frame, world, ball), plus the re-based positions
+//   resize_crops_kernel : the procSz step of fetch (dataio.py:183-189): scipy.misc.imresize(imBall, (procSz, procSz))
+//                        is PIL's Image.resize(..., BILINEAR); this is Pillow's 8-bit two-pass resampler
+//                        (libImaging/Resample.c: triangle filter widened by the scale factor, 22-bit fixed-point
+//                        coefficients, horizontal pass rounded to 8 bits, then the vertical pass), plus the
+//                        position / displacement rescaling of dataio.py:184-189
+//   horizon_kernel     : DynamicsHorizon.get_data's look-ahead matrix (primitives.py:839-852) for every frame of a
+//                        recorded trajectory at once
 //   collision_flag_kernel : utils.detect_collision's test |a|^2 >= thresh |v|^2 on the second
 //                        differences of a recorded trajectory (utils.py:38-49)
 #pragma once
@@ -60,6 +67,117 @@ __global__ void crop_kernel(const uint8_t *frames, const T *traj, int n_worlds, 
       pos_out[item * 2 + 1] = fy;
     }
   }
+}
+
+// ---- Pillow's precompute_coeffs + normalize_coeffs_8bpc for output index xx (in0 = 0, in1 = in_size, bilinear) ----
+// bounds: xmin, count; k[0..count): coefficients scaled by 2^22.  Explicitly rounded double operations: no FMA
+// contraction may move a coefficient by one unit.
+#define PPB_RESAMPLE_BITS 22
+__device__ inline void bilinear_coeffs(int in_size, int out_size, int xx, int ksize, int *xmin_out, int *count_out, int *k) {
+  double scale = __ddiv_rn((double)in_size, (double)out_size), filterscale = scale;
+  if (filterscale < 1.0) filterscale = 1.0;
+  const double support = filterscale;                        // BILINEAR.support = 1.0
+  const double center = __dmul_rn(__dadd_rn((double)xx, 0.5), scale);
+  const double ss = __ddiv_rn(1.0, filterscale);
+  int xmin = (int)__dadd_rn(__dsub_rn(center, support), 0.5);
+  if (xmin < 0) xmin = 0;
+  int xmax = (int)__dadd_rn(__dadd_rn(center, support), 0.5);
+  if (xmax > in_size) xmax = in_size;
+  xmax -= xmin;
+  double w[32];
+  double ww = 0.0;
+  for (int x = 0; x < xmax && x < 32; ++x) {
+    double t = __dmul_rn(__dadd_rn(__dsub_rn((double)(x + xmin), center), 0.5), ss);
+    if (t < 0.0) t = -t;
+    w[x] = t < 1.0 ? __dsub_rn(1.0, t) : 0.0;
+    ww = __dadd_rn(ww, w[x]);
+  }
+  for (int x = 0; x < ksize; ++x) {
+    double v = 0.0;
+    if (x < xmax && x < 32) v = ww != 0.0 ? __ddiv_rn(w[x], ww) : w[x];
+    const double sc = __dmul_rn(v, (double)(1 << PPB_RESAMPLE_BITS));
+    k[x] = v < 0.0 ? (int)__dadd_rn(-0.5, sc) : (int)__dadd_rn(0.5, sc);
+  }
+  *xmin_out = xmin;
+  *count_out = xmax;
+}
+__device__ __forceinline__ uint8_t resample_clip8(int v) {
+  v >>= PPB_RESAMPLE_BITS;
+  return (uint8_t)(v < 0 ? 0 : (v > 255 ? 255 : v));
+}
+
+// One CTA per (frame, world, ball): crops [items][c][c][3] -> out [items][p][p][3]; positions (crop coordinates,
+// float32, in place) times p/c; vel_out[frame i-1] = (centre_i - centre_{i-1}) * p/c from the recorded trajectory.
+// Dynamic shared memory: bounds 2p ints, coefficients p*ksize ints, the crop 3c^2 bytes, the horizontal pass 3cp bytes.
+template <typename T>
+__global__ void resize_crops_kernel(const uint8_t *crops, const T *traj, long long items_per_frame, int c, int p, int ksize,
+                                    uint8_t *out, float *pos, float *vel_out) {
+  extern __shared__ __align__(16) unsigned char rs_smem[];
+  int *bounds = reinterpret_cast<int *>(rs_smem);
+  int *kk = bounds + 2 * p;
+  uint8_t *src = reinterpret_cast<uint8_t *>(kk + p * ksize);
+  uint8_t *tmp = src + 3 * c * c;
+  const long long item = blockIdx.x;
+  for (int xx = threadIdx.x; xx < p; xx += blockDim.x) bilinear_coeffs(c, p, xx, ksize, &bounds[2 * xx], &bounds[2 * xx + 1], kk + xx * ksize);
+  const uint8_t *g = crops + (size_t)item * c * c * 3;
+  for (int i = threadIdx.x; i < 3 * c * c; i += blockDim.x) src[i] = g[i];
+  __syncthreads();
+  // the rows the vertical pass reads (Pillow resamples only those horizontally; the others are never used)
+  for (int i = threadIdx.x; i < c * p; i += blockDim.x) {
+    const int y = i / p, xx = i - y * p;
+    const int xmin = bounds[2 * xx], n = bounds[2 * xx + 1];
+    const int *k = kk + xx * ksize;
+    int s0 = 1 << (PPB_RESAMPLE_BITS - 1), s1 = s0, s2 = s0;
+    for (int x = 0; x < n; ++x) {
+      const uint8_t *q = src + (y * c + x + xmin) * 3;
+      s0 += q[0] * k[x]; s1 += q[1] * k[x]; s2 += q[2] * k[x];
+    }
+    uint8_t *d = tmp + (y * p + xx) * 3;
+    d[0] = resample_clip8(s0); d[1] = resample_clip8(s1); d[2] = resample_clip8(s2);
+  }
+  __syncthreads();
+  uint8_t *o = out + (size_t)item * p * p * 3;
+  for (int i = threadIdx.x; i < p * p; i += blockDim.x) {
+    const int yy = i / p, xx = i - yy * p;
+    const int ymin = bounds[2 * yy], n = bounds[2 * yy + 1];
+    const int *k = kk + yy * ksize;
+    int s0 = 1 << (PPB_RESAMPLE_BITS - 1), s1 = s0, s2 = s0;
+    for (int y = 0; y < n; ++y) {
+      const uint8_t *q = tmp + ((y + ymin) * p + xx) * 3;
+      s0 += q[0] * k[y]; s1 += q[1] * k[y]; s2 += q[2] * k[y];
+    }
+    o[3 * i] = resample_clip8(s0); o[3 * i + 1] = resample_clip8(s1); o[3 * i + 2] = resample_clip8(s2);
+  }
+  if (threadIdx.x < 2) {
+    const double pos_scale = __ddiv_rn((double)p, (double)c);          // float(procSz) / float(cropSz), dataio.py:184
+    const int ch = threadIdx.x;
+    if (pos) pos[item * 2 + ch] = (float)__dmul_rn((double)pos[item * 2 + ch], pos_scale);   // float32 array element * float
+    if (vel_out) {
+      const long long frame = item / items_per_frame;
+      if (frame > 0) {                                                 // vx = pos.x() - pPos[j][0]; velocity[.., i-1] = vx * posScale
+        const double dv = __dsub_rn((double)traj[item * 2 + ch], (double)traj[(item - items_per_frame) * 2 + ch]);
+        vel_out[(item - items_per_frame) * 2 + ch] = (float)__dmul_rn(dv, pos_scale);
+      }
+    }
+  }
+}
+
+// DynamicsHorizon.get_data (primitives.py:839-852), all frames at once.  traj: [n_rows][n_items][2] (row 0 = the
+// positions before the first step); out: [n_rows - N][n_items][2 N] float32, out[t][i][2 k + c] = the displacement of
+// item i during step t + k + 1, i.e. float32(traj[t + k + 1] - traj[t + k]).
+template <typename T>
+__global__ void horizon_kernel(const T *traj, long long n_items, int n_rows, int N, float *out) {
+  const long long i = (long long)blockIdx.x * blockDim.x + threadIdx.x;
+  const long long total = (long long)(n_rows - N) * n_items * N;
+  if (i >= total) return;
+  const int k = (int)(i % N);
+  const long long it = (i / N) % n_items;
+  const long long t = i / ((long long)N * n_items);
+  const T *a = traj + ((t + k) * n_items + it) * 2, *b = a + n_items * 2;
+  float2 d;
+  d.x = (float)(b[0] - a[0]);
+  d.y = (float)(b[1] - a[1]);
+  reinterpret_cast<float2 *>(out)[i] = d;
 }
 
 // traj: [n_steps][n_items][2] float32 (what data.mat holds); flags: [n_items][n_steps - 2] u8,

@@ -373,9 +373,9 @@ class DataSaver(object):
 
     def fetch(self, cropSz=None, procSz=None):
         """One sequence in memory (dataio.py:131-196): the list of frames, or with ``cropSz`` the
-        ball-centred crops ``(imBalls, force, velocity, position)``.  Stepping, drawing and cropping
-        run on the device (``ppb_step_async`` + ``ppb_crop_async``); only the optional ``procSz``
-        resize (scipy.misc.imresize in the reference, i.e. PIL bilinear) is done on the host."""
+        ball-centred crops ``(imBalls, force, velocity, position)``.  Stepping, drawing, cropping and the
+        optional ``procSz`` resize (scipy.misc.imresize in the reference, i.e. PIL bilinear) run on the device
+        (``ppb_step_async`` + ``ppb_crop_async`` + ``ppb_resize_crops_async``)."""
         self.seqLen_ = self._draw_seq_len()
         model, f, ballPos, _ = self.generate_model()
         sp = SequenceSpec(model, f, ballPos, self.pts, self.seqLen_)
@@ -385,7 +385,6 @@ class DataSaver(object):
         return self._fetch_crops(sp, int(cropSz), procSz)
 
     def _fetch_crops(self, sp, cropSz, procSz):
-        from PIL import Image
         nB, L = self.numBalls_, sp.seq_len
         wb = self._batch_from_specs([sp], True)
         try:
@@ -395,9 +394,12 @@ class DataSaver(object):
                 from ._capi import STATUS_NAMES
                 raise AssertionError("the reference raises in step %d (%s)" % (int(at[0]), STATUS_NAMES.get(int(status[0]))))
             crops, cpos = wb.crop(frames, traj, cropSz)
+            vel = None
+            if procSz is not None:                                  # dataio.py:183-189, PIL bilinear on the device
+                crops, cpos, vel = wb.resize_crops(crops, int(procSz), pos=cpos, traj=traj, want_vel=True)
+                vel = vel[:, 0].cpu().numpy()                       # (L, nB, 2); row i-1 = frame i - frame i-1, scaled
             crops = crops[:, 0].cpu().numpy()                       # (L, nB, c, c, 3)
             cpos = cpos[:, 0].cpu().numpy()                         # (L, nB, 2) in crop coordinates
-            pos = traj[:, 0].cpu().numpy().astype(np.float64)       # (L, nB, 2) in canvas coordinates
         finally:
             wb.close()
         force = np.zeros((2 * nB, L), np.float32)
@@ -406,13 +408,8 @@ class DataSaver(object):
         position = cpos.reshape(L, 2 * nB).T.copy()
         velocity = np.zeros((2 * nB, L), np.float32)
         imBalls = [[crops[i, j] for i in range(L)] for j in range(nB)]
-        if procSz is not None:
-            scale = float(procSz) / float(cropSz)
-            imBalls = [[np.asarray(Image.fromarray(im).resize((procSz, procSz), Image.BILINEAR)) for im in seq]
-                       for seq in imBalls]
-            position = (position * np.float32(scale)).astype(np.float32)
-            d = np.diff(pos, axis=0)                                # displacement between consecutive frames
-            velocity[:, :L - 1] = (d * scale).reshape(L - 1, 2 * nB).T
+        if vel is not None:
+            velocity[:, :L - 1] = vel[:L - 1].reshape(L - 1, 2 * nB).T
         return imBalls, force, velocity, position
 
     def fetch_batch(self, numSeq, want_frames=True):

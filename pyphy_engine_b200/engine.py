@@ -351,6 +351,41 @@ class WorldBatch:
                                        _stream_handle(stream, self.device)))
         return crops, pos
 
+    def resize_crops(self, crops, proc_sz: int, pos=None, traj=None, want_vel: bool = False, stream=None):
+        """The procSz step of DataSaver.fetch (dataio.py:183-189) on the device: PIL-bilinear resize (what
+        scipy.misc.imresize does) of crops (F, n_worlds, n_balls, c, c, 3) -> (F, n_worlds, n_balls, p, p, 3); `pos`
+        (crop coordinates from ``crop``) is multiplied in place by p / c; with want_vel the displacements between
+        consecutive frames of `traj`, times p / c, are returned as (F, n_worlds, n_balls, 2) float32 (row i-1 holds
+        frame i minus frame i-1, the last row is zero).  Returns (resized, pos, vel or None)."""
+        import torch
+        F, c = int(crops.shape[0]), int(crops.shape[3])
+        assert crops.is_cuda and crops.is_contiguous() and tuple(crops.shape) == (F, self.n_worlds, self.n_balls, c, c, 3)
+        out = torch.empty((F, self.n_worlds, self.n_balls, proc_sz, proc_sz, 3), dtype=torch.uint8, device=crops.device)
+        vel = None
+        if want_vel:
+            assert traj is not None and traj.is_cuda and traj.is_contiguous() and tuple(traj.shape) == (F, self.n_worlds, self.n_balls, 2)
+            vel = torch.zeros((F, self.n_worlds, self.n_balls, 2), dtype=torch.float32, device=crops.device)
+        if pos is not None:
+            assert pos.is_cuda and pos.is_contiguous() and pos.dtype == torch.float32
+        check(self._lib.ppb_resize_crops_async(
+            self._h, ctypes.c_void_p(crops.data_ptr()), ctypes.c_void_p(traj.data_ptr()) if traj is not None else None, F, c,
+            int(proc_sz), ctypes.c_void_p(out.data_ptr()), ctypes.c_void_p(pos.data_ptr()) if pos is not None else None,
+            ctypes.c_void_p(vel.data_ptr()) if vel is not None else None, _stream_handle(stream, self.device)))
+        return out, pos, vel
+
+    def horizon(self, traj, lookahead: int, stream=None):
+        """DynamicsHorizon.get_data's look-ahead matrix (primitives.py:839-852) for every row of a recorded
+        trajectory (R, n_worlds, n_balls, 2) of the batch dtype (row 0 = positions before the first step):
+        (R - lookahead, n_worlds, n_balls, 2 * lookahead) float32, [t, w, b, 2k + c] = traj[t+k+1] - traj[t+k]."""
+        import torch
+        R = int(traj.shape[0])
+        assert traj.is_cuda and traj.is_contiguous() and tuple(traj.shape) == (R, self.n_worlds, self.n_balls, 2)
+        assert traj.dtype == (torch.float64 if self._np_dtype is np.float64 else torch.float32)
+        out = torch.empty((R - lookahead, self.n_worlds, self.n_balls, 2 * lookahead), dtype=torch.float32, device=traj.device)
+        check(self._lib.ppb_horizon_async(self._h, ctypes.c_void_p(traj.data_ptr()), R, int(lookahead),
+                                          ctypes.c_void_p(out.data_ptr()), _stream_handle(stream, self.device)))
+        return out
+
     def simulate_host(self, n_steps: int, traj_host=None, frames_host=None, render_every: int = 1, stream=None,
                       wait: bool = True):
         """Host-buffer path (DataSaver.fetch analogue): copies are inside the call.

@@ -528,7 +528,7 @@ class World(object):
 # Dynamics
 # ------------------------------------------------------------------------------------------
 class Dynamics(object):
-    """Event-driven stepper (primitives.py:535-805), executed by the collide / integrate kernels."""
+    """Event-driven stepper (primitives.py:535-805), executed by the advance kernel."""
 
     EVENT_CAPACITY = 1 << 16
     EVENT_DRAIN_EVERY = 64      # steps between drains of the device event buffer (one world: << 1000 events per step)
@@ -625,6 +625,27 @@ class Dynamics(object):
         if status[0] != 0:
             raise _status_error(status[0], int(at[0]) + dev.step_base)
 
+    def step_many(self, n, want_frames=True):
+        """``n`` x (step() + generate_image()) in ONE device call (extension; the look-ahead window of
+        DynamicsHorizon is filled with it): returns the positions after every step, (n, n_balls, 2) float64 in
+        dynamic-object order, and the frames (n, ySz, xSz, 4) uint8 (None without want_frames).  The host objects are
+        left at the state after the last step; a reference assertion raises like step() does."""
+        dev = self._dev()
+        if not hasattr(dev, "step_base"):
+            dev.step_base = self._nsteps
+        if want_frames:
+            dev.ensure_styles(self.world_)
+        traj, frames = dev.batch.step(int(n), record_traj=True, render_every=1 if want_frames else 0)
+        dev.steps += int(n)
+        self._nsteps += int(n)
+        self._drain_events()
+        status, at = dev.batch.get_status()
+        dev.pull(self.world_)
+        if status[0] != 0:
+            raise _status_error(status[0], int(at[0]) + dev.step_base)
+        traj = traj[:, 0].cpu().numpy().astype(np.float64)
+        return traj, (frames[:, 0].cpu().numpy() if want_frames else None)
+
     def generate_image(self):
         self._dev()
         return self.world_.generate_image()
@@ -689,36 +710,60 @@ class DynamicsHorizon(object):
     primitives.py:832-836, and ``get_data`` indexes with the ball index instead of the horizon
     index, :848); this one implements the evident intent with the same constructor and
     ``get_data() -> (image, (n_balls, 2*lookAhead) float32)`` signature.
+
+    The window is filled ``chunk`` steps at a time (default: ``lookAhead``): one device call steps and draws the
+    chunk (``Dynamics.step_many``) and one launch turns the recorded positions into the look-ahead matrices of all
+    its frames (``ppb_horizon_async``), instead of one step + one frame + a Python loop per ``get_data``.  The model
+    therefore runs up to ``lookAhead + chunk - 1`` steps ahead of the frame being delivered.
     """
 
-    def __init__(self, model, lookAhead=20):
+    def __init__(self, model, lookAhead=20, chunk=None):
         self.N_ = lookAhead
         self.model_ = model
         self.names_ = list(model.get_dynamic_object_names())
-        self.pos_ = co.OrderedDict((n, co.deque()) for n in self.names_)
+        self._chunk = max(1, int(chunk if chunk is not None else lookAhead))
+        p0 = [model.get_object_position(n) for n in self.names_]
+        self._rows = [np.array([[p.x(), p.y()] for p in p0], np.float64)]   # positions after step 0, 1, 2, ...
+        self._row0 = 0                  # step index of self._rows[0]
+        self._next = 0                  # get_data calls served so far
         self.im_ = co.deque()
+        self._mats = co.deque()
         self.outMat_ = np.zeros((len(self.names_), self.N_ * 2), np.float32)
-        for n in self.names_:
-            self.pos_[n].append(model.get_object_position(n))
-        for _ in range(lookAhead):
-            self.im_.append(self.step())
+        self._advance(lookAhead)
+
+    def _advance(self, n):
+        traj, frames = self.model_.step_many(n)
+        self._rows.extend(traj[i] for i in range(n))
+        self.im_.extend(frames[i] for i in range(n))
 
     def step(self):
-        self.model_.step()
-        for n in self.names_:
-            self.pos_[n].append(self.model_.get_object_position(n))
-        return self.model_.generate_image()
+        """One more step of the window (kept for the reference's method name): returns its frame."""
+        self._advance(1)
+        return self.im_[-1]
+
+    def _fill_mats(self):
+        import torch
+        have = self._row0 + len(self._rows) - 1                 # last step recorded
+        if have < self._next + self.N_:
+            self._advance(max(self._chunk, self._next + self.N_ - have))
+        have = self._row0 + len(self._rows) - 1
+        first = self._next - self._row0
+        window = np.stack(self._rows[first:])                   # rows of steps _next .. have
+        dev = self.model_._dev()
+        t = torch.from_numpy(window[:, None]).to("cuda:%d" % dev.batch.device)
+        if dev.batch.dtype in ("f32", "float32", "fp32"):
+            t = t.float()
+        mats = dev.batch.horizon(t.contiguous(), self.N_).cpu().numpy()[:, 0]   # (have - _next - N + 1, n_balls, 2N)
+        self._mats.extend(mats[i] for i in range(mats.shape[0]))
+        del self._rows[:first]
+        self._row0 = self._next
 
     def get_data(self):
+        if not self._mats:
+            self._fill_mats()
         im = self.im_.popleft()
-        for i, n in enumerate(self.names_):
-            p = self.pos_[n]
-            for k in range(self.N_):
-                d = p[k + 1] - p[k]
-                self.outMat_[i, 2 * k] = np.float32(d.x())
-                self.outMat_[i, 2 * k + 1] = np.float32(d.y())
-            p.popleft()
-        self.im_.append(self.step())
+        self.outMat_[...] = self._mats.popleft()
+        self._next += 1
         return im.copy(), self.outMat_.copy()
 
 

@@ -32,7 +32,7 @@ def test_library_builds_and_exports_every_declared_symbol():
         assert hasattr(lib, s), "missing export: " + s
     # the ctypes binding covers exactly the declared surface
     assert sorted(_capi.SIGNATURES) == _declared_symbols()
-    assert _capi.load().ppb_version() == 2
+    assert _capi.load().ppb_version() == 3
 
 
 def test_no_cpu_fallback():

@@ -222,6 +222,28 @@ def test_dynamics_horizon_delivers_delayed_frames():
     assert np.allclose(mat[0, 0::2], 60 * 0.01, atol=1e-6) and np.allclose(mat[0, 1::2], 25 * 0.01, atol=1e-6)
 
 
+def test_dynamics_horizon_chunks_equal_single_steps():
+    """The window is filled a chunk at a time on the device (Dynamics.step_many + ppb_horizon_async); frames and
+    look-ahead matrices must be what stepping one step per get_data() gives."""
+    N, calls = 4, 23
+    a, b = mg.build_config1_64(NS), mg.build_config1_64(NS)
+    for m in (a, b):
+        m.set_object_velocity('ball-0', gm.Point(900.0, 410.0))      # fast: several wall hits inside the test
+    hor = pm.DynamicsHorizon(a, lookAhead=N, chunk=6)
+    p = b.get_object_position('ball-0')
+    rows, ims = [np.array([p.x(), p.y()])], []
+    for _ in range(N + calls):
+        b.step()
+        p = b.get_object_position('ball-0')
+        rows.append(np.array([p.x(), p.y()]))
+        ims.append(b.generate_image())
+    for j in range(calls):
+        im, mat = hor.get_data()
+        assert np.array_equal(im, ims[j])
+        exp = np.concatenate([np.float32(rows[j + k + 1] - rows[j + k]) for k in range(N)])
+        assert np.array_equal(mat[0], exp), j
+
+
 def test_datasaver_groups_large_jobs(tmp_path):
     """Jobs whose frames exceed the staging budget run as several batches with identical results."""
     kw = dict(wThick=3, isRect=True, mnBallSz=3, mxBallSz=3, arenaSz=64, mnWLen=36, mxWLen=50, numBalls=2,

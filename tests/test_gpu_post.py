@@ -168,3 +168,71 @@ def test_custom_world_glimpse(tmp_path):
             assert np.array_equal(imBalls[b], ref)
     assert not np.allclose(position, [120, 120, 250, 200])           # the balls moved
     assert dio.fix_theta_range(270) == -90 and dio.fix_theta_range(-180) == 180 and dio.fix_theta_range(90) == 90
+
+
+@pytest.mark.parametrize("dtype,crop,proc", [("f32", 16, 8), ("f64", 24, 10), ("f32", 40, 64), ("f32", 17, 5), ("f32", 32, 32),
+                                              ("f32", 64, 7)])
+def test_device_resize_equals_pil_bilinear(dtype, crop, proc):
+    """fetch(cropSz, procSz) (dataio.py:183-189): scipy.misc.imresize(imBall, (procSz, procSz)) is
+    PIL.Image.resize(..., BILINEAR) of the uint8 crop; the device kernel restates Pillow's 8-bit resampler and is
+    compared here with Pillow itself (an implementation this repository did not write), byte for byte.  Positions
+    and displacements follow the reference's expressions literally."""
+    from PIL import Image
+    n, nb, steps = 24, 3, 6
+    W = sampler.sample_rect_worlds(n, nb, seed=9, **sampler.scaled64_params(4))
+    wb = WorldBatch(n, nb, 4, dtype=dtype, canvas=(64, 64))
+    wb.set_walls(W["wall"])
+    wb.set_balls(W["pos"][:, :nb], W["vel"][:, :nb] * 15.0, W["rad"][:, :nb], W["mass"][:, :nb])
+    wb.set_styles([(1, (.5, .5, .5, 1), (0, 0, 0, 1))] * nb, [(0, (1, 0, 0, 1))] * 4, 3, 3)
+    traj, frames = wb.step(steps, record_traj=True, render_every=1)
+    crops, cpos = wb.crop(frames, traj, crop)
+    crops_h, cpos_h = crops.cpu().numpy(), cpos.cpu().numpy().copy()
+    out, pos, vel = wb.resize_crops(crops, proc, pos=cpos, traj=traj, want_vel=True)
+    out, pos, vel = out.cpu().numpy(), pos.cpu().numpy(), vel.cpu().numpy()
+    tr = traj.cpu().numpy().astype(np.float64)
+    scale = float(proc) / float(crop)
+    for s in range(steps):
+        for w in range(0, n, 5):
+            for b in range(nb):
+                ref = np.asarray(Image.fromarray(crops_h[s, w, b]).resize((proc, proc), Image.BILINEAR))
+                assert np.array_equal(out[s, w, b], ref), (s, w, b)
+                # position[2j, i] = position[2j, i] * posScale on a float32 array element (dataio.py:186-187)
+                assert pos[s, w, b, 0] == np.float32(np.float64(cpos_h[s, w, b, 0]) * scale)
+                assert pos[s, w, b, 1] == np.float32(np.float64(cpos_h[s, w, b, 1]) * scale)
+                if s > 0:       # velocity[2j, i-1] = (pos.x() - pPos) * posScale (dataio.py:151-152, 189-190)
+                    assert vel[s - 1, w, b, 0] == np.float32((tr[s, w, b, 0] - tr[s - 1, w, b, 0]) * scale)
+                    assert vel[s - 1, w, b, 1] == np.float32((tr[s, w, b, 1] - tr[s - 1, w, b, 1]) * scale)
+    assert not vel[steps - 1].any()
+    # random content as well: every coefficient pattern, values over the whole byte range
+    rs = np.random.RandomState(crop * 100 + proc)
+    noise = torch.from_numpy(rs.randint(0, 256, (steps, n, nb, crop, crop, 3)).astype(np.uint8)).cuda()
+    out2, _, _ = wb.resize_crops(noise, proc)
+    out2, noise = out2.cpu().numpy(), noise.cpu().numpy()
+    for idx in ((0, 0, 0), (2, 7, 1), (5, 23, 2)):
+        ref = np.asarray(Image.fromarray(noise[idx]).resize((proc, proc), Image.BILINEAR))
+        assert np.array_equal(out2[idx], ref), idx
+    wb.close()
+
+
+@pytest.mark.parametrize("dtype", ["f32", "f64"])
+def test_horizon_matrices_of_a_recorded_trajectory(dtype):
+    """DynamicsHorizon.get_data's matrix (primitives.py:843-850) for all frames in one launch, against the literal
+    loop: outMat[i, 2n], outMat[i, 2n+1] = float32(pos[n+1] - pos[n]) over the look-ahead window."""
+    n, nb, steps, N = 50, 4, 30, 7
+    W = sampler.sample_rect_worlds(n, nb, seed=6, **sampler.scaled64_params(nb))
+    wb = WorldBatch(n, nb, 4, dtype=dtype)
+    wb.set_walls(W["wall"])
+    wb.set_balls(W["pos"], W["vel"] * 10.0, W["rad"], W["mass"])
+    p0, _ = wb.get_balls()
+    traj, _ = wb.step(steps, record_traj=True)
+    full = torch.cat([torch.from_numpy(p0.astype(np.float64 if dtype == "f64" else np.float32))[None].cuda(), traj], 0)
+    mats = wb.horizon(full.contiguous(), N).cpu().numpy()
+    assert mats.shape == (steps + 1 - N, n, nb, 2 * N) and mats.dtype == np.float32
+    rows = full.cpu().numpy()
+    for t in (0, 5, steps - N):
+        for w in (0, 17, 49):
+            for b in range(nb):
+                for k in range(N):
+                    d = rows[t + k + 1, w, b] - rows[t + k, w, b]
+                    assert mats[t, w, b, 2 * k] == np.float32(d[0]) and mats[t, w, b, 2 * k + 1] == np.float32(d[1])
+    wb.close()
