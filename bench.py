@@ -8,7 +8,7 @@
 Workload (BASELINE.json configs[3], the configuration the 1/2/4/8-GPU metric is quoted on):
 per GPU 131,072 independent 8-ball worlds on a 64x64 canvas, synthetic random-initialised
 rectangular tables; one "step" = Dynamics.step() + World.generate_image() for every world of
-the shard (one advance launch per 16 steps + one render launch per step).  Weak scaling: the per-GPU shard is
+the shard (one advance launch per 64 steps + one render launch per step).  Weak scaling: the per-GPU shard is
 fixed, 8 GPUs = the full 1,048,576-world config.  Worlds are independent, so there is no
 collective in the step loop; NCCL only carries the final timing/statistics reduction.
 
@@ -36,7 +36,6 @@ SEED0 = 20161
 MAX_SUBSTEPS = 64
 # algorithmic bytes (fp32 state, RGBA8 frames), SURVEY.md 8(d) / DESIGN.md "Kernels"
 BYTES_K3_PER_FRAME = CANVAS * CANVAS * 4
-DRAWS_PER_ADVANCE = 16        # steps one advance launch covers when a frame is drawn every step (PPB_DRAWS_PER_CHUNK)
 
 
 def _bytes_advance_per_launch(n_worlds, n_balls, n_steps, n_snapshots):
@@ -281,7 +280,7 @@ def run_ours(args, rank, local_rank, world_size):
     e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
     barrier()
     e0.record()
-    wb.step_ring_async(args.steps, frames, 1)      # K steps: K render launches + ceil(K / 16) advance launches
+    wb.step_ring_async(args.steps, frames, 1)      # K steps: K render launches + ceil(K / 64) advance launches
     e1.record()
     barrier()
     ms = e0.elapsed_time(e1)
@@ -441,15 +440,15 @@ def run_ours(args, rank, local_rank, world_size):
             "config": {"workload": "configs[3] shard: 131072 worlds/GPU x 8 balls, 64x64 frame rendered every step",
                        "worlds_total": total_worlds, "balls_per_world": N_BALLS, "canvas": [CANVAS, CANVAS],
                        "l2": "per-step working set (2 GiB of frames + 70 MB of state per GPU) exceeds the 126 MB L2",
-                       "schedule": "one advance launch per 16 steps leaves 16 position snapshots, 16 render launches follow on their own stream; the next advance launch starts beside the last 2 of them; frames into a 2-slot ring",
+                       "schedule": "one advance launch per chunk of up to 64 steps leaves a position snapshot per step, the chunk's render launches follow on their own stream; the next advance launch starts beside the last 2 of them; frames into a 2-slot ring",
                        "max_substeps": MAX_SUBSTEPS, "halted_worlds": int(total_worlds - live_total),
                        "events_per_world_step": events_total / (total_worlds * max(args.steps, 1)),
                        "pair_tests_per_sec_rank0": (c1["pair_tests"] - c0["pair_tests"]) / (ms * 1e-3)},
             "roofline": {"bound": "hbm", "kernel": names[dom], "achieved": achieved[dom], "peak": peak,
                          "unit": "GB/s", "frac": achieved[dom] / peak, "traffic": load_traffic(names[dom]), "peak_source": peak_src,
                          "avg_launch_us": float(avg_us[dom]),
-                         "note": "render: CUDA-event times of every launch inside the timed region (2 of every 16 share the SMs "
-                                 "with the next advance launch); advance: event times of a second pass of the same K steps, "
+                         "note": "render: CUDA-event times of every launch inside the timed region (the last 2 of a chunk share the SMs "
+                                 "with the next chunk's advance launch); advance: event times of a second pass of the same K steps, "
                                  "%.1f steps per launch, bytes = what that launch materialises (state round trip + snapshots) -- "
                                  "it is bound by instruction issue and by its longest sub-step chain, not by HBM; "
                                  "render alone: %.1f us/launch = %.3f of peak"

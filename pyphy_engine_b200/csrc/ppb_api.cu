@@ -57,7 +57,8 @@ inline uint32_t h_premul_rgba8(const float c[4]) {
 // a long sub-step chain catch up, short enough that a launch stays in the millisecond range.  With frames, a launch
 // covers at most PPB_DRAWS_PER_CHUNK drawn steps (their position snapshots are what the render kernels read).
 #define PPB_STEPS_PER_LAUNCH 64
-#define PPB_DRAWS_PER_CHUNK 16
+#define PPB_TICKET_WORLDS_DEFAULT 2
+#define PPB_DRAWS_PER_CHUNK 64
 
 struct ppb_batch {
   ppb_config cfg;
@@ -279,7 +280,10 @@ int check_radii(ppb_batch *b, cudaStream_t st) {
 
 int pipeline_reserve(ppb_batch *b) {
   if (b->render_stream) return PPB_OK;
-  const size_t bytes = (size_t)b->cfg.n_worlds * b->cfg.n_balls * 2 * b->esz * b->draws_per_chunk;
+  // two sets of position snapshots, at most 1 GiB each
+  const size_t one = (size_t)b->cfg.n_worlds * b->cfg.n_balls * 2 * b->esz;
+  if (one && (size_t)b->draws_per_chunk * one > ((size_t)1 << 30)) b->draws_per_chunk = (int)std::max<size_t>(1, ((size_t)1 << 30) / one);
+  const size_t bytes = one * b->draws_per_chunk;
   for (int i = 0; i < 2; ++i) {
     CU(cudaMalloc(&b->snap[i], bytes ? bytes : 16));
     CU(cudaEventCreateWithFlags(&b->ev_phys[i], cudaEventDisableTiming));
@@ -390,6 +394,8 @@ int ppb_create(const ppb_config *cfg, ppb_batch **out) {
   b->P.step_off = 0;
   b->P.step_abs = 0;
   b->P.scan_only = 0;
+  b->P.ticket_worlds = PPB_TICKET_WORLDS_DEFAULT;
+  if (const char *e = getenv("PPB_TICKET")) { const int v = atoi(e); if (v >= 1 && v <= 1024) b->P.ticket_worlds = v; }   // developer switch
   b->P.max_substeps = cfg->max_substeps > 0 ? cfg->max_substeps : (1 << 20);
   b->esz = is64(b) ? 8 : 4;
   CU(cudaDeviceGetAttribute(&b->sm_count, cudaDevAttrMultiProcessorCount, cfg->device));
@@ -801,23 +807,20 @@ static int run_steps(ppb_batch *b, int32_t n_steps, void *traj_dev, uint8_t *fra
     // step, the chunk's render launches follow on the render stream; two sets of snapshot slots alternate.  The
     // next chunk's advance launch is released when all but the last `overlap_renders` renders of this chunk are done:
     // its tail (the few warps that own a world with a long sub-step chain) then hides behind those renders, while the
-    // bulk of the rendering has the SMs to itself -- the render kernel loses about as much time as the physics
-    // instructions it shares the SMs with would take alone.  Measured on B200, 131,072 x 8 worlds with a frame per
-    // step, us per step: chunks of 8 / 16 / 32 draws with overlap 0: 432 / 417 / 411, overlap 2: 412 / 409 / 408,
-    // all renders overlapped: 415 / 411 / 409 (PPB_CHUNK / PPB_OVERLAP in the environment select these for A/B runs).
+    // bulk of the rendering has the SMs to itself -- beside a render launch the physics costs the step about what it
+    // would cost alone, so only the tail is worth hiding.  An advance launch takes about 135 us + 28 us per step at
+    // 131,072 x 8 worlds, hence long chunks: measured on B200 with a frame per step, us per step, chunks of
+    // 8 / 16 / 32 draws with overlap 0: 432 / 417 / 411, overlap 2: 412 / 409 / 408, all renders overlapped:
+    // 415 / 411 / 409 (PPB_CHUNK / PPB_OVERLAP in the environment select these for A/B runs).
     int rc = pipeline_reserve(b);
     if (rc) return rc;
     int per_chunk = b->draws_per_chunk;
     if (per_chunk * render_every > PPB_STEPS_PER_LAUNCH) per_chunk = PPB_STEPS_PER_LAUNCH / render_every;
     if (per_chunk < 1) per_chunk = 1;
-    // the first chunks of a call are short (1, 2, 4, ... drawn steps): nothing hides the first advance launch, so it
-    // should cover few steps; every later one runs beside the renders of the chunk before it
-    int n_rendered = 0, chunk_i = 0, s = 0, ramp = 1;
+    int n_rendered = 0, chunk_i = 0, s = 0;
     while (s < n_steps) {
       int draws = n_draws - n_rendered;
       if (draws > per_chunk) draws = per_chunk;
-      if (draws > ramp) draws = ramp;
-      ramp *= 2;
       // (steps after the last drawn one run without snapshots)
       int n = draws > 0 ? draws * render_every : n_steps - s;
       if (draws == 0 && n > PPB_STEPS_PER_LAUNCH) n = PPB_STEPS_PER_LAUNCH;

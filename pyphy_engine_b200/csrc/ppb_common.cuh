@@ -154,6 +154,7 @@ struct StepParams {
   int32_t draw_first; // index inside the launch of the first step whose positions go to a snapshot slot ...
   int32_t draw_every; // ... then every draw_every-th step (0: no snapshots); slot j lies j * n_worlds * n_balls further on
   int32_t parity;     // which work-ticket counter this launch uses (it resets the other one for the next launch)
+  int32_t ticket_worlds;  // consecutive worlds a team takes per ticket
 };
 
 // ---- render ----

@@ -63,7 +63,6 @@ struct WarpSmem {
 
 #define PPB_COLLIDE_WARPS 4
 #define PPB_K_NONE 0x7fff
-#define PPB_TICKET_WORLDS 8
 
 template <typename T, int LW>
 __device__ __forceinline__ T seg_min(T v) {
@@ -186,13 +185,13 @@ advance_kernel(StatePtrs S, Layout L, StepParams P, T *traj) {
     team_sync<TW>(team);
   }
 
-  // a ticket is PPB_TICKET_WORLDS consecutive worlds: one same-address atomic per world would cost the launch
-  // about as much as eight event-free steps of the whole batch
-  while ((long long)idx * PPB_TICKET_WORLDS < count) {
+  // a ticket is P.ticket_worlds consecutive worlds
+  const int tkw = P.ticket_worlds;
+  while ((long long)idx * tkw < count) {
     int idx_next = 0;
     if (wt == 0 && lane == 0) idx_next = atomicAdd(ticket, 1);   // its latency hides behind these worlds' work
-    const int w_first = idx * PPB_TICKET_WORLDS;
-    const int w_end = min(count, w_first + PPB_TICKET_WORLDS);
+    const int w_first = idx * tkw;
+    const int w_end = min(count, w_first + tkw);
     for (int w = w_first; w < w_end; ++w) {
     const bool has_ball = bi < nB;
     const long long base = (long long)w * nB;
@@ -218,6 +217,11 @@ advance_kernel(StatePtrs S, Layout L, StepParams P, T *traj) {
     uint32_t nev_base = 0u, nev_local = 0u;
     int s_done = 0;
     const bool skip = P.scan_only && (!pending || status != 0);   // ppb_scan_async only drains non-empty queues
+    // where this lane's ball goes in the trajectory rows / snapshot slots of the steps to come
+    const bool rec_traj = traj != nullptr && has_ball && writer && !P.scan_only;
+    T2 *traj_p = reinterpret_cast<T2 *>(traj) + (long long)P.step_off * total + base + bi;
+    T2 *snap_p = reinterpret_cast<T2 *>(S.snap) + base + bi;
+    int next_draw = (S.snap && P.draw_every > 0 && !P.scan_only) ? P.draw_first : 0x7fffffff;
 
     for (int s = 0; s < P.n_steps && !skip; ++s) {
       if (status == 0) {
@@ -455,14 +459,18 @@ advance_kernel(StatePtrs S, Layout L, StepParams P, T *traj) {
         }
       }
       // ---- what the caller wants to see of this step (a halted world keeps recording where it stopped) ----
-      if (has_ball && writer && !P.scan_only) {
+      if (rec_traj) {
         T2 p;
         p.x = pos.x; p.y = pos.y;
-        if (traj) reinterpret_cast<T2 *>(traj)[(long long)(P.step_off + s) * total + base + bi] = p;
-        if (S.snap && P.draw_every > 0 && s >= P.draw_first) {
-          const int r = s - P.draw_first, slot = r / P.draw_every;
-          if (r == slot * P.draw_every) reinterpret_cast<T2 *>(S.snap)[(long long)slot * total + base + bi] = p;
-        }
+        *traj_p = p;
+        traj_p += total;
+      }
+      if (s == next_draw) {
+        T2 p;
+        p.x = pos.x; p.y = pos.y;
+        if (has_ball && writer) *snap_p = p;
+        snap_p += total;
+        next_draw += P.draw_every;
       }
     }
 

@@ -49,7 +49,7 @@ int Launch<T>::advance_grid(int n_worlds, int n_balls, int sm_count) {
   if (occ < 1) occ = 1;
   const int tw = n_balls <= 8 ? 1 : (n_balls <= 16 ? 2 : 4);
   const int teams = PPB_COLLIDE_WARPS / tw;
-  const int need = (n_worlds + teams * PPB_TICKET_WORLDS - 1) / (teams * PPB_TICKET_WORLDS);   // one ticket per team at a time
+  const int need = (n_worlds + teams - 1) / teams;   // at least one world per team
   int grid = sm_count * occ;
   if (grid > need) grid = need;
   return grid < 1 ? 1 : grid;

@@ -189,9 +189,9 @@ def test_pipelined_ring_equals_serial_stepping(n, nb):
     assert np.array_equal(pa, pb) and np.array_equal(va, vb)
 
 
-@pytest.mark.parametrize("steps,every,slots", [(40, 1, 5), (50, 3, 16), (70, 7, 3), (33, 2, 40)])
+@pytest.mark.parametrize("steps,every,slots", [(40, 1, 5), (50, 3, 16), (150, 1, 4), (270, 2, 3), (33, 2, 40)])
 def test_chunked_advance_launches_equal_single_steps(steps, every, slots):
-    """One advance launch covers up to 16 drawn steps (their position snapshots feed the render launches that follow)
+    """One advance launch covers up to 64 drawn steps (their position snapshots feed the render launches that follow)
     and the steps after the last drawn one run without snapshots: frames, trajectories and final state must equal
     stepping and rendering one step at a time, whatever the render period and the ring size."""
     import torch
