@@ -12,6 +12,7 @@
 //   host   : PackPipe -- two job slots; a coordinator thread waits for the packing, starts the token copy and
 //            hands the unpacking to the worker pool; ppb_host_sync waits on the job counter
 #include <emmintrin.h>
+#include <sched.h>
 #include <immintrin.h>
 
 #include <atomic>
@@ -327,8 +328,21 @@ struct PackPipe {
 PackPipe *packpipe_create(int device) {
   PackPipe *p = new PackPipe;
   p->device = device;
+  // unpack threads: the CPUs this process may run on, shared with the other ranks of the node when the process was
+  // started by torchrun (one rank per GPU, all on the same host cores), at most 16
   unsigned hw = std::thread::hardware_concurrency();
-  if (hw == 0) hw = 4;
+  cpu_set_t set;
+  if (sched_getaffinity(0, sizeof set, &set) == 0 && CPU_COUNT(&set) > 0) {
+    const unsigned allowed = (unsigned)CPU_COUNT(&set);
+    if (const char *e = getenv("LOCAL_WORLD_SIZE")) {
+      const int ranks = atoi(e);
+      if (ranks > 1 && allowed == hw) hw = allowed / (unsigned)ranks;   // not pinned: an equal share
+      else hw = allowed;
+    } else {
+      hw = allowed;
+    }
+  }
+  if (hw < 2) hw = 2;
   p->n_workers = hw > 16 ? 16 : hw;
   if (const char *e = getenv("PPB_UNPACK_THREADS")) {
     const int v = atoi(e);

@@ -50,13 +50,13 @@ def main():
     src, dst = os.path.join(ROOT, "gpurun_out"), os.path.join(ROOT, "profiles")
     os.makedirs(dst, exist_ok=True)
     traffic = {}
-    for kern in ("integrate_kernel", "collide_kernel", "render_tile_kernel"):
+    for kern in ("advance_kernel", "render_tile_kernel"):
         rep = os.path.join(src, "%s_full_%s.ncu-rep" % (tag, kern))
         if not os.path.exists(rep):
             continue
         rows, units = raw_page(rep)
         with open(os.path.join(dst, "%s_ncu_%s.txt" % (rnd, kern)), "w") as fh:
-            fh.write("# ncu --set full --import-source on --clock-control none -k regex:%s -s 8 -c 1\n" % kern)
+            fh.write("# ncu --set full --import-source on --clock-control none -k regex:%s -c 1 (after the warm-up launches)\n" % kern)
             fh.write("# python tools/perf_probe.py --worlds 131072 --balls 8 --steps 12 --render --warm 8 --max-substeps 64\n")
             fh.write("# (one steady-state launch; times under ncu are serialised and cold-cache)\n")
             for d in rows:
@@ -71,7 +71,8 @@ def main():
                                  "source": "profiles/%s_ncu_%s.txt" % (rnd, kern)}
             fh.write("\n# heaviest SASS runs (instructions executed per launch)\n")
             fh.write(sass_blocks(rep))
-    for name in ("launches.csv", "bench.json", "bench_reference.json", "pytest_gpu.log", "smoke.log", "sweep.json", "store_ceiling.log"):
+    for name in ("launches.csv", "bench.json", "bench_reference.json", "pytest_gpu.log", "smoke.log", "sweep.json", "store_ceiling.log",
+                 "steps.log", "native.log", "e2e.log"):
         p = os.path.join(src, "%s_%s" % (tag, name))
         if os.path.exists(p):
             shutil.copy(p, os.path.join(dst, "%s_%s" % (rnd, name)))

@@ -8,7 +8,7 @@ wTheta=[30, 60], dataio.py:243-306); the hexagon is one create_cage table (primi
 shared by all worlds, with per-world ball places and velocities drawn on the host.
 
 Every shape is run twice: once plain (ms_per_step / ball_steps_per_s: what a caller gets) and once with
-the library's per-kernel CUDA events switched on (integrate_us / collide_us; the events themselves cost
+the library's per-kernel CUDA events switched on (advance_us_per_launch; the events themselves cost
 about as much as the kernels at this size, so that pass is only used for the split).
 """
 import argparse
@@ -88,9 +88,9 @@ def run(table, n_worlds, n_balls, steps=500, warm=100, max_substeps=64, reps=3):
     status, _ = wb.get_status()
     live = int((status == 0).sum())
     out = dict(table=table, n_worlds=n_worlds, n_balls=n_balls, steps=steps, ms_per_step=ms / steps,
-               ball_steps_per_s=live * n_balls * steps / ms * 1e3, integrate_us=1e3 * kms[0] / max(kn[0], 1),
-               collide_us=1e3 * kms[1] / max(kn[1], 1),
-               collide_world_frac=(c1["collide_world_steps"] - c0["collide_world_steps"]) / (n_worlds * steps * reps),
+               ball_steps_per_s=live * n_balls * steps / ms * 1e3, advance_us_per_launch=1e3 * kms[0] / max(kn[0], 1),
+               advance_launches=kn[0],
+               event_loop_world_frac=(c1["collide_world_steps"] - c0["collide_world_steps"]) / (n_worlds * steps * reps),
                events_per_world_step=(c1["events"] - c0["events"]) / (n_worlds * steps * reps), halted=n_worlds - live,
                max_substeps=max_substeps)
     wb.close()
