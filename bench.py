@@ -317,31 +317,6 @@ def run_ours(args, rank, local_rank, world_size):
     torch.cuda.synchronize(dev)
     render_alone_us = 1e3 * iso0.elapsed_time(iso1) / 5.0
 
-    # ---- the same workload in the bit-exact fp64 mode and under the default sub-step guard (own sub-records; the
-    #      headline `value` is the fp32 run above with the bench's guard of 64) ----
-    def variant(dtype, max_substeps, k_steps, w_steps):
-        vb = WorldBatch(n_worlds, N_BALLS, 4, dtype=dtype, canvas=(CANVAS, CANVAS), device=local_rank,
-                        max_substeps=max_substeps)
-        vb.set_walls(W["wall"])
-        vb.set_balls(W["pos"], W["vel"], W["rad"], W["mass"])
-        vb.set_styles([STYLE_BALL] * N_BALLS, [STYLE_WALL] * 4, 3, 3)
-        vb.step_ring_async(w_steps, frames, 1)
-        torch.cuda.synchronize(dev)
-        v0, v1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
-        v0.record()
-        vb.step_ring_async(k_steps, frames, 1)
-        v1.record()
-        torch.cuda.synchronize(dev)
-        vms = v0.elapsed_time(v1)
-        vst, _ = vb.get_status()
-        vlive = int((vst == 0).sum())
-        vb.close()
-        return {"dtype": dtype, "max_substeps": max_substeps, "steps": k_steps, "warmup": w_steps,
-                "ms_per_step": vms / k_steps, "ball_steps_per_sec_rank0": vlive * N_BALLS * k_steps / (vms * 1e-3),
-                "frames_per_sec_rank0": vlive * k_steps / (vms * 1e-3), "halted_worlds_rank0": n_worlds - vlive}
-    f64_mode = variant("f64", MAX_SUBSTEPS, 5, 3) if rank == 0 else None
-    default_guard = variant("f32", 1 << 20, args.steps, args.warmup) if rank == 0 else None
-
     # ---- end-to-end through the host-buffer API: H2D of the batch state + step + D2H of positions and frames ----
     # Two sets of pinned host buffers: the call of step i only enqueues (ppb_simulate_host_async); while its frames
     # cross PCIe the inputs of step i+1 are uploaded (the other direction) and its kernels run; step i's buffers are
@@ -415,6 +390,31 @@ def run_ours(args, rank, local_rank, world_size):
                                   if distributed else "none (single rank)",
                        "checksum": float(gathered[-1].double().sum().item())}
     del gathered, shard
+
+    # ---- the same workload in the bit-exact fp64 mode and under the default sub-step guard (own sub-records; the
+    #      headline `value` is the fp32 run above with the bench's guard of 64) ----
+    def variant(dtype, max_substeps, k_steps, w_steps):
+        vb = WorldBatch(n_worlds, N_BALLS, 4, dtype=dtype, canvas=(CANVAS, CANVAS), device=local_rank,
+                        max_substeps=max_substeps)
+        vb.set_walls(W["wall"])
+        vb.set_balls(W["pos"], W["vel"], W["rad"], W["mass"])
+        vb.set_styles([STYLE_BALL] * N_BALLS, [STYLE_WALL] * 4, 3, 3)
+        vb.step_ring_async(w_steps, frames, 1)
+        torch.cuda.synchronize(dev)
+        v0, v1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+        v0.record()
+        vb.step_ring_async(k_steps, frames, 1)
+        v1.record()
+        torch.cuda.synchronize(dev)
+        vms = v0.elapsed_time(v1)
+        vst, _ = vb.get_status()
+        vlive = int((vst == 0).sum())
+        vb.close()
+        return {"dtype": dtype, "max_substeps": max_substeps, "steps": k_steps, "warmup": w_steps,
+                "ms_per_step": vms / k_steps, "ball_steps_per_sec_rank0": vlive * N_BALLS * k_steps / (vms * 1e-3),
+                "frames_per_sec_rank0": vlive * k_steps / (vms * 1e-3), "halted_worlds_rank0": n_worlds - vlive}
+    f64_mode = variant("f64", MAX_SUBSTEPS, 5, 3) if rank == 0 else None
+    default_guard = variant("f32", 1 << 20, args.steps, args.warmup) if rank == 0 else None
 
     if rank == 0:
         total_worlds = n_worlds * world_size

@@ -9,7 +9,7 @@ python __graft_entry__.py --smoke > $OUT/${TAG}_smoke.log 2>&1
 python bench.py --impl reference --steps 10 --warmup 3 > $OUT/${TAG}_bench_reference.json 2> $OUT/${TAG}_bench_reference.err
 python bench.py --steps 50 --warmup 5 > $OUT/${TAG}_bench.json 2> $OUT/${TAG}_bench.err
 # launch list of the same command (cold-cache, serialised times: only the SHARES are comparable)
-ncu --metrics gpu__time_duration.sum --clock-control none -c 60 --csv --log-file $OUT/${TAG}_launches.csv \
+ncu --metrics gpu__time_duration.sum --clock-control none -c 40 --csv --log-file $OUT/${TAG}_launches.csv \
     python bench.py --steps 6 --warmup 3 > $OUT/${TAG}_ncu_launches.log 2>&1
 # one full capture per kernel (steady state: skip the first launches)
 # (perf_probe: one warm-up advance launch of 8 steps, then one advance launch of 12 steps with snapshots + 12 renders)

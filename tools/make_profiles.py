@@ -90,7 +90,7 @@ def main():
                 a[1] += float(r["Metric Value"])
         s = sum(v[1] for v in tot.values())
         with open(os.path.join(dst, "%s_launch_shares.txt" % rnd), "w") as fh:
-            fh.write("# ncu --metrics gpu__time_duration.sum --clock-control none -c 60: python bench.py --steps 6 --warmup 3\n")
+            fh.write("# ncu --metrics gpu__time_duration.sum --clock-control none -c 40: python bench.py --steps 6 --warmup 3 (setup, warm-up, the timed steps, the second pass with the advance events, the render-alone loop)\n")
             for k, (n, t) in sorted(tot.items(), key=lambda kv: -kv[1][1]):
                 fh.write("%-40s launches %3d  total %10.1f us  avg %9.1f us  share %5.1f%%\n" % (k, n, t / 1e3, t / 1e3 / n, 100 * t / s))
         print(open(os.path.join(dst, "%s_launch_shares.txt" % rnd)).read())
