@@ -1028,10 +1028,10 @@ static int simulate_host_impl(ppb_batch *b, int32_t n_steps, float *traj_host, u
       const int f0 = done / render_every, nf = (done + cur) / render_every - f0;
       if (nf > 0 && b->pack) {
         std::string perr;
-        if (packpipe_submit(b->pack, buf, b->scr_frames[buf], (long long)nf * (long long)nW, b->RL.W * b->RL.H,
-                            frames_host + (size_t)f0 * frame_bytes, st, &perr))
-          return fail(PPB_E_CUDA, "frame download: %s", perr.c_str());
-        b->launches += 1;
+        const int nl = packpipe_submit(b->pack, buf, b->scr_frames[buf], (long long)nf * (long long)nW, b->RL.W * b->RL.H,
+                                       frames_host + (size_t)f0 * frame_bytes, st, &perr);
+        if (nl < 0) return fail(PPB_E_CUDA, "frame download: %s", perr.c_str());
+        b->launches += nl;
       } else if (nf > 0) {
         CU(cudaMemcpyAsync(frames_host + (size_t)f0 * frame_bytes, b->scr_frames[buf], frame_bytes * nf,
                            cudaMemcpyDeviceToHost, b->copy_stream));
@@ -1084,10 +1084,10 @@ int ppb_download_frames(ppb_batch *b, const uint8_t *frames_dev, int64_t n_frame
   int slot = 0;
   for (int64_t f0 = 0; f0 < n_frames; f0 += per, slot ^= 1) {
     const int64_t nf = std::min<int64_t>(per, n_frames - f0);
-    if (packpipe_submit(b->pack, slot, frames_dev + (size_t)f0 * frame_bytes, nf, b->RL.W * b->RL.H,
-                        frames_host + (size_t)f0 * frame_bytes, st, &perr))
-      return fail(PPB_E_CUDA, "frame download: %s", perr.c_str());
-    b->launches += 1;
+    const int nl = packpipe_submit(b->pack, slot, frames_dev + (size_t)f0 * frame_bytes, nf, b->RL.W * b->RL.H,
+                                   frames_host + (size_t)f0 * frame_bytes, st, &perr);
+    if (nl < 0) return fail(PPB_E_CUDA, "frame download: %s", perr.c_str());
+    b->launches += nl;
   }
   if (packpipe_wait_finished(b->pack, packpipe_submitted(b->pack), &perr))
     return fail(PPB_E_CUDA, "frame download: %s", perr.c_str());

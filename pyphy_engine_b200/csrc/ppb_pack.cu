@@ -13,11 +13,13 @@
 //            hands the unpacking to the worker pool; ppb_host_sync waits on the job counter
 #include <emmintrin.h>
 #include <sched.h>
+#include <unistd.h>
 #include <immintrin.h>
 
 #include <atomic>
 #include <chrono>
 #include <condition_variable>
+#include <cstdio>
 #include <cstdlib>
 #include <cstring>
 #include <deque>
@@ -141,9 +143,66 @@ __attribute__((target("avx2"))) bool unpack_small_avx2(const uint32_t *tokens, c
   return true;
 }
 
+// The same with 512-bit registers: two unconditional 64-byte stores cover a run of up to 32 pixels (the branch for the
+// longer runs -- white rows without a ball -- is rare and predictable), and the block leaves as whole cache lines.
+// Two blocks: while frame k is decoded into one, frame k-1 is streamed out of the other, one line per two tokens, so
+// the streaming stores (bound by the write-combining buffers) and the decoder's L1 stores overlap.
+__attribute__((target("avx512f"))) bool unpack_small_avx512(const uint32_t *tokens, const uint2 *table, long long f0,
+                                                            long long f1, int npx, uint8_t *frames_host) {
+  alignas(64) uint32_t blocks[2][kBlockPx + 128];
+  const int n_lines = npx / 16;
+  uint8_t *prev_dst = nullptr;   // where the frame decoded last goes
+  int prev_line = 0;             // lines of it already streamed
+  int cur = 0;
+#define PPB_STREAM_LINE(src)                                                                          \
+  do {                                                                                                \
+    _mm512_stream_si512(reinterpret_cast<__m512i *>(prev_dst + (size_t)prev_line * 64),               \
+                        _mm512_load_si512((src) + prev_line * 16));                                   \
+    ++prev_line;                                                                                      \
+  } while (0)
+  bool ok = true;
+  for (long long fr = f0; fr < f1 && ok; ++fr) {
+    uint32_t *block = blocks[cur];
+    const uint32_t *pblock = blocks[cur ^ 1];
+    const uint32_t *t = tokens + table[fr].x, *te = t + table[fr].y;
+    uint32_t *p = block;
+    if ((long long)table[fr].y > npx) { ok = false; break; }   // every token holds at least one pixel
+    unsigned k = 0;
+    while (t < te) {
+      const uint32_t tok = *t++;
+      const int cnt = (int)(tok >> 24);
+      const __m512i v = _mm512_set1_epi32((int)(tok | 0xff000000u));
+      _mm512_storeu_si512(p, v);
+      _mm512_storeu_si512(p + 16, v);
+      if (cnt > 32) {
+        if (cnt > 64) { ok = false; break; }
+        _mm512_storeu_si512(p + 32, v);
+        _mm512_storeu_si512(p + 48, v);
+      }
+      p += cnt;
+      if (p > block + kBlockPx) { ok = false; break; }
+      if ((++k & 1u) && prev_dst && prev_line < n_lines) PPB_STREAM_LINE(pblock);
+    }
+    if (p - block != npx) ok = false;
+    if (prev_dst)
+      while (prev_line < n_lines) PPB_STREAM_LINE(pblock);
+    prev_dst = ok ? frames_host + (size_t)fr * npx * 4 : nullptr;
+    prev_line = 0;
+    cur ^= 1;
+  }
+  if (prev_dst)
+    while (prev_line < n_lines) PPB_STREAM_LINE(blocks[cur ^ 1]);
+#undef PPB_STREAM_LINE
+  _mm_sfence();
+  return ok;
+}
+
 // frames [f0, f1) of one job; returns false when a frame's tokens do not add up to its pixel count
 bool unpack_range(const uint32_t *tokens, const uint2 *table, long long f0, long long f1, int npx, uint8_t *frames_host) {
   static const bool have_avx2 = __builtin_cpu_supports("avx2");
+  static const bool have_avx512 = __builtin_cpu_supports("avx512f") && !getenv("PPB_NO_AVX512");
+  if (have_avx512 && npx <= kBlockPx && (npx & 31) == 0 && (reinterpret_cast<uintptr_t>(frames_host) & 63u) == 0)
+    return unpack_small_avx512(tokens, table, f0, f1, npx, frames_host);
   if (have_avx2 && npx <= kBlockPx && (npx & 15) == 0 && (reinterpret_cast<uintptr_t>(frames_host) & 31u) == 0)
     return unpack_small_avx2(tokens, table, f0, f1, npx, frames_host);
   alignas(64) uint32_t block[kBlockPx + 128];
@@ -187,12 +246,26 @@ bool host_check_unpack(const uint32_t *tokens, const uint2 *table, long long f0,
 namespace {
 #endif
 
+constexpr int kMaxPieces = 4;   // a job's packed frames are packed, copied and rebuilt in up to this many pieces
+
+// One ppb_simulate_host* chunk / ppb_download_frames piece.  Frames [0, n_raw) travel raw through the copy engine;
+// frames [n_raw, n_frames) are packed in `n_pieces` pieces, so that the host threads start on the first piece while
+// the tokens of the next ones still cross PCIe (a step's download starts ~1.5 ms instead of ~6 ms after its kernels).
 struct Job {
   int slot = 0;
   const uint8_t *frames_dev = nullptr;
   uint8_t *frames_host = nullptr;
   long long n_frames = 0;
+  long long n_raw = 0;
   int npx = 0;
+  int n_pieces = 0;
+  long long piece_f0[kMaxPieces + 1] = {0};   // piece c = packed frames [piece_f0[c], piece_f0[c + 1]) (relative to n_raw)
+  size_t piece_tok0[kMaxPieces + 1] = {0};    // its region of the slot's token buffer
+  // progress (PackPipe::mu)
+  int pending = 0;            // pieces not yet rebuilt + 1 for the coordinator
+  bool ok = true;
+  double s_tok = 0, s_raw = 0, s_unp = 0;   // seconds: token copies, raw copy, rebuilding (slowest thread, summed over pieces)
+  long long frames_unpacked = 0;
 };
 
 }  // namespace
@@ -203,19 +276,26 @@ struct PackPipe {
   // per slot
   uint32_t *d_tokens[2] = {nullptr, nullptr};
   uint2 *d_table[2] = {nullptr, nullptr};
-  uint32_t *d_ctrl[2] = {nullptr, nullptr};
+  uint32_t *d_ctrl[2] = {nullptr, nullptr};    // 4 words per piece
   uint32_t *h_tokens[2] = {nullptr, nullptr};
   uint2 *h_table[2] = {nullptr, nullptr};
   uint32_t *h_ctrl[2] = {nullptr, nullptr};
   size_t cap_tokens[2] = {0, 0}, cap_frames[2] = {0, 0};
-  cudaEvent_t ev_packed[2] = {nullptr, nullptr};
+  cudaEvent_t ev_packed[2][kMaxPieces] = {};
   cudaStream_t copy_stream = nullptr;
-  // job flow: submit() -> coordinator (copy) -> workers (unpack) -> done
+  // job flow: submit() -> coordinator (copies) -> host threads (rebuild) -> done
   std::mutex mu;
   std::condition_variable cv_coord, cv_work, cv_done;
-  std::deque<Job> q_coord;
-  struct Work { Job job; long long id = 0; std::atomic<long long> next{0}; int left = 0; bool ok = true;
-                std::chrono::steady_clock::time_point t0; };
+  std::deque<Job *> q_coord;
+  struct Work {   // one piece of a job, rebuilt by all host threads together
+    Job *job = nullptr;
+    int piece = 0;
+    long long id = 0;
+    std::atomic<long long> next{0};
+    int left = 0;
+    bool ok = true, started = false;
+    std::chrono::steady_clock::time_point t_start;
+  };
   std::deque<Work *> q_work;
   long long submitted = 0, finished = 0, next_work_id = 0;
   bool slot_busy[2] = {false, false};
@@ -223,22 +303,57 @@ struct PackPipe {
   std::string error;
   long long jobs_raw = 0, jobs_packed = 0;
   unsigned long long bytes_packed = 0, bytes_raw = 0;
-  double us_copy = 0, us_unpack = 0;   // wall time of the token copies / of the unpacking, summed over the packed jobs
+  double us_copy = 0, us_unpack = 0;   // time in the token copies / in the rebuilding, summed over the jobs
+  // Split of a job between the copy engine (raw frames) and the host threads (packed frames): both write the caller's
+  // array at the same time, so a job takes max(token copies + raw copy, rebuilding) and the split that equalises the
+  // two is tracked from the measured costs (seconds per frame; 0: not measured yet).  On the boxes measured the copy
+  // engine reaches ~27 GB/s next to 16 streaming threads (52-57 GB/s alone), the threads 115-140 GB/s.
+  double raw_fraction = 0.1, c_raw = 0, c_tok = 0, c_unp = 0;
+  bool split_fixed = false;
   std::thread coordinator;
   std::vector<std::thread> workers;
 
-  void finish_job(const Job &j, const char *err) {
-    std::lock_guard<std::mutex> lk(mu);
-    if (err && error.empty()) error = err;
-    slot_busy[j.slot] = false;
+  // mu held.  One party of a job (a rebuilt piece, or the coordinator when its copies are done) is finished.
+  void job_part_done(Job *j, bool ok, const char *err) {
+    if (!ok) {
+      j->ok = false;
+      if (error.empty()) error = err;
+    }
+    if (--j->pending > 0) return;
+    us_copy += 1e6 * j->s_tok;
+    us_unpack += 1e6 * j->s_unp;
+    update_split(j);
+    slot_busy[j->slot] = false;
     ++finished;
+    delete j;
     cv_done.notify_all();
+  }
+
+  // mu held
+  void update_split(const Job *j) {
+    auto ema = [](double &c, double v) { c = c > 0 ? 0.5 * c + 0.5 * v : v; };
+    if (j->frames_unpacked > 0) {
+      ema(c_tok, j->s_tok / (double)j->frames_unpacked);
+      ema(c_unp, j->s_unp / (double)j->frames_unpacked);
+    }
+    if (j->n_raw > 0 && j->s_raw > 0) ema(c_raw, j->s_raw / (double)j->n_raw);
+    static const bool debug = getenv("PPB_PACK_DEBUG") != nullptr;
+    if (debug)
+      fprintf(stderr, "[pack] raw %lld frames %.2f ms (%.1f GB/s), tokens %.2f ms, rebuilt %lld frames %.2f ms (%.1f GB/s); split %.3f\n",
+              j->n_raw, 1e3 * j->s_raw, j->s_raw > 0 ? j->n_raw * j->npx * 4e-9 / j->s_raw : 0.0, 1e3 * j->s_tok,
+              j->frames_unpacked, 1e3 * j->s_unp, j->s_unp > 0 ? j->frames_unpacked * j->npx * 4e-9 / j->s_unp : 0.0, raw_fraction);
+    if (split_fixed || c_unp <= 0 || c_raw <= 0) return;
+    // n f c_raw + n (1 - f) c_tok = n (1 - f) c_unp
+    const double gain = c_unp - c_tok;
+    double f = gain > 0 ? gain / (c_raw + gain) : 0.0;
+    f = 0.75 * raw_fraction + 0.25 * f;
+    raw_fraction = f < 0.0 ? 0.0 : (f > 0.6 ? 0.6 : f);
   }
 
   void coordinator_loop() {
     cudaSetDevice(device);
     for (;;) {
-      Job j;
+      Job *j = nullptr;
       {
         std::unique_lock<std::mutex> lk(mu);
         cv_coord.wait(lk, [&] { return stop || !q_coord.empty(); });
@@ -246,46 +361,76 @@ struct PackPipe {
         j = q_coord.front();
         q_coord.pop_front();
       }
-      const int s = j.slot;
-      if (cudaEventSynchronize(ev_packed[s]) != cudaSuccess) { finish_job(j, "pack kernel failed"); continue; }
-      const uint32_t total = h_ctrl[s][0], flags = h_ctrl[s][1];
-      const size_t raw_bytes = (size_t)j.n_frames * j.npx * 4;
-      if (flags) {   // not opaque, or not compressible: the frames travel as they are
-        cudaError_t e = cudaMemcpyAsync(j.frames_host, j.frames_dev, raw_bytes, cudaMemcpyDeviceToHost, copy_stream);
-        if (e == cudaSuccess) e = cudaStreamSynchronize(copy_stream);
-        {
-          std::unique_lock<std::mutex> lk(mu);
-          ++jobs_raw;
-          bytes_raw += raw_bytes;
-          cv_done.wait(lk, [&] { return q_work.empty(); });   // jobs are reported done in submission order
+      const int s = j->slot;
+      const size_t frame_bytes = (size_t)j->npx * 4;
+      const uint8_t *packed_dev = j->frames_dev + (size_t)j->n_raw * frame_bytes;
+      uint8_t *packed_host = j->frames_host + (size_t)j->n_raw * frame_bytes;
+      bool ok = true;
+      const char *err = nullptr;
+      bool any_packed = false;
+      int handled = 0;   // pieces handed to the host threads or finished here
+      for (int c = 0; c < j->n_pieces && ok; ++c) {
+        if (cudaEventSynchronize(ev_packed[s][c]) != cudaSuccess) { ok = false; err = "pack kernel failed"; break; }
+        const uint32_t total = h_ctrl[s][4 * c], flags = h_ctrl[s][4 * c + 1];
+        const long long f0 = j->piece_f0[c], nf = j->piece_f0[c + 1] - f0;
+        const auto t0 = std::chrono::steady_clock::now();
+        if (flags) {   // not opaque, or not compressible: the piece travels as it is
+          cudaError_t e = cudaMemcpyAsync(packed_host + (size_t)f0 * frame_bytes, packed_dev + (size_t)f0 * frame_bytes,
+                                          (size_t)nf * frame_bytes, cudaMemcpyDeviceToHost, copy_stream);
+          if (e == cudaSuccess) e = cudaStreamSynchronize(copy_stream);
+          if (e != cudaSuccess) { ok = false; err = "raw frame copy failed"; }
+          std::lock_guard<std::mutex> lk(mu);
+          bytes_raw += (size_t)nf * frame_bytes;
+          ++handled;
+          job_part_done(j, true, nullptr);   // nothing to rebuild for this piece (pending stays >= 1: the coordinator's own part)
+          continue;
         }
-        finish_job(j, e == cudaSuccess ? nullptr : "raw frame copy failed");
-        continue;
+        cudaError_t e = cudaMemcpyAsync(h_tokens[s] + j->piece_tok0[c], d_tokens[s] + j->piece_tok0[c], (size_t)total * 4,
+                                        cudaMemcpyDeviceToHost, copy_stream);
+        if (e == cudaSuccess)
+          e = cudaMemcpyAsync(h_table[s] + f0, d_table[s] + f0, (size_t)nf * sizeof(uint2), cudaMemcpyDeviceToHost, copy_stream);
+        if (e == cudaSuccess) e = cudaStreamSynchronize(copy_stream);
+        if (e != cudaSuccess) { ok = false; err = "token copy failed"; break; }
+        any_packed = true;
+        Work *w = new Work;
+        w->job = j;
+        w->piece = c;
+        w->left = (int)n_workers;
+        {
+          std::lock_guard<std::mutex> lk(mu);
+          w->id = next_work_id++;
+          j->s_tok += std::chrono::duration<double>(std::chrono::steady_clock::now() - t0).count();
+          bytes_packed += (size_t)total * 4 + (size_t)nf * sizeof(uint2);
+          q_work.push_back(w);
+          ++handled;
+        }
+        cv_work.notify_all();
       }
-      const auto tc0 = std::chrono::steady_clock::now();
-      cudaError_t e = cudaMemcpyAsync(h_tokens[s], d_tokens[s], (size_t)total * 4, cudaMemcpyDeviceToHost, copy_stream);
-      if (e == cudaSuccess)
-        e = cudaMemcpyAsync(h_table[s], d_table[s], (size_t)j.n_frames * sizeof(uint2), cudaMemcpyDeviceToHost, copy_stream);
-      if (e == cudaSuccess) e = cudaStreamSynchronize(copy_stream);
-      if (e != cudaSuccess) { finish_job(j, "token copy failed"); continue; }
-      Work *w = new Work;
-      w->job = j;
-      w->id = next_work_id++;
-      w->left = (int)n_workers;
-      w->t0 = std::chrono::steady_clock::now();
+      if (handled < j->n_pieces) {   // a copy failed: the remaining pieces are never handed out
+        std::lock_guard<std::mutex> lk(mu);
+        j->pending -= j->n_pieces - handled;
+      }
+      // the raw head crosses while the host threads are busy with the packed pieces
+      if (ok && j->n_raw > 0) {
+        const auto t0 = std::chrono::steady_clock::now();
+        cudaError_t e = cudaMemcpyAsync(j->frames_host, j->frames_dev, (size_t)j->n_raw * frame_bytes, cudaMemcpyDeviceToHost,
+                                        copy_stream);
+        if (e == cudaSuccess) e = cudaStreamSynchronize(copy_stream);
+        if (e != cudaSuccess) { ok = false; err = "raw frame copy failed"; }
+        std::lock_guard<std::mutex> lk(mu);
+        j->s_raw = std::chrono::duration<double>(std::chrono::steady_clock::now() - t0).count();
+        bytes_raw += (size_t)j->n_raw * frame_bytes;
+      }
       {
         std::lock_guard<std::mutex> lk(mu);
-        us_copy += std::chrono::duration<double, std::micro>(w->t0 - tc0).count();
-        ++jobs_packed;
-        bytes_packed += (size_t)total * 4 + (size_t)j.n_frames * sizeof(uint2);
-        q_work.push_back(w);
+        if (any_packed) ++jobs_packed; else ++jobs_raw;
+        job_part_done(j, ok, err);
       }
-      cv_work.notify_all();
     }
   }
 
   void worker_loop() {
-    long long my_last = -1;   // id of the last job this thread worked on: every thread takes part in every job once
+    long long my_last = -1;   // id of the last piece this thread worked on: every thread takes part in every piece once
     for (;;) {
       Work *w = nullptr;
       {
@@ -294,32 +439,37 @@ struct PackPipe {
         if (q_work.empty() || q_work.front()->id <= my_last) return;
         w = q_work.front();
         my_last = w->id;
+        if (!w->started) {
+          w->started = true;
+          w->t_start = std::chrono::steady_clock::now();
+        }
       }
-      // frames are handed out in blocks so that a slow thread does not hold the job back
+      const Job *j = w->job;
+      const int c = w->piece;
+      // frames are handed out in blocks so that a slow thread does not hold the piece back
       const long long blockf = 256;
+      const long long p0 = j->piece_f0[c], p1 = j->piece_f0[c + 1];
+      uint8_t *dst = j->frames_host + (size_t)j->n_raw * j->npx * 4;
       bool ok = true;
       for (;;) {
-        const long long f0 = w->next.fetch_add(blockf);
-        if (f0 >= w->job.n_frames) break;
-        const long long f1 = f0 + blockf < w->job.n_frames ? f0 + blockf : w->job.n_frames;
-        ok &= unpack_range(h_tokens[w->job.slot], h_table[w->job.slot], f0, f1, w->job.npx, w->job.frames_host);
+        const long long f0 = p0 + w->next.fetch_add(blockf);
+        if (f0 >= p1) break;
+        const long long f1 = f0 + blockf < p1 ? f0 + blockf : p1;
+        ok &= unpack_range(h_tokens[j->slot] + j->piece_tok0[c], h_table[j->slot], f0, f1, j->npx, dst);
       }
-      bool last = false;
       {
         std::lock_guard<std::mutex> lk(mu);
         if (!ok) w->ok = false;
         if (--w->left == 0) {
-          last = true;
           q_work.pop_front();
-          us_unpack += std::chrono::duration<double, std::micro>(std::chrono::steady_clock::now() - w->t0).count();
+          Job *jj = w->job;
+          jj->s_unp += std::chrono::duration<double>(std::chrono::steady_clock::now() - w->t_start).count();
+          jj->frames_unpacked += p1 - p0;
+          const bool good = w->ok;
+          delete w;
+          job_part_done(jj, good, "packed frame stream is inconsistent");
+          cv_work.notify_all();
         }
-      }
-      if (last) {
-        const Job j = w->job;
-        const bool good = w->ok;
-        delete w;
-        finish_job(j, good ? nullptr : "packed frame stream is inconsistent");
-        cv_work.notify_all();
       }
     }
   }
@@ -328,7 +478,7 @@ struct PackPipe {
 PackPipe *packpipe_create(int device) {
   PackPipe *p = new PackPipe;
   p->device = device;
-  // unpack threads: the CPUs this process may run on, shared with the other ranks of the node when the process was
+  // host threads: the CPUs this process may run on, shared with the other ranks of the node when the process was
   // started by torchrun (one rank per GPU, all on the same host cores), at most 16
   unsigned hw = std::thread::hardware_concurrency();
   cpu_set_t set;
@@ -348,12 +498,23 @@ PackPipe *packpipe_create(int device) {
     const int v = atoi(e);
     if (v >= 1 && v <= 256) p->n_workers = (unsigned)v;
   }
+  if (const char *e = getenv("PPB_RAW_FRACTION")) {   // developer switch: a fixed split instead of the tracked one
+    const double v = atof(e);
+    if (v >= 0.0 && v <= 1.0) { p->raw_fraction = v; p->split_fixed = true; }
+  }
   cudaSetDevice(device);
   if (cudaStreamCreateWithFlags(&p->copy_stream, cudaStreamNonBlocking) != cudaSuccess) { delete p; return nullptr; }
   for (int i = 0; i < 2; ++i)
-    if (cudaEventCreateWithFlags(&p->ev_packed[i], cudaEventDisableTiming) != cudaSuccess) { delete p; return nullptr; }
+    for (int c = 0; c < kMaxPieces; ++c)
+      if (cudaEventCreateWithFlags(&p->ev_packed[i][c], cudaEventDisableTiming) != cudaSuccess) { delete p; return nullptr; }
   p->coordinator = std::thread([p] { p->coordinator_loop(); });
-  for (unsigned i = 0; i < p->n_workers; ++i) p->workers.emplace_back([p] { p->worker_loop(); });
+  for (unsigned i = 0; i < p->n_workers; ++i)
+    p->workers.emplace_back([p] {
+      // the caller's own thread (it uploads the next step's tables and enqueues its kernels) and the coordinator go
+      // first when every CPU is busy rebuilding frames
+      if (nice(5) == -1) { /* not permitted: same priority */ }
+      p->worker_loop();
+    });
   return p;
 }
 
@@ -377,14 +538,18 @@ void packpipe_destroy(PackPipe *p) {
     if (p->h_tokens[i]) cudaFreeHost(p->h_tokens[i]);
     if (p->h_table[i]) cudaFreeHost(p->h_table[i]);
     if (p->h_ctrl[i]) cudaFreeHost(p->h_ctrl[i]);
-    if (p->ev_packed[i]) cudaEventDestroy(p->ev_packed[i]);
+    for (int c = 0; c < kMaxPieces; ++c)
+      if (p->ev_packed[i][c]) cudaEventDestroy(p->ev_packed[i][c]);
   }
   if (p->copy_stream) cudaStreamDestroy(p->copy_stream);
   delete p;
 }
 
+// token capacity of a piece of nf frames: packed frames may take a quarter of the raw size at most
+static size_t piece_capacity(long long nf, int npx) { return (size_t)nf * npx / 4 + 64; }
+
 static cudaError_t reserve_slot(PackPipe *p, int s, long long n_frames, int npx) {
-  const size_t want_tokens = (size_t)n_frames * npx / 4 + 64;   // packed frames may take a quarter of the raw size at most
+  const size_t want_tokens = piece_capacity(n_frames, npx) + 64 * kMaxPieces;
   cudaError_t e = cudaSuccess;
   if (want_tokens > p->cap_tokens[s]) {
     if (p->d_tokens[s]) cudaFree(p->d_tokens[s]);
@@ -403,8 +568,8 @@ static cudaError_t reserve_slot(PackPipe *p, int s, long long n_frames, int npx)
     p->cap_frames[s] = (size_t)n_frames;
   }
   if (!p->d_ctrl[s]) {
-    if ((e = cudaMalloc((void **)&p->d_ctrl[s], 16)) != cudaSuccess) return e;
-    if ((e = cudaHostAlloc((void **)&p->h_ctrl[s], 16, cudaHostAllocDefault)) != cudaSuccess) return e;
+    if ((e = cudaMalloc((void **)&p->d_ctrl[s], 16 * kMaxPieces)) != cudaSuccess) return e;
+    if ((e = cudaHostAlloc((void **)&p->h_ctrl[s], 16 * kMaxPieces, cudaHostAllocDefault)) != cudaSuccess) return e;
   }
   return cudaSuccess;
 }
@@ -412,26 +577,43 @@ static cudaError_t reserve_slot(PackPipe *p, int s, long long n_frames, int npx)
 int packpipe_submit(PackPipe *p, int slot, const uint8_t *frames_dev, long long n_frames, int npx, uint8_t *frames_host,
                     cudaStream_t producer, std::string *err) {
   if (n_frames <= 0) return 0;
+  double f;
   {
     std::unique_lock<std::mutex> lk(p->mu);
     p->cv_done.wait(lk, [&] { return !p->slot_busy[slot]; });   // the slot's previous job has left the host buffers
     if (!p->error.empty()) { *err = p->error; return -1; }
+    f = p->raw_fraction;
   }
-  cudaError_t e = reserve_slot(p, slot, n_frames, npx);
-  if (e == cudaSuccess) e = cudaMemsetAsync(p->d_ctrl[slot], 0, 16, producer);
-  if (e == cudaSuccess) {
-    long long blocks = (n_frames + 7) / 8;
+  Job *j = new Job;
+  j->slot = slot; j->frames_dev = frames_dev; j->frames_host = frames_host; j->n_frames = n_frames; j->npx = npx;
+  // the head of the job goes raw through the copy engine, the rest is packed in pieces (small jobs: one packed piece)
+  if (n_frames >= 4096) {
+    j->n_raw = (long long)(f * (double)n_frames) / 256 * 256;
+    if (j->n_raw > n_frames - 256) j->n_raw = n_frames - 256;
+  }
+  const long long n_packed = n_frames - j->n_raw;
+  j->n_pieces = n_packed >= 8192 ? kMaxPieces : 1;
+  for (int c = 0; c <= j->n_pieces; ++c) j->piece_f0[c] = c == j->n_pieces ? n_packed : (n_packed / j->n_pieces) / 256 * 256 * c;
+  for (int c = 0; c < j->n_pieces; ++c)
+    j->piece_tok0[c + 1] = j->piece_tok0[c] + piece_capacity(j->piece_f0[c + 1] - j->piece_f0[c], npx);
+  j->pending = j->n_pieces + 1;
+  const int n_launched = j->n_pieces;
+  cudaError_t e = reserve_slot(p, slot, n_frames, npx);   // sized for the whole job: the split moves
+  if (e == cudaSuccess) e = cudaMemsetAsync(p->d_ctrl[slot], 0, 16 * kMaxPieces, producer);
+  for (int c = 0; c < j->n_pieces && e == cudaSuccess; ++c) {
+    const long long f0 = j->piece_f0[c], nf = j->piece_f0[c + 1] - f0;
+    long long blocks = (nf + 7) / 8;
     if (blocks > 148 * 8) blocks = 148 * 8;
-    pack_frames_kernel<<<(unsigned)blocks, 256, 0, producer>>>(reinterpret_cast<const uint32_t *>(frames_dev), n_frames, npx,
-                                                               p->d_tokens[slot], (uint32_t)(p->cap_tokens[slot] - 64),
-                                                               p->d_table[slot], p->d_ctrl[slot]);
+    pack_frames_kernel<<<(unsigned)blocks, 256, 0, producer>>>(
+        reinterpret_cast<const uint32_t *>(frames_dev + (size_t)(j->n_raw + f0) * npx * 4), nf, npx,
+        p->d_tokens[slot] + j->piece_tok0[c], (uint32_t)(piece_capacity(nf, npx) - 64), p->d_table[slot] + f0,
+        p->d_ctrl[slot] + 4 * c);
     e = cudaGetLastError();
+    if (e == cudaSuccess)
+      e = cudaMemcpyAsync(p->h_ctrl[slot] + 4 * c, p->d_ctrl[slot] + 4 * c, 16, cudaMemcpyDeviceToHost, producer);
+    if (e == cudaSuccess) e = cudaEventRecord(p->ev_packed[slot][c], producer);
   }
-  if (e == cudaSuccess) e = cudaMemcpyAsync(p->h_ctrl[slot], p->d_ctrl[slot], 16, cudaMemcpyDeviceToHost, producer);
-  if (e == cudaSuccess) e = cudaEventRecord(p->ev_packed[slot], producer);
-  if (e != cudaSuccess) { *err = cudaGetErrorString(e); return -1; }
-  Job j;
-  j.slot = slot; j.frames_dev = frames_dev; j.frames_host = frames_host; j.n_frames = n_frames; j.npx = npx;
+  if (e != cudaSuccess) { *err = cudaGetErrorString(e); delete j; return -1; }
   {
     std::lock_guard<std::mutex> lk(p->mu);
     p->slot_busy[slot] = true;
@@ -439,7 +621,7 @@ int packpipe_submit(PackPipe *p, int slot, const uint8_t *frames_dev, long long 
     p->q_coord.push_back(j);
   }
   p->cv_coord.notify_one();
-  return 0;
+  return n_launched;
 }
 
 long long packpipe_submitted(PackPipe *p) {
