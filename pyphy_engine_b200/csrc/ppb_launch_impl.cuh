@@ -1,6 +1,7 @@
 // ppb_launch_impl.cuh -- body of Launch<T>, included by ppb_f32.cu / ppb_f64.cu
 #pragma once
 #include <cstdlib>
+#include <cstring>
 
 #include "ppb_kernels.cuh"
 #include "ppb_launch.h"
@@ -19,6 +20,31 @@ static inline bool pdl_enabled() {
     on = (e && e[0] == '1') ? 0 : 1;
   }
   return on == 1;
+}
+
+// Tensor map over a frame buffer seen as `n_lines` rows of 128 bytes (32 RGBA pixels), box = `box_lines` rows, stored
+// with the copy engine's 128-byte swizzle (render_tile_kernel, mode PPB_RM_SWZ).  The encoder is a driver function;
+// the library links the static runtime only, so it is looked up once through the runtime.
+static inline cudaError_t encode_frame_lines_map(CUtensorMap *out, void *frames, unsigned long long n_lines, unsigned box_lines) {
+  typedef CUresult (*encode_fn)(CUtensorMap *, CUtensorMapDataType, cuuint32_t, void *, const cuuint64_t *, const cuuint64_t *,
+                                const cuuint32_t *, const cuuint32_t *, CUtensorMapInterleave, CUtensorMapSwizzle,
+                                CUtensorMapL2promotion, CUtensorMapFloatOOBfill);
+  static encode_fn encode = nullptr;
+  if (!encode) {
+    void *fn = nullptr;
+    cudaDriverEntryPointQueryResult qres;
+    cudaError_t e = cudaGetDriverEntryPoint("cuTensorMapEncodeTiled", &fn, cudaEnableDefault, &qres);
+    if (e != cudaSuccess) return e;
+    if (qres != cudaDriverEntryPointSuccess || !fn) return cudaErrorNotSupported;
+    encode = reinterpret_cast<encode_fn>(fn);
+  }
+  const cuuint64_t dims[2] = {32, n_lines};
+  const cuuint64_t strides[1] = {128};            // bytes between rows
+  const cuuint32_t box[2] = {32, box_lines};
+  const cuuint32_t estr[2] = {1, 1};
+  const CUresult r = encode(out, CU_TENSOR_MAP_DATA_TYPE_UINT32, 2, frames, dims, strides, box, estr, CU_TENSOR_MAP_INTERLEAVE_NONE,
+                            CU_TENSOR_MAP_SWIZZLE_128B, CU_TENSOR_MAP_L2_PROMOTION_NONE, CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE);
+  return r == CUDA_SUCCESS ? cudaSuccess : cudaErrorInvalidValue;
 }
 
 template <typename... KArgs, typename... Args>
@@ -142,6 +168,16 @@ cudaError_t Launch<T>::render(const StatePtrs &S, const Layout &L, const RenderL
     }
     const int warps = render_warps(L.n_walls, L.n_balls);
     const int smem = (int)(warps * render_warp_smem_bytes(L.n_walls, L.n_balls));
+    // the 64-pixel canvas: swizzled tile, tensor-map store (frames as an array of 128-byte lines, box = one frame)
+    static const bool no_swz = getenv("PPB_NO_SWIZZLE") != nullptr;   // developer switch (A/B timing)
+    const bool swz = !band && !no_swz && RL.W == PPB_TILE && RL.H <= PPB_TILE &&
+                     (reinterpret_cast<uintptr_t>(frames) & 15u) == 0 && (long long)S.n_worlds * 2 * RL.H <= 2147483647LL;
+    CUtensorMap tmap;
+    memset(&tmap, 0, sizeof tmap);
+    if (swz) {
+      cudaError_t e = encode_frame_lines_map(&tmap, frames, (unsigned long long)S.n_worlds * 2ull * (unsigned)RL.H, 2u * (unsigned)RL.H);
+      if (e != cudaSuccess) return e;
+    }
     const int smem_max = 227 * 1024;
     // per device (and per instantiation T): SM count, opt-in to the large dynamic shared memory
     static int sm_counts[64] = {0};
@@ -151,18 +187,36 @@ cudaError_t Launch<T>::render(const StatePtrs &S, const Layout &L, const RenderL
     if (!sm_counts[dev]) {
       int n = 0;
       cudaDeviceGetAttribute(&n, cudaDevAttrMultiProcessorCount, dev);
-      cudaError_t e = cudaFuncSetAttribute(render_tile_kernel<T, false>, cudaFuncAttributeMaxDynamicSharedMemorySize, smem_max);
+      cudaError_t e = cudaFuncSetAttribute(render_tile_kernel<T, PPB_RM_TILE>, cudaFuncAttributeMaxDynamicSharedMemorySize, smem_max);
       if (e != cudaSuccess) return e;
-      e = cudaFuncSetAttribute(render_tile_kernel<T, true>, cudaFuncAttributeMaxDynamicSharedMemorySize, smem_max);
+      e = cudaFuncSetAttribute(render_tile_kernel<T, PPB_RM_BAND>, cudaFuncAttributeMaxDynamicSharedMemorySize, smem_max);
+      if (e != cudaSuccess) return e;
+      e = cudaFuncSetAttribute(render_tile_kernel<T, PPB_RM_SWZ>, cudaFuncAttributeMaxDynamicSharedMemorySize, smem_max);
       if (e != cudaSuccess) return e;
       sm_counts[dev] = n > 0 ? n : 1;
     }
     const int sm_count = sm_counts[dev];
+    // ticket counters of the dynamic tile hand-out: a ring of {next ticket, warps done} pairs per device, so that render
+    // launches in flight on different streams never share one; a launch leaves its pair zeroed
+    constexpr int kCtrRing = 256;
+    static uint32_t *ctr_ring[64] = {nullptr};
+    static unsigned ctr_next[64] = {0};
+    if (!ctr_ring[dev]) {
+      cudaError_t e = cudaMalloc((void **)&ctr_ring[dev], kCtrRing * 2 * sizeof(uint32_t));
+      if (e == cudaSuccess) e = cudaMemset(ctr_ring[dev], 0, kCtrRing * 2 * sizeof(uint32_t));
+      if (e != cudaSuccess) return e;
+    }
+    uint32_t *tile_ctr = ctr_ring[dev] + 2 * (ctr_next[dev]++ % kCtrRing);
+    static const bool static_split = getenv("PPB_RENDER_STATIC") != nullptr;   // developer switch (A/B timing)
+    if (static_split) tile_ctr = nullptr;
+    // tiles per ticket (see the kernel; 4 - 8 measured alike, 346 - 348 us per launch of 131,072 frames)
+    static const uint32_t chunk = getenv("PPB_RENDER_CHUNK") ? (uint32_t)atoi(getenv("PPB_RENDER_CHUNK")) : 6u;
     // persistent: one CTA of `warps` warps per SM, every warp walks the tile list
     long long blocks = (jobs + warps - 1) / warps;
     if (blocks > sm_count) blocks = sm_count;
-    if (band) render_tile_kernel<T, true><<<(unsigned)blocks, warps * 32, smem, st>>>(S, L, RL, atlas, frames);
-    else render_tile_kernel<T, false><<<(unsigned)blocks, warps * 32, smem, st>>>(S, L, RL, atlas, frames);
+    if (band) render_tile_kernel<T, PPB_RM_BAND><<<(unsigned)blocks, warps * 32, smem, st>>>(S, L, RL, atlas, frames, tmap, tile_ctr, chunk);
+    else if (swz) render_tile_kernel<T, PPB_RM_SWZ><<<(unsigned)blocks, warps * 32, smem, st>>>(S, L, RL, atlas, frames, tmap, tile_ctr, chunk);
+    else render_tile_kernel<T, PPB_RM_TILE><<<(unsigned)blocks, warps * 32, smem, st>>>(S, L, RL, atlas, frames, tmap, tile_ctr, chunk);
   } else {
     if (jobs > 2147483647LL) return cudaErrorInvalidValue;
     render_general_kernel<T><<<(unsigned)jobs, 256, 0, st>>>(S, L, RL, atlas, frames);

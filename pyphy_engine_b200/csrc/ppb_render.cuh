@@ -18,6 +18,8 @@
 // One CTA rasterises one 64x64 tile of one world's canvas; each thread owns runs of 4 pixels
 // (one 128-bit store), the world's walls and balls are staged in shared memory.
 #pragma once
+#include <cuda.h>   // CUtensorMap (the encoder itself is fetched through cudaGetDriverEntryPoint, see ppb_launch_impl.cuh)
+
 #include "ppb_common.cuh"
 
 namespace ppb {
@@ -316,10 +318,14 @@ struct RenderWarpSmem {
   SWallGeom *w;        // [n_walls]
   RTBall *b;           // [n_balls]
 };
-__host__ __device__ inline size_t render_warp_smem_bytes(int n_walls, int n_balls) {
+__host__ __device__ inline size_t render_warp_meta_bytes(int n_walls, int n_balls) {
   size_t meta = (size_t)n_walls * (sizeof(int4) + sizeof(int4) + sizeof(SWallGeom)) + (size_t)n_balls * sizeof(RTBall);
-  meta = (meta + 15) & ~(size_t)15;
-  return (size_t)PPB_TILE * PPB_TILE * 4 + meta;
+  return (meta + 15) & ~(size_t)15;
+}
+// The CTA's shared memory: the tiles of all warps first (16 KB each, so every tile is 1024-byte aligned -- what the
+// swizzled tensor-map store needs), then the metadata of all warps.
+__host__ __device__ inline size_t render_warp_smem_bytes(int n_walls, int n_balls) {
+  return (size_t)PPB_TILE * PPB_TILE * 4 + render_warp_meta_bytes(n_walls, n_balls);
 }
 // warps per CTA for a batch layout: fill the 227 KB, minus the spare for co-resident collide CTAs
 inline int render_warps(int n_walls, int n_balls) {
@@ -334,6 +340,17 @@ __device__ __forceinline__ void bulk_store_s2g(void *gdst, const void *ssrc, uin
                "r"((uint32_t)__cvta_generic_to_shared(ssrc)), "r"(bytes)
                : "memory");
 }
+// One 2-D tensor-map store of a 128-byte-swizzled tile: rows of 128 bytes (32 pixels), `row0` = first row of the box
+// in the tensor (frames seen as an array of 128-byte lines).
+__device__ __forceinline__ void bulk_tensor_store_2d(const CUtensorMap *tmap, int row0, const void *ssrc) {
+  asm volatile("cp.async.bulk.tensor.2d.global.shared::cta.bulk_group [%0, {%1, %2}], [%3];" ::"l"(tmap), "r"(0), "r"(row0),
+               "r"((uint32_t)__cvta_generic_to_shared(ssrc))
+               : "memory");
+}
+// 128-byte swizzle of the copy engine (CU_TENSOR_MAP_SWIZZLE_128B): the 16-byte chunk index inside a 128-byte line is
+// XORed with the line index modulo 8.  w = pixel (32-bit word) index in a 1024-byte aligned tile, ch = 16-byte chunk index.
+template <bool SWZ> __device__ __forceinline__ uint32_t swz_w(uint32_t w) { return SWZ ? (w ^ ((w >> 3) & 0x1cu)) : w; }
+template <bool SWZ> __device__ __forceinline__ int swz_ch(int ch) { return SWZ ? (ch ^ ((ch >> 3) & 7)) : ch; }
 __device__ __forceinline__ void bulk_commit() { asm volatile("cp.async.bulk.commit_group;" ::: "memory"); }
 __device__ __forceinline__ void bulk_wait_read0() { asm volatile("cp.async.bulk.wait_group.read 0;" ::: "memory"); }
 __device__ __forceinline__ void bulk_wait0() { asm volatile("cp.async.bulk.wait_group 0;" ::: "memory"); }
@@ -370,22 +387,34 @@ __global__ void wall_cache_kernel(StatePtrs S, int n_walls, RenderLayout RL, int
 //               ONE linear bulk copy whatever the width.  (Square tiles of a wide canvas leave as 64 row pieces of
 //               256 bytes; with W = 700 every other row starts 16 bytes off a 32-byte sector and the partial-sector
 //               writes halve the store rate: 2.1 TB/s against 3.9 TB/s at W = 704.)
-template <typename T, bool BAND>
-__global__ void __maxnreg__(120) render_tile_kernel(StatePtrs S, Layout L, RenderLayout RL,
-                                                                           const uint32_t *atlas, uint8_t *frames) {
+// MODE 2      : the 64-pixel-wide canvas of at most 64 rows (the whole frame is one tile).  The tile is kept in the copy
+//               engine's 128-byte swizzle and leaves through a 2-D tensor map (frames = an array of 128-byte lines,
+//               box = 32 pixels x 2 H lines): rows of the tile no longer alias on the same banks, so the 8-pixel-wide
+//               sprites and the tall walls stop replaying their shared-memory accesses 4-8 times.
+#define PPB_RM_TILE 0
+#define PPB_RM_BAND 1
+#define PPB_RM_SWZ 2
+template <typename T, int MODE>
+__global__ void __maxnreg__(120) render_tile_kernel(StatePtrs S, Layout L, RenderLayout RL, const uint32_t *atlas,
+                                                    uint8_t *frames, const __grid_constant__ CUtensorMap tmap,
+                                                    uint32_t *tile_ctr, uint32_t kChunk) {
   typedef typename Vec2<T>::type T2;
-  extern __shared__ __align__(128) unsigned char render_smem_raw[];
+  constexpr bool BAND = MODE == PPB_RM_BAND;
+  constexpr bool SWZ = MODE == PPB_RM_SWZ;
+  extern __shared__ __align__(1024) unsigned char render_smem_raw[];
   const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
   const int n_warps = blockDim.x >> 5;
   RenderWarpSmem sm;
   {
-    unsigned char *base = render_smem_raw + (size_t)warp * render_warp_smem_bytes(L.n_walls, L.n_balls);
-    sm.tile = reinterpret_cast<uint32_t *>(base);
-    sm.wpaint = reinterpret_cast<int4 *>(base + (size_t)PPB_TILE * PPB_TILE * 4);
+    unsigned char *base = render_smem_raw + (size_t)n_warps * PPB_TILE * PPB_TILE * 4 +
+                          (size_t)warp * render_warp_meta_bytes(L.n_walls, L.n_balls);
+    sm.tile = reinterpret_cast<uint32_t *>(render_smem_raw + (size_t)warp * PPB_TILE * PPB_TILE * 4);
+    sm.wpaint = reinterpret_cast<int4 *>(base);
     sm.wspan = sm.wpaint + L.n_walls;                                      // 16-byte records first
     sm.b = reinterpret_cast<RTBall *>(sm.wspan + L.n_walls);
     sm.w = reinterpret_cast<SWallGeom *>(sm.b + L.n_balls);                // 4-byte aligned members only
   }
+  if (SWZ && (__cvta_generic_to_shared(render_smem_raw) & 1023u) != 0) __trap();   // the swizzle is a function of the address
   // pixels per tile row (row stride in the buffer; a band pads it to a multiple of 4) and rows per tile
   const int RS = BAND ? ((RL.W + 3) & ~3) : PPB_TILE;
   const int RH = BAND ? (PPB_TILE * PPB_TILE) / RS : PPB_TILE;
@@ -408,8 +437,42 @@ __global__ void __maxnreg__(120) render_tile_kernel(StatePtrs S, Layout L, Rende
   bp.x = bp.y = T(0);
   // small-sprite walk cached per lane: key = (visible width, height, sprite side), offsets of the lane's two pixels
   uint32_t sp_key = 0u, sp_t1 = 0xffffffffu, sp_t2 = 0xffffffffu, sp_d1 = 0u, sp_d2 = 0u;
+  // Tiles are handed out dynamically: a warp's first tile comes from its grid index, every further one from a global
+  // ticket (tile_ctr[0]); the SMs do not all drain their stores at the same rate (ncu: 595 k - 740 k active cycles per
+  // scheduler under an equal static split), and the launch ends when the slowest one does.  The ticket for the tile
+  // after next is drawn one iteration ahead, so its latency and the next tile's state loads hide behind the drawing.
   const long long job0 = (long long)blockIdx.x * n_warps + warp;
-  const long long jstride = (long long)gridDim.x * n_warps;
+  const long long n_static = (long long)gridDim.x * n_warps;
+  // (the atomic's result stays in lane 0's register until the next iteration broadcasts it: a shuffle right behind the
+  // atomic would stall the warp for the round trip to L2)
+  long long static_next = job0;   // (developer switch: tile_ctr == nullptr = the static round-robin split)
+  // One atomic per tile on one address is more than an L2 slice takes (380 us per launch), and a ticket worth several
+  // CONSECUTIVE frames is slow for another reason: frames that are neighbours in memory should be written at about the
+  // same time, by different warps (tickets of 2 / 4 / 8 consecutive frames: 345 / 357 / 371 us).  So a ticket t of the
+  // first phase is worth kChunk tiles that are A / kChunk apart -- the grid then fills kChunk windows of the frame array in
+  // order, like the static split fills one -- and the last 3 tiles per warp are handed out one by one (no warp is left
+  // working alone on a long ticket at the end).
+  uint32_t ticket_raw = 0u, chunk_left = 0u;
+  long long chunk_job = 0;
+  const long long n_dyn = total > n_static ? total - n_static : 0;
+  const long long A_per = kChunk > 1u && n_dyn > 3 * n_static ? (n_dyn - 3 * n_static) / kChunk : 0;   // tickets of phase A
+  const long long A = A_per * kChunk;
+  auto request_ticket = [&]() {
+    if (!tile_ctr) { static_next += n_static; return; }
+    if (chunk_left == 0u && lane == 0) ticket_raw = atomicAdd(tile_ctr, 1u);
+  };
+  auto ticket_job = [&]() -> long long {
+    if (!tile_ctr) return static_next;
+    if (chunk_left == 0u) {
+      const long long t = (long long)__shfl_sync(0xffffffffu, ticket_raw, 0);
+      if (t < A_per) { chunk_job = n_static + t; chunk_left = kChunk; }
+      else { chunk_job = n_static + A + (t - A_per); chunk_left = 1u; }
+    }
+    --chunk_left;
+    const long long j = chunk_job;
+    chunk_job += A_per;
+    return j;
+  };
   auto load_world = [&](int wn) {
     if (lane < nWl) {
       const uint4 *src = reinterpret_cast<const uint4 *>(reinterpret_cast<const WallRC *>(S.wall_rc) + ((long long)wn * nWl + lane));
@@ -421,7 +484,8 @@ __global__ void __maxnreg__(120) render_tile_kernel(StatePtrs S, Layout L, Rende
     }
   };
   if (job0 < total) load_world((tiles == 1) ? (int)job0 : (int)(job0 / tiles));
-  for (long long job = job0; job < total; job += jstride) {
+  if (job0 < total) request_ticket();
+  for (long long job = job0; job < total;) {
     int w = (int)job, tx0 = 0, ty0 = 0;
     if (tiles != 1) {
       w = (int)(job / tiles);
@@ -437,12 +501,11 @@ __global__ void __maxnreg__(120) render_tile_kernel(StatePtrs S, Layout L, Rende
     const uint4 c0 = rc0, c1 = rc1, c2 = rc2;
     const T2 cbp = bp;
     const T cbrad = brad;
-    {
-      const long long nj = job + jstride;
-      if (nj < total) {
-        const int wn = (tiles == 1) ? (int)nj : (int)(nj / tiles);
-        if (wn != w) load_world(wn);
-      }
+    const long long nj = ticket_job();   // requested one iteration ago
+    if (nj < total) {
+      const int wn = (tiles == 1) ? (int)nj : (int)(nj / tiles);
+      if (wn != w) load_world(wn);
+      request_ticket();
     }
     if (lane < nWl) {
       const float wx0 = __uint_as_float(c0.x), wx1 = __uint_as_float(c0.y);
@@ -540,13 +603,14 @@ __global__ void __maxnreg__(120) render_tile_kernel(StatePtrs S, Layout L, Rende
       const int4 span = sm.wspan[q];
       const int items = span.w;
       const float inv_ncg = __int_as_float(span.z);
-      uint4 *base = reinterpret_cast<uint4 *>(sm.tile) + r0 * RS4 + g0;
+      uint4 *tile4 = reinterpret_cast<uint4 *>(sm.tile);
+      const int ch0 = r0 * RS4 + g0;
       if (h.x == PPB_WM_SOLID) {
         const uint32_t width = (uint32_t)(span.y - span.x);
         for (int i = lane; i < items; i += 32) {
           const int r = (int)(((float)i + 0.5f) * inv_ncg);
           const int c = i - r * ncg;
-          uint4 *p = base + r * RS4 + c;
+          uint4 *p = tile4 + swz_ch<SWZ>(ch0 + r * RS4 + c);
           const uint32_t d = (uint32_t)(((g0 + c) << 2) - span.x);   // pixel k of the group is inside iff d + k < width
           uint4 v = *p;
           v.x = (d < width) ? col : v.x;
@@ -560,7 +624,7 @@ __global__ void __maxnreg__(120) render_tile_kernel(StatePtrs S, Layout L, Rende
         for (int i = lane; i < items; i += 32) {
           const int r = (int)(((float)i + 0.5f) * inv_ncg);
           const int c = i - r * ncg;
-          uint4 *p = base + r * RS4 + c;
+          uint4 *p = tile4 + swz_ch<SWZ>(ch0 + r * RS4 + c);
           const int x = tx0 + ((g0 + c) << 2), y = ty0 + r0 + r;
           uint4 v = *p;
           if (h.x == PPB_WM_FAST) {
@@ -608,6 +672,7 @@ __global__ void __maxnreg__(120) render_tile_kernel(StatePtrs S, Layout L, Rende
         }
         const uint32_t dst = ra.y & 0xffffu;
         const bool v1 = sp_t1 != 0xffffffffu, v2 = sp_t2 != 0xffffffffu;
+        const uint32_t a1 = swz_w<SWZ>(dst + sp_d1), a2 = swz_w<SWZ>(dst + sp_d2);
         // the next ball, when it has the same visible geometry and does not touch this one's pixels, is
         // composited in the same trip: four independent load -> blend -> store chains instead of two
         // (measured: step 0.459 -> 0.421 ms; grouping up to four sprites was slower again, 0.459 ms)
@@ -615,16 +680,17 @@ __global__ void __maxnreg__(120) render_tile_kernel(StatePtrs S, Layout L, Rende
           if ((pair_mask >> b) & 1u) {
             const uint2 rn = reinterpret_cast<const uint2 *>(&sm.b[b + 1])[0];   // tex, dst_sz of the partner
             const uint32_t dstn = rn.y & 0xffffu;
+            const uint32_t n1 = swz_w<SWZ>(dstn + sp_d1), n2 = swz_w<SWZ>(dstn + sp_d2);
             const uint32_t t1 = v1 ? __ldg(atlas + ra.x + sp_t1) : 0u;
             const uint32_t t2 = v2 ? __ldg(atlas + ra.x + sp_t2) : 0u;
             const uint32_t u1 = v1 ? __ldg(atlas + rn.x + sp_t1) : 0u;
             const uint32_t u2 = v2 ? __ldg(atlas + rn.x + sp_t2) : 0u;
-            const uint32_t d1 = v1 ? sm.tile[dst + sp_d1] : 0u;
-            const uint32_t d2 = v2 ? sm.tile[dst + sp_d2] : 0u;
-            const uint32_t e1 = v1 ? sm.tile[dstn + sp_d1] : 0u;
-            const uint32_t e2 = v2 ? sm.tile[dstn + sp_d2] : 0u;
-            if (v1) { sm.tile[dst + sp_d1] = over_nb(t1, d1); sm.tile[dstn + sp_d1] = over_nb(u1, e1); }
-            if (v2) { sm.tile[dst + sp_d2] = over_nb(t2, d2); sm.tile[dstn + sp_d2] = over_nb(u2, e2); }
+            const uint32_t d1 = v1 ? sm.tile[a1] : 0u;
+            const uint32_t d2 = v2 ? sm.tile[a2] : 0u;
+            const uint32_t e1 = v1 ? sm.tile[n1] : 0u;
+            const uint32_t e2 = v2 ? sm.tile[n2] : 0u;
+            if (v1) { sm.tile[a1] = over_nb(t1, d1); sm.tile[n1] = over_nb(u1, e1); }
+            if (v2) { sm.tile[a2] = over_nb(t2, d2); sm.tile[n2] = over_nb(u2, e2); }
             __syncwarp();
             ++b;
             continue;
@@ -632,10 +698,10 @@ __global__ void __maxnreg__(120) render_tile_kernel(StatePtrs S, Layout L, Rende
         }
         const uint32_t t1 = v1 ? __ldg(atlas + ra.x + sp_t1) : 0u;
         const uint32_t t2 = v2 ? __ldg(atlas + ra.x + sp_t2) : 0u;
-        const uint32_t d1 = v1 ? sm.tile[dst + sp_d1] : 0u;
-        const uint32_t d2 = v2 ? sm.tile[dst + sp_d2] : 0u;
-        if (v1) sm.tile[dst + sp_d1] = over_nb(t1, d1);
-        if (v2) sm.tile[dst + sp_d2] = over_nb(t2, d2);
+        const uint32_t d1 = v1 ? sm.tile[a1] : 0u;
+        const uint32_t d2 = v2 ? sm.tile[a2] : 0u;
+        if (v1) sm.tile[a1] = over_nb(t1, d1);
+        if (v2) sm.tile[a2] = over_nb(t2, d2);
         __syncwarp();
         continue;
       }
@@ -655,10 +721,11 @@ __global__ void __maxnreg__(120) render_tile_kernel(StatePtrs S, Layout L, Rende
         const bool has2 = sy2 < ah;
         const uint32_t t = __ldg(atlas + ti);
         const uint32_t t2 = has2 ? __ldg(atlas + ti2) : 0u;
-        const uint32_t d = sm.tile[di];
-        const uint32_t d2 = has2 ? sm.tile[di2] : 0u;
-        sm.tile[di] = over_nb(t, d);
-        if (has2) sm.tile[di2] = over_nb(t2, d2);
+        const uint32_t ai = swz_w<SWZ>(di), ai2 = swz_w<SWZ>(di2);
+        const uint32_t d = sm.tile[ai];
+        const uint32_t d2 = has2 ? sm.tile[ai2] : 0u;
+        sm.tile[ai] = over_nb(t, d);
+        if (has2) sm.tile[ai2] = over_nb(t2, d2);
         sx = sx2 + dr; sy = sy2 + dq; ti = ti2 + rb.x; di = di2 + rb.y;
         if (sx >= aw) { sx -= aw; ++sy; ti += wti; di += wdi; }
       }
@@ -668,7 +735,10 @@ __global__ void __maxnreg__(120) render_tile_kernel(StatePtrs S, Layout L, Rende
     fence_async_smem();   // this lane's generic-proxy writes become visible to the async proxy
     __syncwarp();
     uint32_t *out = reinterpret_cast<uint32_t *>(frames) + (size_t)w * RL.W * RL.H;
-    if (BAND && !bulk_ok) {
+    if (SWZ) {
+      // (the launcher only picks this mode for 16-byte aligned frames of 64 x H pixels, H <= 64: one tile per frame)
+      if (lane == 0) bulk_tensor_store_2d(&tmap, w * (2 * RL.H), sm.tile);
+    } else if (BAND && !bulk_ok) {
       // Rows of this canvas are not 16-byte multiples (the reference's default arenaSz = 667) or the frame buffer
       // is not 16-byte aligned: the copy engine cannot take the band.  It is still one contiguous run of
       // th * W pixels in the frame, so the warp streams it out with 16-byte stores from the first aligned pixel
@@ -716,6 +786,16 @@ __global__ void __maxnreg__(120) render_tile_kernel(StatePtrs S, Layout L, Rende
         bulk_store_s2g(out + (size_t)(ty0 + r) * RL.W + tx0, sm.tile + r * RS, row_bytes);
     }
     bulk_commit();
+    job = nj;
+  }
+  // the last warp of the grid to get here re-arms the ticket counter for the next launch that uses it
+  if (lane == 0 && tile_ctr) {
+    __threadfence();
+    if (atomicAdd(tile_ctr + 1, 1u) == (uint32_t)(n_static - 1)) {
+      tile_ctr[0] = 0u;
+      tile_ctr[1] = 0u;
+      __threadfence();
+    }
   }
   bulk_wait0();   // smem must stay valid until the copy engine has read it; writes complete before exit
 }
