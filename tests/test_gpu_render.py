@@ -285,9 +285,11 @@ def test_full_size_frame_properties():
 
 
 @pytest.mark.parametrize("canvas", [(32, 48), (128, 70), (700, 333), (1000, 37), (2048, 9), (4096, 5), (4100, 6), (68, 64),
-                                    (667, 41), (33, 70), (1001, 9), (2047, 4), (4095, 3), (63, 65)])
+                                    (667, 41), (33, 70), (1001, 9), (2047, 4), (4095, 3), (63, 65),
+                                    (64, 64), (64, 48), (64, 9), (64, 63), (64, 100), (64, 130)])
 def test_frames_band_tiles_identical(canvas):
-    """Canvases that are not 64 pixels wide are drawn in bands of whole frame rows (4096 / W rows per band, one
+    """(64-pixel-wide canvases of at most 64 rows: the swizzled tile stored through a tensor map, box = 2 H lines of
+    128 bytes; taller ones: square tiles.)  Canvases that are not 64 pixels wide are drawn in bands of whole frame rows (4096 / W rows per band, one
     linear bulk copy each -- or, when W is not a multiple of 4, a stream of 16-byte stores out of a padded buffer;
     wider than 4096 pixels: square tiles again): every band geometry -- several rows, two rows, one row per band,
     a last band that is cut short, balls cut by band edges and by the canvas, small sprites composited in pairs --
