@@ -1,7 +1,9 @@
 // ppb_launch_impl.cuh -- body of Launch<T>, included by ppb_f32.cu / ppb_f64.cu
 #pragma once
+#include <atomic>
 #include <cstdlib>
 #include <cstring>
+#include <mutex>
 
 #include "ppb_kernels.cuh"
 #include "ppb_launch.h"
@@ -200,13 +202,19 @@ cudaError_t Launch<T>::render(const StatePtrs &S, const Layout &L, const RenderL
     // launches in flight on different streams never share one; a launch leaves its pair zeroed
     constexpr int kCtrRing = 256;
     static uint32_t *ctr_ring[64] = {nullptr};
-    static unsigned ctr_next[64] = {0};
-    if (!ctr_ring[dev]) {
-      cudaError_t e = cudaMalloc((void **)&ctr_ring[dev], kCtrRing * 2 * sizeof(uint32_t));
-      if (e == cudaSuccess) e = cudaMemset(ctr_ring[dev], 0, kCtrRing * 2 * sizeof(uint32_t));
-      if (e != cudaSuccess) return e;
+    static std::atomic<unsigned> ctr_next[64];
+    static std::mutex ctr_mu;
+    {
+      std::lock_guard<std::mutex> lk(ctr_mu);   // (host threads with batches of their own may render at the same time)
+      if (!ctr_ring[dev]) {
+        uint32_t *ring = nullptr;
+        cudaError_t e = cudaMalloc((void **)&ring, kCtrRing * 2 * sizeof(uint32_t));
+        if (e == cudaSuccess) e = cudaMemset(ring, 0, kCtrRing * 2 * sizeof(uint32_t));
+        if (e != cudaSuccess) return e;
+        ctr_ring[dev] = ring;
+      }
     }
-    uint32_t *tile_ctr = ctr_ring[dev] + 2 * (ctr_next[dev]++ % kCtrRing);
+    uint32_t *tile_ctr = ctr_ring[dev] + 2 * (ctr_next[dev].fetch_add(1u) % kCtrRing);
     static const bool static_split = getenv("PPB_RENDER_STATIC") != nullptr;   // developer switch (A/B timing)
     if (static_split) tile_ctr = nullptr;
     // tiles per ticket (see the kernel; 4 - 8 measured alike, 346 - 348 us per launch of 131,072 frames)

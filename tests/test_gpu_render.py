@@ -329,3 +329,42 @@ def test_frames_maximum_object_counts(canvas):
     cols = [(rs.rand(), rs.rand(), rs.rand(), 1.0) for _ in range(16)]
     dev, ref = _render_both(wall, pos, 3, canvas, 1, wall_rgba=cols)
     assert np.array_equal(dev, ref)
+
+
+def test_ticketed_tiles_many_launches_two_batches_two_streams():
+    """render_tile_kernel hands its tiles out through ticket counters taken from a ring of 256 pairs that every launch
+    re-arms: 600 launches (the ring wraps twice) of two batches interleaved on two streams, each with more frames
+    than the grid has warps (so most tiles come from tickets), give the same bytes as the first launch -- and the
+    first launch gives the bytes of the restated renderer."""
+    import torch
+    from pyphy_engine_b200 import sampler
+    from pyphy_engine_b200.engine import WorldBatch
+    nb = 8
+    batches, want = [], []
+    for seed, n in ((5, 9000), (6, 12345)):
+        W = sampler.sample_rect_worlds(n, nb, seed=seed, **sampler.scaled64_params(nb))
+        wb = WorldBatch(n, nb, 4, dtype="f32", canvas=(64, 64))
+        wb.set_walls(W["wall"])
+        wb.set_balls(W["pos"], W["vel"], W["rad"], W["mass"])
+        wb.set_styles([(1, GRAY, BLACK)] * nb, [(0, RED)] * 4, 3, 3)
+        first = wb.render().clone()
+        ref = oracle.render_frames(W["wall"][:2048], W["pos"][:2048], W["rad"][:2048], (64, 64), s_thick=1, n_threads=8)
+        assert np.array_equal(first[:2048].cpu().numpy(), ref)
+        tail = oracle.render_frames(W["wall"][-512:], W["pos"][-512:], W["rad"][-512:], (64, 64), s_thick=1, n_threads=8)
+        assert np.array_equal(first[-512:].cpu().numpy(), tail)
+        batches.append(wb)
+        want.append(first)
+    streams = [torch.cuda.Stream(), torch.cuda.Stream()]
+    outs = [torch.empty_like(w) for w in want]
+    for it in range(300):
+        for k in (0, 1):
+            with torch.cuda.stream(streams[k]):
+                batches[k].render(out=outs[k])
+        if it % 50 == 49 or it < 3:
+            torch.cuda.synchronize()
+            for k in (0, 1):
+                assert torch.equal(outs[k], want[k]), (it, k)
+                outs[k].zero_()
+    torch.cuda.synchronize()
+    for wb in batches:
+        wb.close()
