@@ -368,25 +368,32 @@ def run_ours(args, rank, local_rank, world_size):
 
     # ---- end-of-run gather of the datagen shard (NCCL over NVLink when distributed): 100 steps of positions of every
     #      rank's worlds arrive on rank 0 in world order (`position` (2N, seqLen) fp32 per world).  The
-    #      first gather of a process pays the lazy NCCL connection set-up, so a one-step gather goes first; not part
-    #      of any timed region above ----
+    #      first gather of a process pays the lazy NCCL connection set-up and the allocator's first cudaMallocs, so an
+    #      untimed gather of the same shard goes first; not part of any timed region above ----
     GATHER_STEPS = 100
     shard = torch.empty((GATHER_STEPS, n_worlds, N_BALLS, 2), dtype=torch.float32, device=dev)
     wb.step_async(GATHER_STEPS, traj=shard)
     torch.cuda.synchronize(dev)
-    _sh.gather_trajectories(shard[:1].contiguous(), n_worlds * world_size, dst=0)      # warm-up
+    warm = _sh.gather_trajectories(shard, n_worlds * world_size, dst=0)      # warm-up: connections, allocator
+    del warm
+    torch.cuda.synchronize(dev)
     barrier()
+    gt = {}
     tg0 = time.perf_counter()
-    gathered = _sh.gather_trajectories(shard, n_worlds * world_size, dst=0)
+    gathered = _sh.gather_trajectories(shard, n_worlds * world_size, dst=0, timing=gt)
     torch.cuda.synchronize(dev)
     barrier()
     gather_ms = 1e3 * (time.perf_counter() - tg0)
     gather_info = None
     if rank == 0:
         nbytes = int(gathered.numel() * 4)
-        gather_info = {"shape": list(gathered.shape), "bytes": nbytes, "ms": gather_ms,
-                       "gb_per_s": nbytes * (world_size - 1) / max(world_size, 1) / (gather_ms * 1e-3) / 1e9 if distributed else None,
-                       "backend": "nccl (dist.gather to rank 0; GB/s counts the bytes that arrive from the other ranks)"
+        coll_ms = gt.get("collective_ms")
+        gather_info = {"shape": list(gathered.shape), "bytes": nbytes, "ms": gather_ms, "collective_ms": coll_ms,
+                       "gb_per_s": nbytes * (world_size - 1) / max(world_size, 1) / (coll_ms * 1e-3) / 1e9
+                       if distributed and coll_ms else None,
+                       "backend": "nccl (dist.gather to rank 0; collective_ms = CUDA events around the collective on rank 0, "
+                                  "GB/s = bytes arriving from the other ranks / collective_ms; ms = wall clock of the whole "
+                                  "call between barriers, incl. the reordering into world order on rank 0)"
                                   if distributed else "none (single rank)",
                        "checksum": float(gathered[-1].double().sum().item())}
     del gathered, shard

@@ -155,20 +155,33 @@ def all_gather_stats(stats: Dict[str, float], device=None) -> Dict[str, np.ndarr
     return {k: mat[:, i] for i, k in enumerate(keys)}
 
 
-def gather_trajectories(local, n_worlds_total: int, dst: int = 0):
+def gather_trajectories(local, n_worlds_total: int, dst: int = 0, timing: dict | None = None):
     """Gather the per-rank ``position`` shards (steps, local_worlds, balls, 2) on rank ``dst`` in
     world order (the reference collects ``Pool`` results the same way, parallel_fetch.py:22-25).
-    Returns the full tensor on ``dst`` and None elsewhere."""
+    Returns the full tensor on ``dst`` and None elsewhere.  With ``timing`` (a dict) the collective alone is
+    bracketed by CUDA events on the current stream and its duration lands in ``timing["collective_ms"]``
+    (the padding of ragged shards and the reordering into world order on ``dst`` are outside that bracket)."""
     import torch
     if not is_distributed():
         return local
     dist = _dist()
     rank, ws = dist.get_rank(), dist.get_world_size()
     per = -(-int(n_worlds_total) // ws)
-    pad = torch.zeros((local.shape[0], per) + tuple(local.shape[2:]), dtype=local.dtype, device=local.device)
-    pad[:, :local.shape[1]] = local
+    if local.shape[1] == per and local.is_contiguous():
+        pad = local                     # even shards (the usual case): nothing to pad
+    else:
+        pad = torch.zeros((local.shape[0], per) + tuple(local.shape[2:]), dtype=local.dtype, device=local.device)
+        pad[:, :local.shape[1]] = local
     bufs = [torch.empty_like(pad) for _ in range(ws)] if rank == dst else None
+    ev = None
+    if timing is not None and local.is_cuda:
+        ev = (torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True))
+        ev[0].record()
     dist.gather(pad, bufs, dst=dst)
+    if ev is not None:
+        ev[1].record()
+        ev[1].synchronize()
+        timing["collective_ms"] = ev[0].elapsed_time(ev[1])
     if rank != dst:
         return None
     parts = []

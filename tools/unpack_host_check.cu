@@ -6,11 +6,12 @@
 #include <chrono>
 #include <cstdio>
 #include <random>
+#include <string>
 
 int main(int argc, char **argv) {
   const int threads = argc > 1 ? atoi(argv[1]) : 8;
   const int npx = 4096;
-  const long long n_frames = 32768;
+  const long long n_frames = 65536;
   std::mt19937 rng(1);
   // a frame: white, a 3-pixel red border of a box, eight 8x8 "sprites" with 6 distinct values per row
   std::vector<uint32_t> frames((size_t)n_frames * npx, 0xffffffffu);
@@ -48,24 +49,42 @@ int main(int argc, char **argv) {
     table[f] = make_uint2(off, (uint32_t)tokens.size() - off);
   }
   printf("%.0f tokens per frame, %.2f KB per frame\n", (double)tokens.size() / n_frames, 4.0 * tokens.size() / n_frames / 1024);
-  uint8_t *out = (uint8_t *)aligned_alloc(4096, (size_t)n_frames * npx * 4);
+  // destination: ordinary memory, or (second argument "pinned", needs a CUDA device) page-locked memory like the
+  // caller's array of ppb_simulate_host
+  const bool pinned = argc > 2 && std::string(argv[2]) == "pinned";
+  uint8_t *out = nullptr;
+  if (pinned) {
+    if (cudaHostAlloc((void **)&out, (size_t)n_frames * npx * 4, cudaHostAllocDefault) != cudaSuccess) {
+      printf("cudaHostAlloc failed (no device?)\n");
+      return 2;
+    }
+  } else {
+    out = (uint8_t *)aligned_alloc(4096, (size_t)n_frames * npx * 4);
+  }
   memset(out, 0, (size_t)n_frames * npx * 4);
   double best = 1e9;
-  for (int rep = 0; rep < 3; ++rep) {
-    auto t0 = std::chrono::steady_clock::now();
+  for (int rep = 0; rep < 4; ++rep) {
+    // the threads exist before the clock starts (the library's pool is persistent); they leave a spin barrier together
     std::vector<std::thread> th;
-    std::atomic<int> bad{0};
+    std::atomic<int> bad{0}, ready{0};
+    std::atomic<bool> go{false};
     for (int t = 0; t < threads; ++t)
       th.emplace_back([&, t] {
+        ready++;
+        while (!go.load(std::memory_order_acquire)) {}
         const long long per = n_frames / threads;
         if (!ppb::host_check_unpack(tokens.data(), table.data(), t * per, t == threads - 1 ? n_frames : (t + 1) * per, npx, out)) bad++;
       });
+    while (ready.load() < threads) {}
+    auto t0 = std::chrono::steady_clock::now();
+    go.store(true, std::memory_order_release);
     for (auto &x : th) x.join();
     const double s = std::chrono::duration<double>(std::chrono::steady_clock::now() - t0).count();
     if (s < best) best = s;
     if (bad) { printf("inconsistent stream\n"); return 1; }
   }
   const bool same = memcmp(out, frames.data(), (size_t)n_frames * npx * 4) == 0;
-  printf("%d threads: %.1f GB/s of RGBA rebuilt, %s\n", threads, (double)n_frames * npx * 4 / best / 1e9, same ? "identical" : "DIFFERENT");
+  printf("%d threads%s: %.1f GB/s of RGBA rebuilt, %s\n", threads, pinned ? " (pinned destination)" : "",
+         (double)n_frames * npx * 4 / best / 1e9, same ? "identical" : "DIFFERENT");
   return same ? 0 : 1;
 }
