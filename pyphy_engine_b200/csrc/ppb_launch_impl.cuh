@@ -75,6 +75,15 @@ int Launch<T>::advance_grid(int n_worlds, int n_balls, int sm_count) {
   else if (n_balls <= 16) cudaOccupancyMaxActiveBlocksPerMultiprocessor(&occ, advance_kernel<T, 16, 2>, PPB_COLLIDE_WARPS * 32, 0);
   else cudaOccupancyMaxActiveBlocksPerMultiprocessor(&occ, advance_kernel<T, 32, 4>, PPB_COLLIDE_WARPS * 32, 0);
   if (occ < 1) occ = 1;
+  if (getenv("PPB_ADV_CARVEOUT")) {   // developer switch (A/B timing): same L1 / shared-memory split as the render kernel
+    cudaFuncSetAttribute(advance_kernel<T, 1, 1>, cudaFuncAttributePreferredSharedMemoryCarveout, cudaSharedmemCarveoutMaxShared);
+    cudaFuncSetAttribute(advance_kernel<T, 2, 1>, cudaFuncAttributePreferredSharedMemoryCarveout, cudaSharedmemCarveoutMaxShared);
+    cudaFuncSetAttribute(advance_kernel<T, 4, 1>, cudaFuncAttributePreferredSharedMemoryCarveout, cudaSharedmemCarveoutMaxShared);
+    cudaFuncSetAttribute(advance_kernel<T, 8, 1>, cudaFuncAttributePreferredSharedMemoryCarveout, cudaSharedmemCarveoutMaxShared);
+    cudaFuncSetAttribute(advance_kernel<T, 16, 2>, cudaFuncAttributePreferredSharedMemoryCarveout, cudaSharedmemCarveoutMaxShared);
+    cudaFuncSetAttribute(advance_kernel<T, 32, 4>, cudaFuncAttributePreferredSharedMemoryCarveout, cudaSharedmemCarveoutMaxShared);
+  }
+  if (const char *e = getenv("PPB_ADV_OCC")) { const int v = atoi(e); if (v >= 1 && v < occ) occ = v; }   // developer switch (A/B timing)
   const int tw = n_balls <= 8 ? 1 : (n_balls <= 16 ? 2 : 4);
   const int teams = PPB_COLLIDE_WARPS / tw;
   const int need = (n_worlds + teams - 1) / teams;   // at least one world per team

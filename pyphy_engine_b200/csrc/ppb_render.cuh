@@ -332,6 +332,12 @@ inline int render_warps(int n_walls, int n_balls) {
   const size_t per = render_warp_smem_bytes(n_walls, n_balls);
   int w = (int)((227 * 1024 - PPB_RENDER_SMEM_SPARE) / per);
   if (w > PPB_RENDER_MAX_WARPS) w = PPB_RENDER_MAX_WARPS;
+  static const int forced = getenv("PPB_RENDER_WARPS") ? atoi(getenv("PPB_RENDER_WARPS")) : 0;   // developer switch (A/B timing)
+  if (forced > 0) {
+    w = forced;
+    const int fit = (int)((227 * 1024) / per);
+    if (w > fit) w = fit;
+  }
   return w < 1 ? 1 : w;
 }
 

@@ -3,7 +3,7 @@
 import os
 import sys
 
-sys.path.insert(0, os.path.dirname(os.path.dirname(os.path.abspath(__file__))))
+sys.path.insert(0, os.path.abspath(os.environ.get("PPB_ROOT") or os.path.dirname(os.path.dirname(os.path.abspath(__file__)))))   # PPB_ROOT: another build (A/B)
 import torch  # noqa: E402
 from pyphy_engine_b200 import sampler  # noqa: E402
 from pyphy_engine_b200.engine import WorldBatch  # noqa: E402
@@ -15,7 +15,7 @@ for N, NB in ((131072, 8), (65536, 4)):
     wb.set_balls(W["pos"], W["vel"], W["rad"], W["mass"])
     wb.step_async(100)
     e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
-    for n in (1, 4, 16, 20, 64):
+    for n in ((50, 64) if os.environ.get("PROBE_SHORT") else (1, 4, 16, 20, 64)):
         reps = max(4, 128 // n)
         torch.cuda.synchronize()
         e0.record()
