@@ -335,7 +335,9 @@ PPB_API int ppb_get_counters(ppb_batch *b, int64_t out[8], void *stream);
  *         1: tCol        [n_worlds][n_balls]
  *         2: walls       [n_worlds][n_walls][4][2]
  *         3: radius/mass [n_worlds][n_balls] x {r, m}
- *         4: velocities  [n_worlds][n_balls] x {vx, vy}                             */
+ *         4: velocities  [n_worlds][n_balls] x {vx, vy}
+ * State written through these pointers takes effect after ppb_requeue (collision caches; the renderer's copy of the
+ * radii); walls written this way also need ppb_set_styles again (the renderer's per-wall cache).                  */
 PPB_API int ppb_device_ptr(ppb_batch *b, int32_t which, void **ptr, int64_t *nbytes);
 
 /* time (ms) and launch count of the integrate / collide / render kernels, measured with

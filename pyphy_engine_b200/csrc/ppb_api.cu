@@ -260,8 +260,8 @@ int check_radii(ppb_batch *b, cudaStream_t st) {
     const int32_t init[4] = {0x7fffffff, -1, 0, 0};
     int32_t got[4];
     CU(cudaMemcpyAsync(b->d_rchk, init, sizeof init, cudaMemcpyHostToDevice, st));
-    CU(is64(b) ? Launch<double>::radius_range(b->S, b->cfg.n_balls, b->d_rchk, st)
-               : Launch<float>::radius_range(b->S, b->cfg.n_balls, b->d_rchk, st));
+    CU(is64(b) ? Launch<double>::radius_range(b->S, b->cfg.n_walls, b->cfg.n_balls, b->d_rchk, st)
+               : Launch<float>::radius_range(b->S, b->cfg.n_walls, b->cfg.n_balls, b->d_rchk, st));
     ++b->launches;
     CU(cudaMemcpyAsync(got, b->d_rchk, sizeof got, cudaMemcpyDeviceToHost, st));
     CU(cudaStreamSynchronize(st));
@@ -411,7 +411,7 @@ int ppb_create(const ppb_config *cfg, ppb_batch **out) {
       {&b->S.pos, nb * 2 * b->esz},   {&b->S.vel, nb * 2 * b->esz},
       {&b->S.aux, nb * 4 * b->esz},   {&b->S.tcol, nb * b->esz},
       {&b->S.rm, nb * 2 * b->esz},    {&b->S.wall, nw * (size_t)(nW > 0 ? nW : 1) * 8 * b->esz},
-      {&b->S.wall_rc, nw * (size_t)(nW > 0 ? nW : 1) * sizeof(WallRC)},
+      {&b->S.wall_rc, nw * render_rec_stride(nW, nB) + 16},
       {&b->S.hdr, nw * 16},           {(void **)&b->S.partner, nb * 4},
       {(void **)&b->S.nev, nw * 4},   {(void **)&b->S.events, (size_t)(cfg->event_capacity > 0 ? cfg->event_capacity : 1) * sizeof(ppb_event)},
       {(void **)&b->S.counters, 8 * sizeof(unsigned long long)},
@@ -632,6 +632,7 @@ int ppb_requeue(ppb_batch *b, int32_t world0, int32_t count, void *stream) {
   CU(cudaSetDevice(b->cfg.device));
   CU(do_reset(b, world0, count, 1, (cudaStream_t)stream));
   CU(cudaStreamSynchronize((cudaStream_t)stream));
+  b->radii_known = false;   // radii written through ppb_device_ptr(3) reach the renderer's records at its next call
   return PPB_OK;
 }
 

@@ -130,7 +130,7 @@ struct StatePtrs {
   void *tcol;      // [n_worlds][n_balls]
   void *rm;        // [n_worlds][n_balls] {radius, mass}
   void *wall;      // [n_worlds][n_walls][4][2]
-  void *wall_rc;   // [n_worlds][n_walls] WallRC: what the render kernel needs of a wall, derived once per
+  void *wall_rc;   // [n_worlds] render records (render_rec_stride bytes: WallRC x n_walls, then the radii): what the render kernel needs of a wall, derived once per
                    // ppb_set_walls / ppb_set_styles (walls never move)
   void *hdr;       // [n_worlds] Hdr<T>
   int32_t *partner;   // [n_worlds][n_balls]
@@ -165,6 +165,14 @@ struct __align__(16) WallRC {
   int flags;                  // bit 0: axis-aligned, bit 1: axis-aligned with integral y edges
   uint32_t col;               // premultiplied RGBA8 of the wall slot
 };
+// The render kernel's static input of one world is ONE contiguous record: the WallRC of its walls followed by the
+// radii of its ball slots as fp32 (< 0 = empty slot), padded to 16 bytes.  One region per frame instead of two keeps
+// the scattered reads that interrupt the frame write stream in HBM to a minimum (each separately read array costs a
+// launch of 131,072 frames ~14 us, whatever its size: measured, profiles/r2_experiments_last_session.log).
+__host__ __device__ inline size_t render_rec_stride(int n_walls, int n_balls) {
+  return (size_t)n_walls * sizeof(WallRC) + ((((size_t)n_balls * sizeof(float)) + 15) & ~(size_t)15);
+}
+
 struct RenderWall {  // per wall slot, shared by the batch
   int32_t kind;
   uint32_t rgba8;    // colour as premultiplied 8-bit r | g<<8 | b<<16 | a<<24 (array channel order)

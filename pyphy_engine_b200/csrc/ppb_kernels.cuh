@@ -571,13 +571,20 @@ __global__ void apply_force_kernel(StatePtrs S, int n_balls, int world0, int cou
 // Range of the radii of all occupied ball slots: out[0] = min floor(r), out[1] = max ceil(r), out[2] = 1 if some radius
 // is not an integer.  The renderer draws a ball from the pre-rendered sprite of its integer radius (get_ball_im takes
 // the radius as an array shape, primitives.py:39-40), so the API refuses to draw anything else (ppb_render_async).
+// The same pass copies every slot's radius (fp32; integral radii are exact) into the world's render record.
 template <typename T>
-__global__ void radius_range_kernel(StatePtrs S, int n_balls, int32_t *out) {
+__global__ void radius_range_kernel(StatePtrs S, int n_walls, int n_balls, int32_t *out) {
   typedef typename Vec2<T>::type T2;
   const long long i = (long long)blockIdx.x * blockDim.x + threadIdx.x;
   int lo = 0x7fffffff, hi = -1, frac = 0;
   if (i < (long long)S.n_worlds * n_balls) {
     const T r = reinterpret_cast<const T2 *>(S.rm)[i].x;
+    if (S.wall_rc) {
+      const long long w = i / n_balls;
+      const int b = (int)(i - w * n_balls);
+      reinterpret_cast<float *>(reinterpret_cast<char *>(S.wall_rc) + (size_t)w * render_rec_stride(n_walls, n_balls) +
+                                (size_t)n_walls * sizeof(WallRC))[b] = (float)r;
+    }
     if (r >= T(0)) {
       const double rd = (double)r;
       lo = (int)floor(rd);

@@ -36,7 +36,7 @@ struct Launch {
   static cudaError_t apply_force(const StatePtrs &S, int n_balls, int world0, int count, const double *force,
                                  double force_t, cudaStream_t st);
   // out[0..2] = {min floor(radius), max ceil(radius), any non-integer radius} over the occupied slots (out pre-set)
-  static cudaError_t radius_range(const StatePtrs &S, int n_balls, int32_t *out, cudaStream_t st);
+  static cudaError_t radius_range(const StatePtrs &S, int n_walls, int n_balls, int32_t *out, cudaStream_t st);
   // traj (batch dtype) -> float32
   static cudaError_t traj_to_f32(const void *src, float *dst, long long n, cudaStream_t st);
 };

@@ -155,7 +155,7 @@ cudaError_t Launch<T>::wall_cache(const StatePtrs &S, const Layout &L, const Ren
                                   cudaStream_t st) {
   const long long n = (long long)count * L.n_walls;
   if (n <= 0) return cudaSuccess;
-  wall_cache_kernel<T><<<(unsigned)((n + 127) / 128), 128, 0, st>>>(S, L.n_walls, RL, world0, count);
+  wall_cache_kernel<T><<<(unsigned)((n + 127) / 128), 128, 0, st>>>(S, L.n_walls, L.n_balls, RL, world0, count);
   return cudaGetLastError();
 }
 
@@ -190,6 +190,10 @@ cudaError_t Launch<T>::render(const StatePtrs &S, const Layout &L, const RenderL
       if (e != cudaSuccess) return e;
     }
     const int smem_max = 227 * 1024;
+    // a small sprite atlas rides along in shared memory (the 64-pixel canvas only)
+    static const bool no_satl = getenv("PPB_NO_SMEM_ATLAS") != nullptr;   // developer switch (A/B timing)
+    const int atlas_bytes = L.n_balls * RL.sprite_slot_stride;
+    const bool satl = swz && !no_satl && atlas_bytes > 0 && atlas_bytes <= 8192 && (atlas_bytes & 3) == 0 && smem + atlas_bytes <= smem_max;
     // per device (and per instantiation T): SM count, opt-in to the large dynamic shared memory
     static int sm_counts[64] = {0};
     int dev = 0;
@@ -203,6 +207,8 @@ cudaError_t Launch<T>::render(const StatePtrs &S, const Layout &L, const RenderL
       e = cudaFuncSetAttribute(render_tile_kernel<T, PPB_RM_BAND>, cudaFuncAttributeMaxDynamicSharedMemorySize, smem_max);
       if (e != cudaSuccess) return e;
       e = cudaFuncSetAttribute(render_tile_kernel<T, PPB_RM_SWZ>, cudaFuncAttributeMaxDynamicSharedMemorySize, smem_max);
+      if (e != cudaSuccess) return e;
+      e = cudaFuncSetAttribute(render_tile_kernel<T, PPB_RM_SWZ, true>, cudaFuncAttributeMaxDynamicSharedMemorySize, smem_max);
       if (e != cudaSuccess) return e;
       sm_counts[dev] = n > 0 ? n : 1;
     }
@@ -232,6 +238,7 @@ cudaError_t Launch<T>::render(const StatePtrs &S, const Layout &L, const RenderL
     long long blocks = (jobs + warps - 1) / warps;
     if (blocks > sm_count) blocks = sm_count;
     if (band) render_tile_kernel<T, PPB_RM_BAND><<<(unsigned)blocks, warps * 32, smem, st>>>(S, L, RL, atlas, frames, tmap, tile_ctr, chunk);
+    else if (swz && satl) render_tile_kernel<T, PPB_RM_SWZ, true><<<(unsigned)blocks, warps * 32, smem + atlas_bytes, st>>>(S, L, RL, atlas, frames, tmap, tile_ctr, chunk);
     else if (swz) render_tile_kernel<T, PPB_RM_SWZ><<<(unsigned)blocks, warps * 32, smem, st>>>(S, L, RL, atlas, frames, tmap, tile_ctr, chunk);
     else render_tile_kernel<T, PPB_RM_TILE><<<(unsigned)blocks, warps * 32, smem, st>>>(S, L, RL, atlas, frames, tmap, tile_ctr, chunk);
   } else {
@@ -259,10 +266,10 @@ cudaError_t Launch<T>::apply_force(const StatePtrs &S, int n_balls, int world0, 
 }
 
 template <typename T>
-cudaError_t Launch<T>::radius_range(const StatePtrs &S, int n_balls, int32_t *out, cudaStream_t st) {
+cudaError_t Launch<T>::radius_range(const StatePtrs &S, int n_walls, int n_balls, int32_t *out, cudaStream_t st) {
   const long long n = (long long)S.n_worlds * n_balls;
   if (n <= 0) return cudaSuccess;
-  radius_range_kernel<T><<<(unsigned)((n + 255) / 256), 256, 0, st>>>(S, n_balls, out);
+  radius_range_kernel<T><<<(unsigned)((n + 255) / 256), 256, 0, st>>>(S, n_walls, n_balls, out);
   return cudaGetLastError();
 }
 

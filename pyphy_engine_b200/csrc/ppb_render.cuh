@@ -291,9 +291,9 @@ __global__ void __launch_bounds__(256) render_general_kernel(StatePtrs S, Layout
 //           the buffer, and only waits (cp.async.bulk.wait_group.read) before overwriting it.
 // HBM sees exactly one full-line write per frame byte and a few hundred bytes of state reads.
 // ------------------------------------------------------------------------------------
-// Warps per render CTA: as many as fit next to PPB_RENDER_SMEM_SPARE bytes left for the collide CTAs that
-// share the SM in the pipelined step (see render_warps()); the per-warp metadata is sized by the batch's
-// actual wall / ball counts.
+// Warps per render CTA: as many as fit next to PPB_RENDER_SMEM_SPARE bytes (room for two advance CTAs beside the last
+// renders of a chunk and for the shared-memory copy of a small sprite atlas; see render_warps()); the per-warp
+// metadata is sized by the batch's actual wall / ball counts.
 #define PPB_RENDER_MAX_WARPS 12
 #define PPB_RENDER_SMEM_SPARE (2 * (11264 + 1024) + 1024)
 struct RTBall {      // one ball inside the current tile, already clipped to it (32 bytes)
@@ -357,6 +357,43 @@ __device__ __forceinline__ void bulk_tensor_store_2d(const CUtensorMap *tmap, in
 // XORed with the line index modulo 8.  w = pixel (32-bit word) index in a 1024-byte aligned tile, ch = 16-byte chunk index.
 template <bool SWZ> __device__ __forceinline__ uint32_t swz_w(uint32_t w) { return SWZ ? (w ^ ((w >> 3) & 0x1cu)) : w; }
 template <bool SWZ> __device__ __forceinline__ int swz_ch(int ch) { return SWZ ? (ch ^ ((ch >> 3) & 7)) : ch; }
+// ---- L2 policies: the render state is read evict-last, the frames are written evict-first (see load_world) ----
+__device__ __forceinline__ uint64_t l2_policy_evict_last() {
+  uint64_t p;
+  asm volatile("createpolicy.fractional.L2::evict_last.b64 %0, 1.0;" : "=l"(p));
+  return p;
+}
+__device__ __forceinline__ uint64_t l2_policy_evict_first() {
+  uint64_t p;
+  asm volatile("createpolicy.fractional.L2::evict_first.b64 %0, 1.0;" : "=l"(p));
+  return p;
+}
+__device__ __forceinline__ uint4 ld_hint_v4(const uint4 *a, uint64_t pol) {
+  uint4 v;
+  asm volatile("ld.global.nc.L2::cache_hint.v4.u32 {%0, %1, %2, %3}, [%4], %5;"
+               : "=r"(v.x), "=r"(v.y), "=r"(v.z), "=r"(v.w) : "l"(a), "l"(pol));
+  return v;
+}
+__device__ __forceinline__ float2 ld_hint(const float2 *a, uint64_t pol) {
+  float2 v;
+  asm volatile("ld.global.nc.L2::cache_hint.v2.f32 {%0, %1}, [%2], %3;" : "=f"(v.x), "=f"(v.y) : "l"(a), "l"(pol));
+  return v;
+}
+__device__ __forceinline__ double2 ld_hint(const double2 *a, uint64_t pol) {
+  double2 v;
+  asm volatile("ld.global.nc.L2::cache_hint.v2.f64 {%0, %1}, [%2], %3;" : "=d"(v.x), "=d"(v.y) : "l"(a), "l"(pol));
+  return v;
+}
+__device__ __forceinline__ float ld_hint(const float *a, uint64_t pol) {
+  float v;
+  asm volatile("ld.global.nc.L2::cache_hint.f32 %0, [%1], %2;" : "=f"(v) : "l"(a), "l"(pol));
+  return v;
+}
+__device__ __forceinline__ void bulk_tensor_store_2d_hint(const CUtensorMap *tmap, int row0, const void *ssrc, uint64_t pol) {
+  asm volatile("cp.async.bulk.tensor.2d.global.shared::cta.bulk_group.L2::cache_hint [%0, {%1, %2}], [%3], %4;" ::"l"(tmap), "r"(0),
+               "r"(row0), "r"((uint32_t)__cvta_generic_to_shared(ssrc)), "l"(pol)
+               : "memory");
+}
 __device__ __forceinline__ void bulk_commit() { asm volatile("cp.async.bulk.commit_group;" ::: "memory"); }
 __device__ __forceinline__ void bulk_wait_read0() { asm volatile("cp.async.bulk.wait_group.read 0;" ::: "memory"); }
 __device__ __forceinline__ void bulk_wait0() { asm volatile("cp.async.bulk.wait_group 0;" ::: "memory"); }
@@ -371,11 +408,12 @@ __device__ __forceinline__ uint32_t over_nb(uint32_t src, uint32_t dst) { return
 // WallRC of every wall of worlds [world0, world0 + count): walls never move, so the bounding boxes,
 // paste rectangles and row ranges the render kernel needs are derived once per ppb_set_walls / ppb_set_styles
 template <typename T>
-__global__ void wall_cache_kernel(StatePtrs S, int n_walls, RenderLayout RL, int world0, int count) {
+__global__ void wall_cache_kernel(StatePtrs S, int n_walls, int n_balls, RenderLayout RL, int world0, int count) {
   const long long i = (long long)blockIdx.x * blockDim.x + threadIdx.x;
   if (i >= (long long)count * n_walls) return;
   const int q = (int)(i % n_walls);
   const long long idx = (long long)world0 * n_walls + i;
+  const long long wld = world0 + i / n_walls;
   SWall s;
   setup_wall<T>(s, reinterpret_cast<const T *>(S.wall) + idx * 8, RL.wall[q]);
   WallRC rc;
@@ -384,7 +422,7 @@ __global__ void wall_cache_kernel(StatePtrs S, int n_walls, RenderLayout RL, int
   rc.lo = s.lo; rc.hi = s.hi;
   rc.flags = (s.axis ? 1 : 0) | (s.fast ? 2 : 0);
   rc.col = s.col;
-  reinterpret_cast<WallRC *>(S.wall_rc)[idx] = rc;
+  reinterpret_cast<WallRC *>(reinterpret_cast<char *>(S.wall_rc) + (size_t)wld * render_rec_stride(n_walls, n_balls))[q] = rc;
 }
 
 // BAND = false: 64 x 64 pixel tiles (the whole frame on the 64-pixel canvas).
@@ -400,7 +438,10 @@ __global__ void wall_cache_kernel(StatePtrs S, int n_walls, RenderLayout RL, int
 #define PPB_RM_TILE 0
 #define PPB_RM_BAND 1
 #define PPB_RM_SWZ 2
-template <typename T, int MODE>
+// SATL        : the sprite atlas (a few KB when the batch draws one or two radii) is copied into the CTA's shared memory
+//               once per launch and the compositing loop reads its texels from there: one address instruction and a
+//               shared-memory latency per texel instead of a 64-bit address chain and an L1 round trip.
+template <typename T, int MODE, bool SATL = false>
 __global__ void __maxnreg__(120) render_tile_kernel(StatePtrs S, Layout L, RenderLayout RL, const uint32_t *atlas,
                                                     uint8_t *frames, const __grid_constant__ CUtensorMap tmap,
                                                     uint32_t *tile_ctr, uint32_t kChunk) {
@@ -421,6 +462,17 @@ __global__ void __maxnreg__(120) render_tile_kernel(StatePtrs S, Layout L, Rende
     sm.w = reinterpret_cast<SWallGeom *>(sm.b + L.n_balls);                // 4-byte aligned members only
   }
   if (SWZ && (__cvta_generic_to_shared(render_smem_raw) & 1023u) != 0) __trap();   // the swizzle is a function of the address
+  // the atlas copy sits behind the tiles and the metadata of all warps
+  const uint32_t *satlas = reinterpret_cast<const uint32_t *>(
+      render_smem_raw + (size_t)n_warps * render_warp_smem_bytes(L.n_walls, L.n_balls));
+  if (SATL) {
+    uint32_t *dstw = reinterpret_cast<uint32_t *>(
+        render_smem_raw + (size_t)n_warps * render_warp_smem_bytes(L.n_walls, L.n_balls));
+    const int words = (L.n_balls * RL.sprite_slot_stride) >> 2;
+    for (int i = threadIdx.x; i < words; i += blockDim.x) dstw[i] = __ldg(atlas + i);
+    __syncthreads();
+  }
+  auto texel = [&](uint32_t idx) -> uint32_t { return SATL ? satlas[idx] : __ldg(atlas + idx); };
   // pixels per tile row (row stride in the buffer; a band pads it to a multiple of 4) and rows per tile
   const int RS = BAND ? ((RL.W + 3) & ~3) : PPB_TILE;
   const int RH = BAND ? (PPB_TILE * PPB_TILE) / RS : PPB_TILE;
@@ -428,8 +480,8 @@ __global__ void __maxnreg__(120) render_tile_kernel(StatePtrs S, Layout L, Rende
   const int tiles_x = BAND ? 1 : (RL.W + PPB_TILE - 1) / PPB_TILE;
   const int tiles_y = (RL.H + RH - 1) / RH;
   const int tiles = tiles_x * tiles_y;
-  const long long total = (long long)S.n_worlds * tiles;
   const int nB = L.n_balls, nWl = L.n_walls;
+  const long long total = (long long)S.n_worlds * tiles;
   const bool whole_rows = (BAND && RS == RL.W) || (RL.W == PPB_TILE);   // the tile is contiguous in the frame
   const bool bulk_ok = ((RL.W & 3) == 0) && ((reinterpret_cast<uintptr_t>(frames) & 15u) == 0);
   // raw state of the world of the current / next tile, held in registers: lane q < nWl keeps wall q's
@@ -479,14 +531,22 @@ __global__ void __maxnreg__(120) render_tile_kernel(StatePtrs S, Layout L, Rende
     chunk_job += A_per;
     return j;
   };
+  const size_t rec_stride = render_rec_stride(nWl, nB);
+  // One contiguous record per world (walls, radii) and its ball positions.  These few scattered reads are what keeps the
+  // launch from the rate of a store-only kernel (measured on B200, 131,072 frames: 298 us without them, 327 us with a
+  // single 16-byte read per frame, 337 - 345 us with all of them, whatever the warp count; fetching two worlds per read
+  // changed nothing): they are read with an evict-last L2 policy and the frames leave with an evict-first one, which is
+  // worth 8 us.
+  const uint64_t pol_keep = l2_policy_evict_last();
   auto load_world = [&](int wn) {
+    const char *rec = reinterpret_cast<const char *>(S.wall_rc) + (size_t)wn * rec_stride;
     if (lane < nWl) {
-      const uint4 *src = reinterpret_cast<const uint4 *>(reinterpret_cast<const WallRC *>(S.wall_rc) + ((long long)wn * nWl + lane));
-      rc0 = src[0]; rc1 = src[1]; rc2 = src[2];
+      const uint4 *src = reinterpret_cast<const uint4 *>(rec) + 3 * lane;
+      rc0 = ld_hint_v4(src, pol_keep); rc1 = ld_hint_v4(src + 1, pol_keep); rc2 = ld_hint_v4(src + 2, pol_keep);
     }
     if (lane < nB) {
-      bp = reinterpret_cast<const T2 *>(S.pos)[(long long)wn * nB + lane];
-      brad = reinterpret_cast<const T2 *>(S.rm)[(long long)wn * nB + lane].x;
+      bp = ld_hint(reinterpret_cast<const T2 *>(S.pos) + ((long long)wn * nB + lane), pol_keep);
+      brad = (T)ld_hint(reinterpret_cast<const float *>(rec + (size_t)nWl * sizeof(WallRC)) + lane, pol_keep);
     }
   };
   if (job0 < total) load_world((tiles == 1) ? (int)job0 : (int)(job0 / tiles));
@@ -687,10 +747,10 @@ __global__ void __maxnreg__(120) render_tile_kernel(StatePtrs S, Layout L, Rende
             const uint2 rn = reinterpret_cast<const uint2 *>(&sm.b[b + 1])[0];   // tex, dst_sz of the partner
             const uint32_t dstn = rn.y & 0xffffu;
             const uint32_t n1 = swz_w<SWZ>(dstn + sp_d1), n2 = swz_w<SWZ>(dstn + sp_d2);
-            const uint32_t t1 = v1 ? __ldg(atlas + ra.x + sp_t1) : 0u;
-            const uint32_t t2 = v2 ? __ldg(atlas + ra.x + sp_t2) : 0u;
-            const uint32_t u1 = v1 ? __ldg(atlas + rn.x + sp_t1) : 0u;
-            const uint32_t u2 = v2 ? __ldg(atlas + rn.x + sp_t2) : 0u;
+            const uint32_t t1 = v1 ? texel(ra.x + sp_t1) : 0u;
+            const uint32_t t2 = v2 ? texel(ra.x + sp_t2) : 0u;
+            const uint32_t u1 = v1 ? texel(rn.x + sp_t1) : 0u;
+            const uint32_t u2 = v2 ? texel(rn.x + sp_t2) : 0u;
             const uint32_t d1 = v1 ? sm.tile[a1] : 0u;
             const uint32_t d2 = v2 ? sm.tile[a2] : 0u;
             const uint32_t e1 = v1 ? sm.tile[n1] : 0u;
@@ -702,8 +762,8 @@ __global__ void __maxnreg__(120) render_tile_kernel(StatePtrs S, Layout L, Rende
             continue;
           }
         }
-        const uint32_t t1 = v1 ? __ldg(atlas + ra.x + sp_t1) : 0u;
-        const uint32_t t2 = v2 ? __ldg(atlas + ra.x + sp_t2) : 0u;
+        const uint32_t t1 = v1 ? texel(ra.x + sp_t1) : 0u;
+        const uint32_t t2 = v2 ? texel(ra.x + sp_t2) : 0u;
         const uint32_t d1 = v1 ? sm.tile[a1] : 0u;
         const uint32_t d2 = v2 ? sm.tile[a2] : 0u;
         if (v1) sm.tile[a1] = over_nb(t1, d1);
@@ -725,8 +785,8 @@ __global__ void __maxnreg__(120) render_tile_kernel(StatePtrs S, Layout L, Rende
         uint32_t ti2 = ti + rb.x, di2 = di + rb.y;
         if (sx2 >= aw) { sx2 -= aw; ++sy2; ti2 += wti; di2 += wdi; }
         const bool has2 = sy2 < ah;
-        const uint32_t t = __ldg(atlas + ti);
-        const uint32_t t2 = has2 ? __ldg(atlas + ti2) : 0u;
+        const uint32_t t = texel(ti);
+        const uint32_t t2 = has2 ? texel(ti2) : 0u;
         const uint32_t ai = swz_w<SWZ>(di), ai2 = swz_w<SWZ>(di2);
         const uint32_t d = sm.tile[ai];
         const uint32_t d2 = has2 ? sm.tile[ai2] : 0u;
@@ -743,7 +803,7 @@ __global__ void __maxnreg__(120) render_tile_kernel(StatePtrs S, Layout L, Rende
     uint32_t *out = reinterpret_cast<uint32_t *>(frames) + (size_t)w * RL.W * RL.H;
     if (SWZ) {
       // (the launcher only picks this mode for 16-byte aligned frames of 64 x H pixels, H <= 64: one tile per frame)
-      if (lane == 0) bulk_tensor_store_2d(&tmap, w * (2 * RL.H), sm.tile);
+      if (lane == 0) bulk_tensor_store_2d_hint(&tmap, w * (2 * RL.H), sm.tile, l2_policy_evict_first());
     } else if (BAND && !bulk_ok) {
       // Rows of this canvas are not 16-byte multiples (the reference's default arenaSz = 667) or the frame buffer
       // is not 16-byte aligned: the copy engine cannot take the band.  It is still one contiguous run of
