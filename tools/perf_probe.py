@@ -10,7 +10,7 @@ import time
 import numpy as np
 import torch
 
-sys.path.insert(0, os.path.dirname(os.path.dirname(os.path.abspath(__file__))))
+sys.path.insert(0, os.path.abspath(os.environ.get("PPB_ROOT") or os.path.dirname(os.path.dirname(os.path.abspath(__file__)))))   # PPB_ROOT: another build (A/B)
 from pyphy_engine_b200 import sampler  # noqa: E402
 from pyphy_engine_b200.engine import WorldBatch  # noqa: E402
 
