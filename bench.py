@@ -59,6 +59,16 @@ def load_traffic(kernel):
         return None
 
 
+def load_store_ceiling():
+    """GB/s a store-only kernel with the render kernel's tile hand-out reaches over the same 2 GiB (measured once on
+    B200, profiles/store_ceiling.json), or None."""
+    try:
+        with open(os.path.join(ROOT, "profiles", "store_ceiling.json")) as fh:
+            return float(json.load(fh)["store_only_ceiling_gbs"])
+    except Exception:
+        return None
+
+
 def load_python_reference():
     """The UNMODIFIED Python reference timed in the build container (tools/time_reference.py; it cannot travel to the
     GPU box): the committed record, echoed next to the C port's number."""
@@ -461,6 +471,12 @@ def run_ours(args, rank, local_rank, world_size):
                                  "render alone: %.1f us/launch = %.3f of peak"
                                  % (steps_per_adv, render_alone_us, alg_bytes[2] / (render_alone_us * 1e-6) / 1e9 / peak),
                          "render_alone_us": render_alone_us,
+                         # the peak above is a copy (read + write) figure; a write-only stream goes above it, so the
+                         # fraction can exceed 1: the store-only ceiling of this launch shape is reported beside it
+                         "store_only_ceiling": (lambda c: None if not c else {
+                             "gbs": c, "frac": achieved[dom] / c,
+                             "source": "profiles/store_ceiling.json (tools/store_pattern.cu: the render kernel's bulk-store "
+                                       "skeleton and tile hand-out without any drawing or state loads)"})(load_store_ceiling()),
                          "all_kernels": {names[i]: {"avg_launch_us": float(avg_us[i]), "achieved_gbs": achieved[i],
                                                     "frac": achieved[i] / peak, "algorithmic_bytes_per_launch": alg_bytes[i]}
                                          for i in names}},
