@@ -368,3 +368,46 @@ def test_ticketed_tiles_many_launches_two_batches_two_streams():
     torch.cuda.synchronize()
     for wb in batches:
         wb.close()
+
+
+def test_frames_follow_radius_changes():
+    """The render kernel reads the radii from the per-world render record (wall cache + radii), which is refreshed after
+    the balls changed: new radii through set_balls (whole batch, then a partial world range, with empty slots), and radii
+    written through the raw device pointer followed by requeue() -- every frame equals the restated pipeline's."""
+    import torch
+    from pyphy_engine_b200 import sampler
+    from pyphy_engine_b200.engine import WorldBatch
+    n, nb = 300, 8
+    W = sampler.sample_rect_worlds(n, nb, seed=11, **sampler.scaled64_params(nb))
+    wb = WorldBatch(n, nb, 4, dtype="f32", canvas=(64, 64))
+    wb.set_walls(W["wall"])
+    wb.set_styles([(1, GRAY, BLACK)] * nb, [(0, RED)] * 4, 3, 4)
+    rng = np.random.RandomState(5)
+
+    def check(rad):
+        dev = wb.render().cpu().numpy()
+        ref = oracle.render_frames(W["wall"], W["pos"], rad, (64, 64), s_thick=1, n_threads=8)
+        assert np.array_equal(dev, ref)
+
+    rad = np.full((n, nb), 3.0)
+    wb.set_balls(W["pos"], W["vel"], rad, W["mass"])
+    check(rad)
+    rad = rng.randint(3, 5, size=(n, nb)).astype(np.float64)          # radii 3 and 4 mixed
+    rad[rng.rand(n, nb) < 0.2] = -1.0                                  # empty slots
+    wb.set_balls(W["pos"], W["vel"], rad, W["mass"])
+    check(rad)
+    rad[100:150] = 4.0                                                 # a partial world range
+    wb.set_balls(W["pos"][100:150], W["vel"][100:150], rad[100:150], W["mass"][100:150], world0=100)
+    check(rad)
+    # radii written through the raw pointer take effect after requeue()
+    ptr, nbytes = wb.device_ptr(3)
+    assert nbytes == n * nb * 2 * 4
+    rad = np.where(rad > 0, 3.0, -1.0)                                 # every live ball back to radius 3
+    rm = np.stack([rad.astype(np.float32), W["mass"].astype(np.float32)], axis=-1)
+    class _Raw:   # zero-copy view of the library's {radius, mass} array (the use ppb_device_ptr documents)
+        __cuda_array_interface__ = {"shape": (n, nb, 2), "typestr": "<f4", "data": (ptr, False), "version": 2}
+    torch.as_tensor(_Raw(), device="cuda").copy_(torch.from_numpy(np.ascontiguousarray(rm)))
+    torch.cuda.synchronize()
+    wb.requeue()
+    check(rad)
+    wb.close()
