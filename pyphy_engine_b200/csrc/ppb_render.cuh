@@ -561,11 +561,11 @@ __global__ void __maxnreg__(120) render_tile_kernel(StatePtrs S, Layout L, Rende
     return j;
   };
   const size_t rec_stride = render_rec_stride(nWl, nB);
-  // One contiguous record per world (walls, radii) and its ball positions.  These few scattered reads are what keeps the
-  // launch from the rate of a store-only kernel (measured on B200, 131,072 frames: 298 us without them, 327 us with a
-  // single 16-byte read per frame, 337 - 345 us with all of them, whatever the warp count; fetching two worlds per read
-  // changed nothing): they are read with an evict-last L2 policy and the frames leave with an evict-first one, which is
-  // worth 8 us.
+  // One contiguous record per world (walls, radii) and its ball positions.  L2-missing reads that trickle in during the
+  // launch pull HBM out of its write stream (measured on B200, 131,072 frames, kernel without its paint loops: 298 us
+  // without these loads, 327 us with a single 16-byte read per frame, 337 - 345 us with all of them, whatever the warp
+  // count; two worlds per read, or one contiguous read per 12 worlds, changed nothing): they are read with an evict-last
+  // L2 policy and the frames leave with an evict-first one, which is worth 8 us.
   const uint64_t pol_keep = l2_policy_evict_last();
   auto load_world = [&](int wn) {
     const char *rec = reinterpret_cast<const char *>(S.wall_rc) + (size_t)wn * rec_stride;
