@@ -702,17 +702,30 @@ __global__ void __maxnreg__(120) render_tile_kernel(StatePtrs S, Layout L, Rende
       const int ch0 = r0 * RS4 + g0;
       if (h.x == PPB_WM_SOLID) {
         const uint32_t width = (uint32_t)(span.y - span.x);
-        for (int i = lane; i < items; i += 32) {
+        // two items per trip (i and i + 32: different groups of the tile, so the two read-modify-write chains are
+        // independent and their shared-memory latencies overlap -- this loop is latency-bound, one chain per warp)
+        for (int i = lane; i < items; i += 64) {
+          const int i2 = i + 32;
+          const bool has2 = i2 < items;
           const int r = (int)(((float)i + 0.5f) * inv_ncg);
-          const int c = i - r * ncg;
+          const int r2 = (int)(((float)i2 + 0.5f) * inv_ncg);
+          const int c = i - r * ncg, c2 = i2 - r2 * ncg;
           uint4 *p = tile4 + swz_ch<SWZ>(ch0 + r * RS4 + c);
+          uint4 *p2 = tile4 + swz_ch<SWZ>(ch0 + (has2 ? r2 * RS4 + c2 : 0));
           const uint32_t d = (uint32_t)(((g0 + c) << 2) - span.x);   // pixel k of the group is inside iff d + k < width
+          const uint32_t d2 = (uint32_t)(((g0 + c2) << 2) - span.x);
           uint4 v = *p;
+          uint4 v2 = has2 ? *p2 : make_uint4(0u, 0u, 0u, 0u);
           v.x = (d < width) ? col : v.x;
           v.y = (d + 1u < width) ? col : v.y;
           v.z = (d + 2u < width) ? col : v.z;
           v.w = (d + 3u < width) ? col : v.w;
+          v2.x = (d2 < width) ? col : v2.x;
+          v2.y = (d2 + 1u < width) ? col : v2.y;
+          v2.z = (d2 + 2u < width) ? col : v2.z;
+          v2.w = (d2 + 3u < width) ? col : v2.w;
           *p = v;
+          if (has2) *p2 = v2;
         }
       } else {
         const SWallGeom &g = sm.w[q];
