@@ -223,9 +223,10 @@ PPB_API int ppb_set_gravity(ppb_batch *b, double gx, double gy);
  *                (primitives.py:991-1008, dataio.py:119-120)                       */
 PPB_API int ppb_step_async(ppb_batch *b, int32_t n_steps, void *traj_dev, uint8_t *frames_dev,
                    int32_t render_every, void *stream);
-/* Scheduling note: when frames are requested, the render of step k runs on a stream owned by the
- * batch, concurrently with the integrate / collide kernels of step k+1 (it reads a snapshot of
- * the positions); `stream` waits for the last render before the call's work counts as complete,
+/* Scheduling note: when more than one frame is requested, one advance launch covers a chunk of up
+ * to 64 steps and leaves a position snapshot per drawn step; the chunk's render launches run on a
+ * stream owned by the batch and read those snapshots while the next chunk's advance launch may
+ * already start; `stream` waits for the last render before the call's work counts as complete,
  * so stream-ordered consumers of `frames_dev` need no extra synchronisation. */
 
 /* Drains the collision queue without stepping: Dynamics.time_to_collide_all (primitives.py:720-733)
@@ -323,9 +324,9 @@ PPB_API int ppb_collision_flags_async(const float *traj_dev, int64_t n_items, in
 PPB_API int ppb_read_events(ppb_batch *b, ppb_event *out, int64_t cap, int64_t *n_total, void *stream);
 PPB_API int ppb_clear_events(ppb_batch *b, void *stream);
 
-/* counters since creation: [0] kernels launched by this batch, [1] world-steps taken by the
- * collide kernel (all other world-steps went through the integrate kernel), [2] sub-step loop
- * iterations inside the collide kernel, [3] collision events, [4] world rescans (one rescan =
+/* counters since creation: [0] kernels launched by this batch, [1] world-steps that ran the
+ * event-driven loop of Dynamics.step (all other world-steps were event-free: move_object only),
+ * [2] sub-step loop iterations inside that loop, [3] collision events, [4] world rescans (one rescan =
  * time_to_collide_all for every ball of a world = n_balls x (4 n_walls + n_balls - 1) pair tests),
  * [5..7] reserved (0) */
 PPB_API int ppb_get_counters(ppb_batch *b, int64_t out[8], void *stream);

@@ -3,7 +3,7 @@
 ``get_toc_ball_wall(ball, wall)`` and ``get_toc_ball_ball(ball1, ball2, name1, name2)`` keep the
 reference's signatures and return conventions ``(tCol, nrmlCol, ptCol)`` -- ``(inf, None, None)``
 when the objects never meet (dynamics.py:8-63, 67-136).  The arithmetic is not done here: the
-pair is uploaded as a one-world batch and evaluated by the scan stage of the collide kernel
+pair is uploaded as a one-world batch and evaluated by the scan stage of the advance kernel
 (``ppb_scan_async``, csrc/ppb_kernels.cuh + ppb_math.cuh ``Compat``), i.e. by exactly the code
 that ``Dynamics.step`` uses, in the reference's fp64 operation order.
 
