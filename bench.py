@@ -433,6 +433,28 @@ def run_ours(args, rank, local_rank, world_size):
     f64_mode = variant("f64", MAX_SUBSTEPS, 5, 3) if rank == 0 else None
     default_guard = variant("f32", 1 << 20, args.steps, args.warmup) if rank == 0 else None
 
+    # ---- BASELINE.json configs[2]: 65,536 independent 4-ball worlds, random init, physics only, one GPU (rank 0;
+    #      the reference's own table: DataSaver / save_rect_arena distribution, arena 700, r = 25, dataio.py:435-446) ----
+    def physics_only(nw, nb, k_steps, w_steps):
+        pb = WorldBatch(nw, nb, 4, dtype="f32", device=local_rank, max_substeps=MAX_SUBSTEPS)
+        nf = pb.sample_rect_worlds(seed=3, arena=700, mn_wlen=300, mx_wlen=550)
+        pb.step_async(w_steps)
+        torch.cuda.synchronize(dev)
+        p0, p1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+        p0.record()
+        pb.step_async(k_steps)
+        p1.record()
+        torch.cuda.synchronize(dev)
+        pms = p0.elapsed_time(p1)
+        pst, _ = pb.get_status()
+        plive = int((pst == 0).sum())
+        pb.close()
+        return {"workload": "configs[2]: %d worlds x %d balls, physics only, fp32, DataSaver rect tables (arena 700, r = 25)" % (nw, nb),
+                "steps": k_steps, "warmup": w_steps, "ms_per_step": pms / k_steps, "sampler_failures": int(nf),
+                "ball_steps_per_sec_rank0": plive * nb * k_steps / (pms * 1e-3), "halted_worlds_rank0": nw - plive,
+                "max_substeps": MAX_SUBSTEPS}
+    physics_cfg2 = physics_only(65536, 4, 1000, 100) if rank == 0 else None
+
     if rank == 0:
         total_worlds = n_worlds * world_size
         ball_steps = live_total * N_BALLS * args.steps          # halted worlds do not count
@@ -494,6 +516,7 @@ def run_ours(args, rank, local_rank, world_size):
             "final_gather": gather_info,
             "f64_mode": f64_mode,
             "default_guard": default_guard,
+            "physics_only_configs2": physics_cfg2,
             "gpu_launches": int(launches_total),
             "clocks": {"sm_mhz": clk["sm_mhz"], "sm_max_mhz": clk["sm_max_mhz"], "reasons": clk["reasons"]},
         }
